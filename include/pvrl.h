@@ -1,0 +1,174 @@
+/* pvrl.h -- C ABI of libpvrl_sm100.so: the Blackwell (sm_100a) kernels behind the ProcedureVRL
+ * TimeSformer hot path.
+ *
+ * The reference has no FFI layer: every op below replaces a PyTorch-eager call site inside
+ * lib/models/vit.py / tools/train_net.py (cited per function, paths relative to the reference root).
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller
+ *     (the library allocates nothing persistent except a cache of TMA descriptors);
+ *   - every call only enqueues work on `stream` (a cudaStream_t passed as void*), never syncs;
+ *   - return value: 0 = ok, < 0 = argument / shape / arch error, > 0 = cudaError_t;
+ *     pvrl_last_error() returns a thread-local message for the last non-zero return;
+ *   - activations "act" are bf16 (act_dtype 0) or fp32 (act_dtype 1); the residual stream,
+ *     statistics, parameters' gradients and all reductions are fp32;
+ *   - token order inside a clip is (h w t) with t fastest, cls first: vit.py:131,142,406.
+ */
+#ifndef PVRL_H_
+#define PVRL_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PVRL_ABI_VERSION 1
+
+/* dtypes of activation buffers */
+#define PVRL_BF16 0
+#define PVRL_F32 1
+
+/* Row maps: how logical row m of an op addresses the [Bc, S = 1 + HW*T, D] residual stream. */
+#define PVRL_MAP_IDENT 0   /* row = m                                                              */
+#define PVRL_MAP_SKIPCLS 1 /* m over Bc*HW*T : row = m + m/(HW*T) + 1        (vit.py:130 x[:,1:])   */
+#define PVRL_MAP_SPATIAL 2 /* m=(b,t,n) over Bc*T*(HW+1): n>0 -> b*S+1+(n-1)*T+t, n==0 -> cls (vit.py:138-143) */
+#define PVRL_MAP_PATCH 3   /* m=(b,t,n) over Bc*T*HW : row = b*S+1+n*T+t      (vit.py:393-407)      */
+#define PVRL_MAP_CLS 4     /* m over Bc : row = m*S                            (vit.py:421)          */
+
+/* GEMM epilogues */
+#define PVRL_EPI_STORE 0  /* out[map(m)] = rowscale*(acc + bias)                     -> act dtype        */
+#define PVRL_EPI_GELU 1   /* out = acc + bias ; out2 = gelu_erf(out)                 -> act dtype (vit.py:54-60) */
+#define PVRL_EPI_DGELU 2  /* out = acc * gelu_erf'(aux[m])                           -> act dtype        */
+#define PVRL_EPI_RESID 3  /* out[map(m)] = resid[map(m)] + rowscale*(acc + bias) (+pos+time) -> fp32     */
+#define PVRL_EPI_ATOMIC 4 /* out[m] += acc  (fp32 red.add; split-K weight gradients)                     */
+
+typedef struct pvrl_geom {
+  int32_t T;  /* frames                     */
+  int32_t HW; /* patches per frame (196)    */
+} pvrl_geom_t;
+
+/* D[M,N] = A * B^T over a contraction of length K, bf16 operands, fp32 accumulate (tcgen05 + TMA).
+ *   trans == 0 ("NT"): A is [M,K] row-major (lda), B is [N,K] row-major (ldb)       -- nn.Linear forward / dX
+ *   trans == 1 ("TN"): A is [K,M] row-major (lda), B is [K,N] row-major (ldb)       -- dW = dY^T X
+ * Replaces cuBLAS addmm/mm behind nn.Linear (vit.py:47-60,72-90,118), nn.Conv2d patch embed (vit.py:172-179)
+ * and their autograd (SURVEY 2a K1,K4,K6,K8,K10,K15). */
+typedef struct pvrl_gemm {
+  int32_t M, N, K;
+  int32_t trans;
+  const void* A;
+  int64_t lda;
+  const void* B;
+  int64_t ldb;
+  int32_t epilogue;  /* PVRL_EPI_*                                        */
+  int32_t out_dtype; /* PVRL_BF16 / PVRL_F32 (STORE, GELU, DGELU only)    */
+  void* out;
+  int64_t ldo;
+  void* out2;        /* GELU: activations; RESID+MAP_SPATIAL: cls side buffer fp32 [Bc*T, N] */
+  const float* bias; /* [N] or NULL                                       */
+  const float* rowscale; /* DropPath factors mask/keep, indexed m / rs_div, or NULL (vit_utils.py:140-155) */
+  int32_t rs_div;
+  int32_t map;       /* PVRL_MAP_* applied to out / resid rows            */
+  const void* aux;   /* DGELU: pre-activations [M, ld_aux], act dtype = out_dtype */
+  int64_t ld_aux;
+  const float* resid;    /* RESID: fp32 residual, same row map / ldo as out */
+  const float* add_pos;  /* RESID+MAP_PATCH: pos_embed [(1+HW), N]  (vit.py:373-389) */
+  const float* add_time; /* RESID+MAP_PATCH: time_embed [T, N]      (vit.py:393-404) */
+  pvrl_geom_t g;
+  int32_t k_splits;  /* ATOMIC only: 0 = auto                             */
+} pvrl_gemm_t;
+
+int pvrl_gemm_bf16(const pvrl_gemm_t* d, void* stream);
+
+/* ---- elementwise / normalisation / layout ------------------------------------------------------ */
+
+/* frames fp32 [Bc,3,T,H,W] -> im2col rows (b,t,ph,pw) x K=(c,kh,kw), act dtype.  vit.py:176-179 */
+int pvrl_patchify(const float* frames, void* out, int32_t out_dtype, int32_t Bc, int32_t T, int32_t H, int32_t W,
+                  int32_t patch, void* stream);
+
+/* x[b,0,:] = cls_token + pos_embed[0]  (vit.py:371-389) */
+int pvrl_cls_init(float* x, const float* cls_token, const float* pos_embed, int32_t Bc, int32_t S, int32_t D,
+                  void* stream);
+
+/* y[m] = LN(x[src(m)]) * w + b, eps; stats[m] = (mean, rstd).  nn.LayerNorm(768, eps=1e-6): vit.py:102,108,115,225.
+ * MAP_SPATIAL reads cls rows from x_cls (block input) and token rows from x. */
+int pvrl_layernorm_fwd(const float* x, const float* x_cls, const float* w, const float* b, void* y, int32_t y_dtype,
+                       float* stats, int32_t M, int32_t D, float eps, int32_t map, pvrl_geom_t g, void* stream);
+
+/* dx[src(m)] += LN'(dy[m]); dw += sum dy*xhat; db += sum dy.  (autograd of the above) */
+int pvrl_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const float* x_cls, const float* w,
+                       const float* stats, float* dx, float* dw, float* db, int32_t M, int32_t D, int32_t map,
+                       pvrl_geom_t g, void* stream);
+
+/* out[m] = act( rowscale[m/rs_div] * clsf(m) * src[map(m)] ), fp32 -> act dtype.  clsf = 1/T on the cls rows of
+ * MAP_SPATIAL (backward of the mean over frames, vit.py:147-149), else 1. */
+int pvrl_gather_cast(const float* src, void* out, int32_t out_dtype, const float* rowscale, int32_t rs_div,
+                     int32_t M, int32_t D, int32_t map, pvrl_geom_t g, void* stream);
+
+/* x2[b,0,:] = x0[b,0,:] + mean_t side[b*T+t,:]   (vit.py:147-149,156) */
+int pvrl_cls_merge(const float* x0, const float* side, float* x2, int32_t Bc, int32_t T, int32_t S, int32_t D,
+                   void* stream);
+
+/* out[n] += sum_m a[m,n]   (bias gradients) */
+int pvrl_colsum(const void* a, int32_t a_dtype, int64_t lda, float* out, int32_t M, int32_t N, void* stream);
+
+/* fp32 [rows, cols] -> copy w_out [rows, cols] and transposed copy wT_out [cols, rows] in out_dtype
+ * (either output may be NULL): the bf16 operand copies of the fp32 master weights. */
+int pvrl_cast_weight(const float* w, void* w_out, void* wT_out, int32_t out_dtype, int32_t rows, int32_t cols,
+                     void* stream);
+
+/* Error-compensated operand split for the "bf16x3" parity mode: a = hi + lo with hi = bf16(a), lo = bf16(a - hi).
+ * pattern 0: out = [hi | hi | lo], pattern 1: out = [hi | lo | hi]; along = 1 concatenates along columns
+ * ([M, 3*K]), along = 0 along rows ([3*M, K]).  A GEMM over the 3x longer contraction then yields
+ * hi*hi + hi*lo + lo*hi (relative error ~2^-17 per product instead of 2^-9). */
+int pvrl_split3(const float* a, void* out, int32_t M, int32_t K, int32_t pattern, int32_t along, void* stream);
+
+/* embed gradients: dpos[0] = dcls = sum_b dx[b,0]; dpos[1+n] = sum_{b,t}; dtime[t] = sum_{b,n}  (vit.py:371-407) */
+int pvrl_embed_bwd(const float* dx, float* dcls, float* dpos, float* dtime, int32_t Bc, int32_t D, pvrl_geom_t g,
+                   void* stream);
+
+/* ---- attention (Attention.forward vit.py:84-88 and its autograd) -------------------------------------- */
+
+/* qkv [n_seq*seq, 3*H*64] (act dtype, column order [3][H][64], vit.py:78) -> out [n_seq*seq, H*64],
+ * lse fp32 [n_seq, H, seq] (log-sum-exp of the scaled scores).  Any seq; CUDA-core fp32 math. */
+int pvrl_attn_fwd(const void* qkv, void* out, float* lse, int32_t dtype, int32_t n_seq, int32_t seq, int32_t H,
+                  float scale, void* stream);
+int pvrl_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int32_t dtype,
+                  int32_t n_seq, int32_t seq, int32_t H, float scale, void* stream);
+
+/* ---- head + similarity + loss (vit.py:300-307, train_net.py:153-162) ----------------------------------- */
+
+/* y[m, j] = sum_k x[m,k] w[j,k] + b[j]   fp32, small M (head 768->512, vit.py:301) */
+int pvrl_linear_small_fwd(const float* x, const float* w, const float* b, float* y, int32_t M, int32_t K, int32_t N,
+                          void* stream);
+int pvrl_linear_small_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, int32_t M,
+                          int32_t K, int32_t N, void* stream);
+/* y = x / ||x||_2 (rows), norms saved.  vit.py:302 */
+int pvrl_l2norm_fwd(const float* x, float* y, float* norms, int32_t M, int32_t C, void* stream);
+int pvrl_l2norm_bwd(const float* y, const float* norms, const float* dy, float* dx, int32_t M, int32_t C,
+                    void* stream);
+/* logits[m, c] = emb[m,:] . label[c,:] * inv_temp   (vit.py:307; label rows pre-normalised, vit.py:435-440) */
+int pvrl_sim_logits_fwd(const float* emb, const float* label, float* logits, int32_t M, int32_t C, int32_t K,
+                        float inv_temp, void* stream);
+/* demb[m,:] += sum_c dlogits[m,c] label[c,:] * inv_temp */
+int pvrl_sim_logits_bwd(const float* dlogits, const float* label, float* demb, int32_t M, int32_t C, int32_t K,
+                        float inv_temp, void* stream);
+/* Pre-training loss, train_net.py:153-162: teacher = renorm(top-k(softmax(teacher_logits))),
+ * loss = KLDiv(log_softmax(pred), teacher, batchmean); dpred = (softmax(pred)*sum(t) - t) / M * gscale.
+ * row_loss fp32 [M] (sum to get the loss), teacher_out optional fp32 [M,K]. */
+int pvrl_kl_topk_loss(const float* pred, const float* teacher_logits, float* row_loss, float* dpred,
+                      float* teacher_out, int32_t M, int32_t K, int32_t topk, float gscale, void* stream);
+/* eval-mode softmax over rows (vit.py:355-356) */
+int pvrl_softmax_rows(const float* x, float* y, int32_t M, int32_t K, void* stream);
+
+/* ---- misc ----------------------------------------------------------------------------------------------- */
+const char* pvrl_last_error(void);
+int pvrl_abi_version(void);
+/* number of kernels this library has launched in this process (bench.py "gpu_launches") */
+int64_t pvrl_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVRL_H_ */

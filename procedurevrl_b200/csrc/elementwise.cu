@@ -1,0 +1,448 @@
+// HBM-bound kernels around the GEMMs: patch im2col, LayerNorm forward/backward (warp-shuffle, one warp
+// per 768-wide row), gather/cast of gradients through the (h w t) <-> (t)(h w) token permutes, bias-gradient
+// column sums, weight casts/transposes, the bf16x3 operand split and the embedding gradients.
+// All loads/stores are 128-bit and coalesced along the feature dimension.
+#include "pvrl_host.h"
+#include "pvrl_ptx.cuh"
+
+namespace pvrl {
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T>
+__device__ __forceinline__ void store4(T* dst, float a, float b, float c, float d);
+template <>
+__device__ __forceinline__ void store4<float>(float* dst, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(dst) = make_float4(a, b, c, d);
+}
+template <>
+__device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* dst, float a, float b, float c, float d) {
+  uint2 u;
+  u.x = pack_bf16x2(a, b);
+  u.y = pack_bf16x2(c, d);
+  *reinterpret_cast<uint2*>(dst) = u;
+}
+template <typename T>
+__device__ __forceinline__ float4 load4(const T* src);
+template <>
+__device__ __forceinline__ float4 load4<float>(const float* src) {
+  return __ldg(reinterpret_cast<const float4*>(src));
+}
+template <>
+__device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* src) {
+  uint2 u = __ldg(reinterpret_cast<const uint2*>(src));
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// ---------------------------------------------------------------------------------------- patchify
+// out row (b,t,ph,pw), column k = c*P*P + kh*P + kw  == Conv2d(k=s=P) as a GEMM (vit.py:172-179).
+template <typename OutT>
+__global__ void patchify_kernel(const float* __restrict__ frames, OutT* __restrict__ out, int Bc, int T, int H, int W,
+                                int P, long long total_vec) {
+  const int nW = W / P, nH = H / P, KP = 3 * P * P, vec_per_row = KP / 4, pv = P / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / vec_per_row;
+    const int kv = static_cast<int>(i - row * vec_per_row);
+    const int kwv = kv % pv, kh = (kv / pv) % P, c = kv / (pv * P);
+    const int pw = static_cast<int>(row % nW);
+    const int ph = static_cast<int>((row / nW) % nH);
+    const int t = static_cast<int>((row / (nW * nH)) % T);
+    const int b = static_cast<int>(row / ((long long)nW * nH * T));
+    const float* src = frames + (((long long)(b * 3 + c) * T + t) * H + (ph * P + kh)) * W + pw * P + kwv * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src));
+    store4<OutT>(out + row * KP + kv * 4, v.x, v.y, v.z, v.w);
+  }
+}
+
+__global__ void cls_init_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos,
+                                int S, int D) {
+  const int b = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) x[(long long)b * S * D + d] = cls[d] + pos[d];
+}
+
+// ---------------------------------------------------------------------------------------- LayerNorm
+constexpr int LN_MAX_VEC = 8;  // D <= 1024
+constexpr int LN_WARPS = 8;
+
+__device__ __forceinline__ const float* ln_src_row(const float* x, const float* x_cls, int map, int m, const Geom& g,
+                                                   int D) {
+  const long long r = map_row(map, m, g);
+  if (r >= 0) return x + r * D;
+  const long long bt = -r - 1;
+  return x_cls + (bt / g.T) * (long long)g.S * D;
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ x_cls, const float* __restrict__ w,
+                     const float* __restrict__ b, OutT* __restrict__ y, float* __restrict__ stats, int M, int D,
+                     float eps, int map, Geom g) {
+  const int lane = threadIdx.x & 31;
+  const int m = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const float* xp = ln_src_row(x, x_cls, map, m, g, D);
+  const int nvec = D >> 7;
+  float4 v[LN_MAX_VEC];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i)
+    if (i < nvec) {
+      v[i] = __ldg(reinterpret_cast<const float4*>(xp) + i * 32 + lane);
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  const float mean = warp_sum(s) / D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i)
+    if (i < nvec) {
+      const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += a * a + bb * bb + c * c + d * d;
+    }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / D + eps);
+  OutT* yp = y + (long long)m * D;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i)
+    if (i < nvec) {
+      const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + i * 32 + lane);
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(b) + i * 32 + lane);
+      store4<OutT>(yp + (i * 32 + lane) * 4, (v[i].x - mean) * rstd * ww.x + bv.x, (v[i].y - mean) * rstd * ww.y + bv.y,
+                   (v[i].z - mean) * rstd * ww.z + bv.z, (v[i].w - mean) * rstd * ww.w + bv.w);
+    }
+  if (lane == 0 && stats != nullptr) reinterpret_cast<float2*>(stats)[m] = make_float2(mean, rstd);
+}
+
+// dx[src(m)] += rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * w;  dw += dy * xhat;  db += dy.
+template <typename InT>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_bwd_kernel(const InT* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ x_cls,
+                     const float* __restrict__ w, const float* __restrict__ stats, float* __restrict__ dx,
+                     float* __restrict__ dw, float* __restrict__ db, int M, int D, int map, Geom g) {
+  extern __shared__ float sacc[];  // [2][D]
+  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = D >> 7;
+  float4 aw[LN_MAX_VEC], ab[LN_MAX_VEC], wv[LN_MAX_VEC];
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    aw[i] = make_float4(0.f, 0.f, 0.f, 0.f), ab[i] = aw[i];
+    if (i < nvec) wv[i] = __ldg(reinterpret_cast<const float4*>(w) + i * 32 + lane);
+  }
+  for (int m = blockIdx.x * LN_WARPS + warp; m < M; m += gridDim.x * LN_WARPS) {
+    const long long r = map_row(map, m, g);
+    const bool cls = r < 0;
+    const long long xr = cls ? ((-r - 1) / g.T) * (long long)g.S : r;
+    const float* xp = (cls ? x_cls : x) + xr * D;
+    const float2 st = reinterpret_cast<const float2*>(stats)[m];
+    float4 xh[LN_MAX_VEC], gg[LN_MAX_VEC];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i)
+      if (i < nvec) {
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(xp) + i * 32 + lane);
+        const float4 d = load4<InT>(dy + (long long)m * D + (i * 32 + lane) * 4);
+        xh[i] = make_float4((xv.x - st.x) * st.y, (xv.y - st.x) * st.y, (xv.z - st.x) * st.y, (xv.w - st.x) * st.y);
+        gg[i] = make_float4(d.x * wv[i].x, d.y * wv[i].y, d.z * wv[i].z, d.w * wv[i].w);
+        s1 += gg[i].x + gg[i].y + gg[i].z + gg[i].w;
+        s2 += gg[i].x * xh[i].x + gg[i].y * xh[i].y + gg[i].z * xh[i].z + gg[i].w * xh[i].w;
+        aw[i].x += d.x * xh[i].x, aw[i].y += d.y * xh[i].y, aw[i].z += d.z * xh[i].z, aw[i].w += d.w * xh[i].w;
+        ab[i].x += d.x, ab[i].y += d.y, ab[i].z += d.z, ab[i].w += d.w;
+      }
+    const float c1 = warp_sum(s1) / D, c2 = warp_sum(s2) / D;
+    float* dp = dx + xr * D;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i)
+      if (i < nvec) {
+        const float4 o = make_float4(st.y * (gg[i].x - c1 - xh[i].x * c2), st.y * (gg[i].y - c1 - xh[i].y * c2),
+                                     st.y * (gg[i].z - c1 - xh[i].z * c2), st.y * (gg[i].w - c1 - xh[i].w * c2));
+        float* p = dp + (i * 32 + lane) * 4;
+        if (cls) {  // T frames of one clip share the cls row (vit.py:138-140)
+          atomicAdd(p, o.x), atomicAdd(p + 1, o.y), atomicAdd(p + 2, o.z), atomicAdd(p + 3, o.w);
+        } else {
+          float4 cur = *reinterpret_cast<float4*>(p);
+          cur.x += o.x, cur.y += o.y, cur.z += o.z, cur.w += o.w;
+          *reinterpret_cast<float4*>(p) = cur;
+        }
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i)
+    if (i < nvec) {
+      const int c = (i * 32 + lane) * 4;
+      atomicAdd(&sacc[c], aw[i].x), atomicAdd(&sacc[c + 1], aw[i].y), atomicAdd(&sacc[c + 2], aw[i].z),
+          atomicAdd(&sacc[c + 3], aw[i].w);
+      atomicAdd(&sacc[D + c], ab[i].x), atomicAdd(&sacc[D + c + 1], ab[i].y), atomicAdd(&sacc[D + c + 2], ab[i].z),
+          atomicAdd(&sacc[D + c + 3], ab[i].w);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    if (dw != nullptr) atomicAdd(dw + i, sacc[i]);
+    if (db != nullptr) atomicAdd(db + i, sacc[D + i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------- gather + cast
+template <typename OutT>
+__global__ void gather_cast_kernel(const float* __restrict__ src, OutT* __restrict__ out,
+                                   const float* __restrict__ rowscale, int rs_div, int M, int D, int map, Geom g) {
+  const int vec_per_row = D >> 2;
+  const long long total = (long long)M * vec_per_row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int m = static_cast<int>(i / vec_per_row);
+    const int c = static_cast<int>(i - (long long)m * vec_per_row) * 4;
+    long long r = map_row(map, m, g);
+    float f = rowscale != nullptr ? __ldg(rowscale + m / rs_div) : 1.0f;
+    if (r < 0) {  // cls row of a spatial sequence: d(mean over T) = 1/T
+      r = ((-r - 1) / g.T) * (long long)g.S;
+      f *= 1.0f / g.T;
+    }
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + r * D + c));
+    store4<OutT>(out + (long long)m * D + c, v.x * f, v.y * f, v.z * f, v.w * f);
+  }
+}
+
+__global__ void cls_merge_kernel(const float* __restrict__ x0, const float* __restrict__ side, float* __restrict__ x2,
+                                 int T, int S, int D) {
+  const int b = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float s = 0.f;
+    for (int t = 0; t < T; ++t) s += side[((long long)b * T + t) * D + d];
+    x2[(long long)b * S * D + d] = x0[(long long)b * S * D + d] + s / T;
+  }
+}
+
+// ---------------------------------------------------------------------------------------- column sums
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ a, long long lda, float* __restrict__ out, int M, int N,
+                              int rows_per_block) {
+  __shared__ float red[8][128];
+  const int col = blockIdx.x * 128 + threadIdx.x * 4;  // blockDim = (32, 8)
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < N)
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      const float4 v = load4<T>(a + (long long)r * lda + col);
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
+  float* rr = &red[threadIdx.y][threadIdx.x * 4];
+  rr[0] = acc.x, rr[1] = acc.y, rr[2] = acc.z, rr[3] = acc.w;
+  __syncthreads();
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  if (tid < 128 && blockIdx.x * 128 + tid < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][tid];
+    atomicAdd(out + blockIdx.x * 128 + tid, s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------- weight cast
+template <typename OutT>
+__global__ void cast_weight_kernel(const float* __restrict__ w, OutT* __restrict__ o, OutT* __restrict__ oT, int rows,
+                                   int cols) {
+  __shared__ float tile[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int r = blockIdx.y * 32 + j;
+    float v = 0.f;
+    if (r < rows && c < cols) {
+      v = w[(long long)r * cols + c];
+      if (o != nullptr) o[(long long)r * cols + c] = static_cast<OutT>(v);
+    }
+    tile[j][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (oT != nullptr) {
+    const int r = blockIdx.y * 32 + threadIdx.x;  // original row -> fast index of the transposed output
+    for (int j = threadIdx.y; j < 32; j += 8) {
+      const int cc = blockIdx.x * 32 + j;
+      if (r < rows && cc < cols) oT[(long long)cc * rows + r] = static_cast<OutT>(tile[threadIdx.x][j]);
+    }
+  }
+}
+
+// a = hi + lo (+ O(2^-17 |a|)); the three K-concatenated segments pair up as hi*hi + hi*lo + lo*hi.
+__global__ void split3_kernel(const float* __restrict__ a, __nv_bfloat16* __restrict__ out, int M, int K, int pattern,
+                              int along) {
+  const long long total = (long long)M * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float v = a[i];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    const __nv_bfloat16 s1 = pattern == 0 ? hi : lo, s2 = pattern == 0 ? lo : hi;
+    if (along == 1) {
+      const long long m = i / K, k = i - m * K;
+      __nv_bfloat16* o = out + m * 3 * K + k;
+      o[0] = hi, o[K] = s1, o[2 * (long long)K] = s2;
+    } else {
+      out[i] = hi, out[total + i] = s1, out[2 * total + i] = s2;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------- embed gradients
+__global__ void embed_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dcls, float* __restrict__ dpos,
+                                 float* __restrict__ dtime, int Bc, int D, Geom g) {
+  const int n = blockIdx.x;  // 0..HW-1 : patch index; block HW handles the cls row
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    if (n == g.HW) {
+      float s = 0.f;
+      for (int b = 0; b < Bc; ++b) s += dx[(long long)b * g.S * D + d];
+      if (dcls != nullptr) dcls[d] += s;
+      if (dpos != nullptr) dpos[d] += s;
+      continue;
+    }
+    float pos = 0.f;
+    for (int t = 0; t < g.T; ++t) {
+      float s = 0.f;
+      for (int b = 0; b < Bc; ++b) s += dx[((long long)b * g.S + 1 + (long long)n * g.T + t) * D + d];
+      pos += s;
+      if (dtime != nullptr) atomicAdd(dtime + (long long)t * D + d, s);
+    }
+    if (dpos != nullptr) dpos[(long long)(1 + n) * D + d] += pos;
+  }
+}
+
+inline int grid_for(long long work, int block, int cap_per_sm = 16) {
+  long long g = (work + block - 1) / block;
+  const long long cap = 148LL * cap_per_sm;
+  return static_cast<int>(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace
+}  // namespace pvrl
+
+using namespace pvrl;
+#define STREAM static_cast<cudaStream_t>(stream)
+
+extern "C" int pvrl_patchify(const float* frames, void* out, int32_t out_dtype, int32_t Bc, int32_t T, int32_t H,
+                             int32_t W, int32_t patch, void* stream) {
+  PVRL_CHECK_ARG(frames && out && Bc > 0 && T > 0, "pvrl_patchify: bad arguments");
+  PVRL_CHECK_ARG(patch % 4 == 0 && H % patch == 0 && W % patch == 0, "pvrl_patchify: H=%d W=%d patch=%d", H, W, patch);
+  const long long total_vec = (long long)Bc * T * (H / patch) * (W / patch) * 3 * patch * patch / 4;
+  const int grid = grid_for(total_vec, 256);
+  if (out_dtype == PVRL_F32)
+    patchify_kernel<float><<<grid, 256, 0, STREAM>>>(frames, static_cast<float*>(out), Bc, T, H, W, patch, total_vec);
+  else
+    patchify_kernel<__nv_bfloat16>
+        <<<grid, 256, 0, STREAM>>>(frames, static_cast<__nv_bfloat16*>(out), Bc, T, H, W, patch, total_vec);
+  return launched("patchify_kernel");
+}
+
+extern "C" int pvrl_cls_init(float* x, const float* cls_token, const float* pos_embed, int32_t Bc, int32_t S,
+                             int32_t D, void* stream) {
+  PVRL_CHECK_ARG(x && cls_token && pos_embed && Bc > 0, "pvrl_cls_init: bad arguments");
+  cls_init_kernel<<<Bc, 256, 0, STREAM>>>(x, cls_token, pos_embed, S, D);
+  return launched("cls_init_kernel");
+}
+
+extern "C" int pvrl_layernorm_fwd(const float* x, const float* x_cls, const float* w, const float* b, void* y,
+                                  int32_t y_dtype, float* stats, int32_t M, int32_t D, float eps, int32_t map,
+                                  pvrl_geom_t g, void* stream) {
+  PVRL_CHECK_ARG(x && w && b && y && M > 0, "pvrl_layernorm_fwd: bad arguments");
+  PVRL_CHECK_ARG(D % 128 == 0 && D <= 128 * LN_MAX_VEC, "pvrl_layernorm_fwd: D=%d must be a multiple of 128, <= 1024", D);
+  PVRL_CHECK_ARG(map != PVRL_MAP_SPATIAL || x_cls != nullptr, "pvrl_layernorm_fwd: MAP_SPATIAL needs x_cls");
+  const Geom gg(g.T > 0 ? g.T : 1, g.HW > 0 ? g.HW : 1);
+  const int grid = (M + LN_WARPS - 1) / LN_WARPS;
+  if (y_dtype == PVRL_F32)
+    layernorm_fwd_kernel<float>
+        <<<grid, LN_WARPS * 32, 0, STREAM>>>(x, x_cls, w, b, static_cast<float*>(y), stats, M, D, eps, map, gg);
+  else
+    layernorm_fwd_kernel<__nv_bfloat16><<<grid, LN_WARPS * 32, 0, STREAM>>>(
+        x, x_cls, w, b, static_cast<__nv_bfloat16*>(y), stats, M, D, eps, map, gg);
+  return launched("layernorm_fwd_kernel");
+}
+
+extern "C" int pvrl_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const float* x_cls, const float* w,
+                                  const float* stats, float* dx, float* dw, float* db, int32_t M, int32_t D,
+                                  int32_t map, pvrl_geom_t g, void* stream) {
+  PVRL_CHECK_ARG(dy && x && w && stats && dx && M > 0, "pvrl_layernorm_bwd: bad arguments");
+  PVRL_CHECK_ARG(D % 128 == 0 && D <= 128 * LN_MAX_VEC, "pvrl_layernorm_bwd: D=%d must be a multiple of 128, <= 1024", D);
+  PVRL_CHECK_ARG(map != PVRL_MAP_SPATIAL || x_cls != nullptr, "pvrl_layernorm_bwd: MAP_SPATIAL needs x_cls");
+  const Geom gg(g.T > 0 ? g.T : 1, g.HW > 0 ? g.HW : 1);
+  int grid = (M + LN_WARPS - 1) / LN_WARPS;
+  if (grid > 148 * 4) grid = 148 * 4;
+  const size_t smem = 2 * D * sizeof(float);
+  if (dy_dtype == PVRL_F32)
+    layernorm_bwd_kernel<float><<<grid, LN_WARPS * 32, smem, STREAM>>>(static_cast<const float*>(dy), x, x_cls, w,
+                                                                        stats, dx, dw, db, M, D, map, gg);
+  else
+    layernorm_bwd_kernel<__nv_bfloat16><<<grid, LN_WARPS * 32, smem, STREAM>>>(
+        static_cast<const __nv_bfloat16*>(dy), x, x_cls, w, stats, dx, dw, db, M, D, map, gg);
+  return launched("layernorm_bwd_kernel");
+}
+
+extern "C" int pvrl_gather_cast(const float* src, void* out, int32_t out_dtype, const float* rowscale, int32_t rs_div,
+                                int32_t M, int32_t D, int32_t map, pvrl_geom_t g, void* stream) {
+  PVRL_CHECK_ARG(src && out && M > 0 && D % 4 == 0, "pvrl_gather_cast: bad arguments");
+  PVRL_CHECK_ARG(rowscale == nullptr || rs_div > 0, "pvrl_gather_cast: rowscale needs rs_div > 0");
+  const Geom gg(g.T > 0 ? g.T : 1, g.HW > 0 ? g.HW : 1);
+  const int grid = grid_for((long long)M * (D / 4), 256);
+  if (out_dtype == PVRL_F32)
+    gather_cast_kernel<float>
+        <<<grid, 256, 0, STREAM>>>(src, static_cast<float*>(out), rowscale, rs_div > 0 ? rs_div : 1, M, D, map, gg);
+  else
+    gather_cast_kernel<__nv_bfloat16><<<grid, 256, 0, STREAM>>>(src, static_cast<__nv_bfloat16*>(out), rowscale,
+                                                                 rs_div > 0 ? rs_div : 1, M, D, map, gg);
+  return launched("gather_cast_kernel");
+}
+
+extern "C" int pvrl_cls_merge(const float* x0, const float* side, float* x2, int32_t Bc, int32_t T, int32_t S,
+                              int32_t D, void* stream) {
+  PVRL_CHECK_ARG(x0 && side && x2 && Bc > 0 && T > 0, "pvrl_cls_merge: bad arguments");
+  cls_merge_kernel<<<Bc, 256, 0, STREAM>>>(x0, side, x2, T, S, D);
+  return launched("cls_merge_kernel");
+}
+
+extern "C" int pvrl_colsum(const void* a, int32_t a_dtype, int64_t lda, float* out, int32_t M, int32_t N,
+                           void* stream) {
+  PVRL_CHECK_ARG(a && out && M > 0 && N > 0 && N % 4 == 0, "pvrl_colsum: bad arguments");
+  const int rows_per_block = 256;
+  dim3 grid((N + 127) / 128, (M + rows_per_block - 1) / rows_per_block), block(32, 8);
+  if (a_dtype == PVRL_F32)
+    colsum_kernel<float><<<grid, block, 0, STREAM>>>(static_cast<const float*>(a), lda, out, M, N, rows_per_block);
+  else
+    colsum_kernel<__nv_bfloat16>
+        <<<grid, block, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(a), lda, out, M, N, rows_per_block);
+  return launched("colsum_kernel");
+}
+
+extern "C" int pvrl_cast_weight(const float* w, void* w_out, void* wT_out, int32_t out_dtype, int32_t rows,
+                                int32_t cols, void* stream) {
+  PVRL_CHECK_ARG(w && (w_out || wT_out) && rows > 0 && cols > 0, "pvrl_cast_weight: bad arguments");
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  if (out_dtype == PVRL_F32)
+    cast_weight_kernel<float>
+        <<<grid, block, 0, STREAM>>>(w, static_cast<float*>(w_out), static_cast<float*>(wT_out), rows, cols);
+  else
+    cast_weight_kernel<__nv_bfloat16><<<grid, block, 0, STREAM>>>(w, static_cast<__nv_bfloat16*>(w_out),
+                                                                   static_cast<__nv_bfloat16*>(wT_out), rows, cols);
+  return launched("cast_weight_kernel");
+}
+
+extern "C" int pvrl_split3(const float* a, void* out, int32_t M, int32_t K, int32_t pattern, int32_t along,
+                           void* stream) {
+  PVRL_CHECK_ARG(a && out && M > 0 && K > 0, "pvrl_split3: bad arguments");
+  PVRL_CHECK_ARG((pattern == 0 || pattern == 1) && (along == 0 || along == 1), "pvrl_split3: bad pattern/along");
+  const int grid = grid_for((long long)M * K, 256);
+  split3_kernel<<<grid, 256, 0, STREAM>>>(a, static_cast<__nv_bfloat16*>(out), M, K, pattern, along);
+  return launched("split3_kernel");
+}
+
+extern "C" int pvrl_embed_bwd(const float* dx, float* dcls, float* dpos, float* dtime, int32_t Bc, int32_t D,
+                              pvrl_geom_t g, void* stream) {
+  PVRL_CHECK_ARG(dx && Bc > 0 && D > 0 && g.T > 0 && g.HW > 0, "pvrl_embed_bwd: bad arguments");
+  const Geom gg(g.T, g.HW);
+  embed_bwd_kernel<<<g.HW + 1, 256, 0, STREAM>>>(dx, dcls, dpos, dtime, Bc, D, gg);
+  return launched("embed_bwd_kernel");
+}

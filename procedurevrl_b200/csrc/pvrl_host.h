@@ -1,0 +1,74 @@
+// Host-side helpers shared by the .cu translation units: error reporting and launch accounting.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/pvrl.h"
+
+namespace pvrl {
+
+char* last_error_buf();              // thread-local, 512 bytes
+std::atomic<int64_t>& launch_counter();
+
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(last_error_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+// Call after every kernel launch: counts it and converts a launch error into a return code.
+inline int launched(const char* what) {
+  launch_counter().fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(static_cast<int>(e), "%s: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+#define PVRL_CHECK_ARG(cond, ...) \
+  do {                            \
+    if (!(cond)) return ::pvrl::fail(-1, __VA_ARGS__); \
+  } while (0)
+
+#define PVRL_CUDA(expr)                                                                         \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess) return ::pvrl::fail(static_cast<int>(e__), "%s: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+struct Geom {
+  int T, HW, L, S;
+  __host__ __device__ Geom() : T(1), HW(1), L(1), S(2) {}
+  __host__ __device__ Geom(int t, int hw) : T(t), HW(hw), L(t * hw), S(1 + t * hw) {}
+};
+
+// Row maps of include/pvrl.h.  Returns the residual-stream row of logical row m; for the cls rows of
+// MAP_SPATIAL returns -(bt + 1) (the caller decides what a cls row means for it).
+__host__ __device__ inline long long map_row(int map, int m, const Geom& g) {
+  switch (map) {
+    case PVRL_MAP_SKIPCLS:
+      return (long long)m + m / g.L + 1;
+    case PVRL_MAP_SPATIAL: {
+      int bt = m / (g.HW + 1), n = m - bt * (g.HW + 1);
+      if (n == 0) return -(long long)(bt + 1);
+      int b = bt / g.T, t = bt - b * g.T;
+      return (long long)b * g.S + 1 + (long long)(n - 1) * g.T + t;
+    }
+    case PVRL_MAP_PATCH: {
+      int bt = m / g.HW, n = m - bt * g.HW;
+      int b = bt / g.T, t = bt - b * g.T;
+      return (long long)b * g.S + 1 + (long long)n * g.T + t;
+    }
+    case PVRL_MAP_CLS:
+      return (long long)m * g.S;
+    default:
+      return m;
+  }
+}
+
+}  // namespace pvrl

@@ -1,0 +1,266 @@
+"""ctypes binding of libpvrl_sm100.so (include/pvrl.h): the only way the host code reaches the GPU math.
+
+There is no fallback: if the shared library is missing or a call returns non-zero this raises.  Every
+function takes torch CUDA tensors purely as (pointer, shape) carriers and enqueues on torch's current
+stream; nothing here computes."""
+import ctypes
+import os
+
+import torch
+
+from . import build as _build
+
+BF16, F32 = 0, 1
+MAP_IDENT, MAP_SKIPCLS, MAP_SPATIAL, MAP_PATCH, MAP_CLS = 0, 1, 2, 3, 4
+EPI_STORE, EPI_GELU, EPI_DGELU, EPI_RESID, EPI_ATOMIC = 0, 1, 2, 3, 4
+
+_c_void_p, _c_int, _c_i64, _c_float = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+
+
+class Geom(ctypes.Structure):
+    _fields_ = [("T", _c_int), ("HW", _c_int)]
+
+
+class GemmDesc(ctypes.Structure):
+    _fields_ = [
+        ("M", _c_int), ("N", _c_int), ("K", _c_int), ("trans", _c_int),
+        ("A", _c_void_p), ("lda", _c_i64), ("B", _c_void_p), ("ldb", _c_i64),
+        ("epilogue", _c_int), ("out_dtype", _c_int),
+        ("out", _c_void_p), ("ldo", _c_i64), ("out2", _c_void_p),
+        ("bias", _c_void_p), ("rowscale", _c_void_p), ("rs_div", _c_int), ("map", _c_int),
+        ("aux", _c_void_p), ("ld_aux", _c_i64),
+        ("resid", _c_void_p), ("add_pos", _c_void_p), ("add_time", _c_void_p),
+        ("g", Geom), ("k_splits", _c_int),
+    ]
+
+
+_SIGS = {
+    "pvrl_gemm_bf16": [ctypes.POINTER(GemmDesc), _c_void_p],
+    "pvrl_patchify": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
+    "pvrl_cls_init": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
+    "pvrl_layernorm_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int,
+                           _c_float, _c_int, Geom, _c_void_p],
+    "pvrl_layernorm_bwd": [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                           _c_void_p, _c_int, _c_int, _c_int, Geom, _c_void_p],
+    "pvrl_gather_cast": [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int, Geom, _c_void_p],
+    "pvrl_cls_merge": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],
+    "pvrl_colsum": [_c_void_p, _c_int, _c_i64, _c_void_p, _c_int, _c_int, _c_void_p],
+    "pvrl_cast_weight": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
+    "pvrl_split3": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],
+    "pvrl_embed_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, Geom, _c_void_p],
+    "pvrl_attn_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p],
+    "pvrl_attn_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float,
+                      _c_void_p],
+    "pvrl_linear_small_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
+    "pvrl_linear_small_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int,
+                              _c_void_p],
+    "pvrl_l2norm_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p],
+    "pvrl_l2norm_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p],
+    "pvrl_sim_logits_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_void_p],
+    "pvrl_sim_logits_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_void_p],
+    "pvrl_kl_topk_loss": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float,
+                          _c_void_p],
+    "pvrl_softmax_rows": [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p],
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library.  Fails loudly when it has not been built (python -m procedurevrl_b200.build)."""
+    global _lib
+    if _lib is None:
+        path = _build.LIB_PATH
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: run `python -m procedurevrl_b200.build` (there is no fallback path)")
+        L = ctypes.CDLL(path)
+        for name, args in _SIGS.items():
+            fn = getattr(L, name)
+            fn.argtypes, fn.restype = args, ctypes.c_int
+        L.pvrl_last_error.restype = ctypes.c_char_p
+        L.pvrl_abi_version.restype = ctypes.c_int
+        L.pvrl_launch_count.restype = ctypes.c_int64
+        if L.pvrl_abi_version() != 1:
+            raise RuntimeError("libpvrl_sm100.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    return list(_SIGS) + ["pvrl_last_error", "pvrl_abi_version", "pvrl_launch_count"]
+
+
+def launch_count():
+    return int(lib().pvrl_launch_count())
+
+
+def _check(rc, name):
+    if rc != 0:
+        raise RuntimeError(f"{name} failed (rc={rc}): {lib().pvrl_last_error().decode()}")
+
+
+def _p(t):
+    if t is None:
+        return None
+    assert t.is_cuda, "pvrl ops take CUDA tensors only (no CPU fallback)"
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dt(t):
+    if t.dtype == torch.bfloat16:
+        return BF16
+    assert t.dtype == torch.float32, t.dtype
+    return F32
+
+
+def _geom(T=1, HW=1):
+    return Geom(int(T), int(HW))
+
+
+# ---------------------------------------------------------------------------------------------- GEMM
+def gemm(A, B, out, *, M, N, K, trans=0, epilogue=EPI_STORE, out2=None, bias=None, rowscale=None, rs_div=0,
+         map=MAP_IDENT, aux=None, resid=None, add_pos=None, add_time=None, T=1, HW=1, k_splits=0,
+         lda=None, ldb=None, ldo=None):
+    """out = epilogue(A @ B^T) -- see pvrl_gemm_t in include/pvrl.h.  A, B bf16; contiguous 2-D tensors."""
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
+    d = GemmDesc()
+    d.M, d.N, d.K, d.trans = M, N, K, trans
+    d.A, d.lda = _p(A), lda if lda is not None else A.stride(0)
+    d.B, d.ldb = _p(B), ldb if ldb is not None else B.stride(0)
+    d.epilogue = epilogue
+    d.out_dtype = F32 if epilogue in (EPI_RESID, EPI_ATOMIC) else _dt(out)
+    d.out, d.ldo = _p(out), ldo if ldo is not None else out.stride(-2)
+    d.out2 = _p(out2)
+    d.bias, d.rowscale, d.rs_div, d.map = _p(bias), _p(rowscale), rs_div, map
+    d.aux, d.ld_aux = _p(aux), (aux.stride(0) if aux is not None else 0)
+    d.resid, d.add_pos, d.add_time = _p(resid), _p(add_pos), _p(add_time)
+    d.g = _geom(T, HW)
+    d.k_splits = k_splits
+    _check(lib().pvrl_gemm_bf16(ctypes.byref(d), _stream()), "pvrl_gemm_bf16")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- elementwise
+def patchify(frames, out, patch=16):
+    Bc, C, T, H, W = frames.shape
+    assert C == 3 and frames.dtype == torch.float32 and frames.is_contiguous()
+    _check(lib().pvrl_patchify(_p(frames), _p(out), _dt(out), Bc, T, H, W, patch, _stream()), "pvrl_patchify")
+    return out
+
+
+def cls_init(x, cls_token, pos_embed):
+    Bc, S, D = x.shape
+    _check(lib().pvrl_cls_init(_p(x), _p(cls_token), _p(pos_embed), Bc, S, D, _stream()), "pvrl_cls_init")
+
+
+def layernorm_fwd(x, w, b, y, stats, M, D, eps, map=MAP_IDENT, x_cls=None, T=1, HW=1):
+    _check(lib().pvrl_layernorm_fwd(_p(x), _p(x_cls), _p(w), _p(b), _p(y), _dt(y), _p(stats), M, D, eps, map,
+                                    _geom(T, HW), _stream()), "pvrl_layernorm_fwd")
+    return y
+
+
+def layernorm_bwd(dy, x, w, stats, dx, dw, db, M, D, map=MAP_IDENT, x_cls=None, T=1, HW=1):
+    _check(lib().pvrl_layernorm_bwd(_p(dy), _dt(dy), _p(x), _p(x_cls), _p(w), _p(stats), _p(dx), _p(dw), _p(db), M, D,
+                                    map, _geom(T, HW), _stream()), "pvrl_layernorm_bwd")
+
+
+def gather_cast(src, out, M, D, map=MAP_IDENT, rowscale=None, rs_div=0, T=1, HW=1):
+    _check(lib().pvrl_gather_cast(_p(src), _p(out), _dt(out), _p(rowscale), rs_div, M, D, map, _geom(T, HW), _stream()),
+           "pvrl_gather_cast")
+    return out
+
+
+def cls_merge(x0, side, x2, Bc, T, S, D):
+    _check(lib().pvrl_cls_merge(_p(x0), _p(side), _p(x2), Bc, T, S, D, _stream()), "pvrl_cls_merge")
+
+
+def colsum(a, out, M, N):
+    _check(lib().pvrl_colsum(_p(a), _dt(a), a.stride(0), _p(out), M, N, _stream()), "pvrl_colsum")
+
+
+def cast_weight(w, w_out, wT_out):
+    rows, cols = w.shape
+    ref = w_out if w_out is not None else wT_out
+    _check(lib().pvrl_cast_weight(_p(w), _p(w_out), _p(wT_out), _dt(ref), rows, cols, _stream()), "pvrl_cast_weight")
+
+
+def split3(a, out, M, K, pattern, along):
+    assert a.dtype == torch.float32 and out.dtype == torch.bfloat16
+    _check(lib().pvrl_split3(_p(a), _p(out), M, K, pattern, along, _stream()), "pvrl_split3")
+    return out
+
+
+def embed_bwd(dx, dcls, dpos, dtime, Bc, D, T, HW):
+    _check(lib().pvrl_embed_bwd(_p(dx), _p(dcls), _p(dpos), _p(dtime), Bc, D, _geom(T, HW), _stream()),
+           "pvrl_embed_bwd")
+
+
+# ---------------------------------------------------------------------------------------------- attention
+def attn_fwd(qkv, out, lse, n_seq, seq, H, scale):
+    _check(lib().pvrl_attn_fwd(_p(qkv), _p(out), _p(lse), _dt(qkv), n_seq, seq, H, scale, _stream()), "pvrl_attn_fwd")
+    return out
+
+
+def attn_bwd(qkv, out, dout, lse, dqkv, n_seq, seq, H, scale):
+    _check(lib().pvrl_attn_bwd(_p(qkv), _p(out), _p(dout), _p(lse), _p(dqkv), _dt(qkv), n_seq, seq, H, scale,
+                               _stream()), "pvrl_attn_bwd")
+    return dqkv
+
+
+# ---------------------------------------------------------------------------------------------- head / loss
+def linear_small_fwd(x, w, b, y):
+    M, K = x.shape
+    N = w.shape[0]
+    _check(lib().pvrl_linear_small_fwd(_p(x), _p(w), _p(b), _p(y), M, K, N, _stream()), "pvrl_linear_small_fwd")
+    return y
+
+
+def linear_small_bwd(x, w, dy, dx, dw, db):
+    M, K = x.shape
+    N = w.shape[0]
+    _check(lib().pvrl_linear_small_bwd(_p(x), _p(w), _p(dy), _p(dx), _p(dw), _p(db), M, K, N, _stream()),
+           "pvrl_linear_small_bwd")
+
+
+def l2norm_fwd(x, y, norms):
+    M, C = x.shape
+    _check(lib().pvrl_l2norm_fwd(_p(x), _p(y), _p(norms), M, C, _stream()), "pvrl_l2norm_fwd")
+    return y
+
+
+def l2norm_bwd(y, norms, dy, dx):
+    M, C = y.shape
+    _check(lib().pvrl_l2norm_bwd(_p(y), _p(norms), _p(dy), _p(dx), M, C, _stream()), "pvrl_l2norm_bwd")
+    return dx
+
+
+def sim_logits_fwd(emb, label, logits, inv_temp):
+    M, K = emb.shape
+    C = label.shape[0]
+    _check(lib().pvrl_sim_logits_fwd(_p(emb), _p(label), _p(logits), M, C, K, inv_temp, _stream()),
+           "pvrl_sim_logits_fwd")
+    return logits
+
+
+def sim_logits_bwd(dlogits, label, demb, inv_temp):
+    M, C = dlogits.shape
+    K = label.shape[1]
+    _check(lib().pvrl_sim_logits_bwd(_p(dlogits), _p(label), _p(demb), M, C, K, inv_temp, _stream()),
+           "pvrl_sim_logits_bwd")
+    return demb
+
+
+def kl_topk_loss(pred, teacher_logits, row_loss, dpred, teacher_out, topk, gscale=1.0):
+    M, K = pred.shape
+    _check(lib().pvrl_kl_topk_loss(_p(pred), _p(teacher_logits), _p(row_loss), _p(dpred), _p(teacher_out), M, K, topk,
+                                   gscale, _stream()), "pvrl_kl_topk_loss")
+
+
+def softmax_rows(x, y):
+    M, K = x.shape
+    _check(lib().pvrl_softmax_rows(_p(x), _p(y), M, K, _stream()), "pvrl_softmax_rows")
+    return y
