@@ -143,7 +143,7 @@ class EncoderEngine:
         """frames fp32 [Bc, 3, T, H, W] -> (cls feature fp32 [Bc, D], saved state or None).
         drop_scales: optional list (len depth) of dicts {'temporal': [Bc*HW], 'spatial': [Bc*T], 'mlp': [Bc]}
         of DropPath factors mask/keep (vit_utils.py:140-155); None entries = identity."""
-        assert frames.is_cuda and frames.dtype == torch.float32
+        assert frames.dtype == torch.float32          # ops._p rejects non-CUDA tensors: there is no CPU path
         frames = frames.contiguous()
         Bc, C, T, Hh, Ww = frames.shape
         D, P = self.D, self.patch
@@ -336,8 +336,7 @@ class EncoderFunction(torch.autograd.Function):
     """autograd boundary: forward_features as one node whose backward is EncoderEngine.backward."""
 
     @staticmethod
-    def forward(ctx, engine, frames, drop_scales, *params):
-        need = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    def forward(ctx, engine, frames, drop_scales, need, *params):
         feat, saved = engine.forward(frames, drop_scales, save=need)
         ctx.engine, ctx.saved = engine, saved
         return feat
@@ -349,10 +348,11 @@ class EncoderFunction(torch.autograd.Function):
             raise RuntimeError("EncoderFunction.backward called without saved activations")
         G = eng.backward(ctx.saved, dfeat)
         ctx.saved = None
-        return (None, None, None) + tuple(G[n] for n in eng.grad_names)
+        return (None, None, None, None) + tuple(G[n] for n in eng.grad_names)
 
 
 def encode(engine, frames, drop_scales=None):
     """cls feature [Bc, D] with autograd through the engine's parameters."""
     params = [engine.p[n] for n in engine.grad_names]
-    return EncoderFunction.apply(engine, frames, drop_scales, *params)
+    need = torch.is_grad_enabled() and any(p.requires_grad for p in params)   # Function.forward runs under no_grad
+    return EncoderFunction.apply(engine, frames, drop_scales, need, *params)

@@ -1,0 +1,49 @@
+"""Model registry / DDP boundary (reference lib/models/build.py:8-54).
+
+`MODEL_REGISTRY.get(cfg.MODEL.MODEL_NAME)(cfg)` builds the module, `build_model` moves it to the current CUDA
+device and, for NUM_GPUS > 1, wraps it in DistributedDataParallel: one process per GPU, a single bucketed NCCL
+gradient all-reduce over NVLink/NVSwitch overlapped with backward -- the only collective on
+the path.  Unlike the reference (`find_unused_parameters=True`, build.py:49-53) no per-step graph walk is
+needed: the encoder is one autograd node that always produces every parameter gradient."""
+import torch
+
+
+class Registry:
+    """The two calls of fvcore.common.registry.Registry the reference uses: register() and get()."""
+
+    def __init__(self, name):
+        self._name, self._map = name, {}
+
+    def register(self, obj=None):
+        def deco(o):
+            self._map[o.__name__] = o
+            return o
+        return deco if obj is None else deco(obj)
+
+    def get(self, name):
+        if name not in self._map:
+            raise KeyError(f"No object named '{name}' found in '{self._name}' registry!")
+        return self._map[name]
+
+    def __contains__(self, name):
+        return name in self._map
+
+
+MODEL_REGISTRY = Registry("MODEL")
+
+
+def build_model(cfg, gpu_id=None):
+    """build.py:17-54: construct cfg.MODEL.MODEL_NAME, move to GPU, wrap in DDP when NUM_GPUS > 1."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("build_model: the sm_100a implementation needs a CUDA device (there is no CPU fallback)")
+    assert cfg.NUM_GPUS <= torch.cuda.device_count(), "Cannot use more GPU devices than available"
+    name = cfg.MODEL.MODEL_NAME
+    model = MODEL_REGISTRY.get(name)(cfg)
+    cur_device = torch.cuda.current_device() if gpu_id is None else gpu_id
+    model = model.cuda(device=cur_device)
+    if cfg.NUM_GPUS > 1 and torch.distributed.is_available() and torch.distributed.is_initialized():
+        bucket_mb = cfg.B200.GRAD_BUCKET_MB if "B200" in cfg else 64
+        model = torch.nn.parallel.DistributedDataParallel(
+            module=model, device_ids=[cur_device], output_device=cur_device, find_unused_parameters=False,
+            gradient_as_bucket_view=True, bucket_cap_mb=bucket_mb, broadcast_buffers=False)
+    return model

@@ -1,0 +1,304 @@
+"""TEST INFRASTRUCTURE: plain-torch restatement of every function of `procedurevrl_b200.ops` with the same
+signatures and the same rounding points (bf16 operands / outputs where the CUDA kernels round).
+
+Two uses: (1) CPU tests monkeypatch `procedurevrl_b200.ops` with these to check the *host logic* -- the
+engine's forward/backward schedule, row maps, gradient routing -- against the oracle without a GPU;
+(2) they document the contract each CUDA kernel is unit-tested against in tests/test_ops_gpu.py.
+Never imported by the product package."""
+import math
+
+import torch
+import torch.nn.functional as F
+
+BF16, F32 = 0, 1
+MAP_IDENT, MAP_SKIPCLS, MAP_SPATIAL, MAP_PATCH, MAP_CLS = 0, 1, 2, 3, 4
+EPI_STORE, EPI_GELU, EPI_DGELU, EPI_RESID, EPI_ATOMIC = 0, 1, 2, 3, 4
+
+_launches = [0]
+
+
+def launch_count():
+    return _launches[0]
+
+
+def lib():
+    return None
+
+
+def _rows(map, M, T, HW, dev):
+    """residual-stream row of logical row m; -(bt+1) for the cls rows of MAP_SPATIAL."""
+    m = torch.arange(M, device=dev)
+    L, S = T * HW, 1 + T * HW
+    if map == MAP_IDENT:
+        return m
+    if map == MAP_SKIPCLS:
+        return m + m // L + 1
+    if map == MAP_CLS:
+        return m * S
+    if map == MAP_PATCH:
+        bt, n = m // HW, m % HW
+        return (bt // T) * S + 1 + n * T + bt % T
+    bt, n = m // (HW + 1), m % (HW + 1)
+    r = (bt // T) * S + 1 + (n - 1) * T + bt % T
+    return torch.where(n == 0, -(bt + 1), r)
+
+
+def gemm(A, B, out, *, M, N, K, trans=0, epilogue=EPI_STORE, out2=None, bias=None, rowscale=None, rs_div=0,
+         map=MAP_IDENT, aux=None, resid=None, add_pos=None, add_time=None, T=1, HW=1, k_splits=0,
+         lda=None, ldb=None, ldo=None):
+    _launches[0] += 1
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
+    if trans == 0:
+        acc = A[:M, :K].float() @ B[:N, :K].float().t()
+    else:
+        acc = A[:K, :M].float().t() @ B[:K, :N].float()
+    dev = acc.device
+    if epilogue == EPI_ATOMIC:
+        out.view(-1, out.shape[-1])[:M, :N] += acc
+        return out
+    if bias is not None:
+        acc = acc + bias
+    if epilogue == EPI_GELU:
+        out[:M] = acc.to(out.dtype)
+        out2[:M] = F.gelu(acc).to(out2.dtype)
+        return out
+    if epilogue == EPI_DGELU:
+        p = aux[:M].float()
+        acc = acc * (0.5 * (1 + torch.erf(p / math.sqrt(2))) + p * torch.exp(-0.5 * p * p) / math.sqrt(2 * math.pi))
+    if rowscale is not None:
+        acc = acc * rowscale[torch.arange(M, device=dev) // rs_div].unsqueeze(1)
+    rows = _rows(map, M, T, HW, dev)
+    o2 = out.view(-1, out.shape[-1])
+    if epilogue == EPI_RESID:
+        cls = rows < 0
+        if cls.any():
+            out2[(-rows[cls] - 1)] = acc[cls]
+        tok = ~cls
+        val = acc[tok]
+        if resid is not None:
+            val = val + resid.view(-1, resid.shape[-1])[rows[tok]]
+        if add_pos is not None:
+            m = torch.arange(M, device=dev)
+            bt, n = m // HW, m % HW
+            val = val + add_pos[1 + n] + add_time[bt % T]
+        o2[rows[tok]] = val
+        return out
+    o2[rows] = acc.to(out.dtype)
+    return out
+
+
+def patchify(frames, out, patch=16):
+    _launches[0] += 1
+    Bc, C, T, H, W = frames.shape
+    nh, nw = H // patch, W // patch
+    x = frames.permute(0, 2, 1, 3, 4).reshape(Bc * T, C, nh, patch, nw, patch).permute(0, 2, 4, 1, 3, 5)
+    out.copy_(x.reshape(Bc * T * nh * nw, C * patch * patch).to(out.dtype))
+    return out
+
+
+def cls_init(x, cls_token, pos_embed):
+    _launches[0] += 1
+    x[:, 0] = cls_token.reshape(-1) + pos_embed.reshape(-1, x.shape[-1])[0]
+
+
+def _ln_src(x, x_cls, M, D, map, T, HW):
+    rows = _rows(map, M, T, HW, x.device)
+    xf = x.reshape(-1, D)
+    if map != MAP_SPATIAL:
+        return xf[rows], rows
+    S = 1 + T * HW
+    cls = rows < 0
+    src = xf[rows.clamp(min=0)].clone()
+    b = (-rows[cls] - 1) // T
+    src[cls] = x_cls.reshape(-1, D)[b * S]
+    return src, rows
+
+
+def layernorm_fwd(x, w, b, y, stats, M, D, eps, map=MAP_IDENT, x_cls=None, T=1, HW=1):
+    _launches[0] += 1
+    src, _ = _ln_src(x, x_cls, M, D, map, T, HW)
+    mu = src.mean(-1, keepdim=True)
+    var = ((src - mu) ** 2).mean(-1, keepdim=True)
+    rstd = 1.0 / torch.sqrt(var + eps)
+    y[:M] = ((src - mu) * rstd * w + b).to(y.dtype)
+    if stats is not None:
+        stats[:M, 0], stats[:M, 1] = mu.squeeze(-1), rstd.squeeze(-1)
+    return y
+
+
+def layernorm_bwd(dy, x, w, stats, dx, dw, db, M, D, map=MAP_IDENT, x_cls=None, T=1, HW=1):
+    _launches[0] += 1
+    src, rows = _ln_src(x, x_cls, M, D, map, T, HW)
+    d = dy[:M].float()
+    xh = (src - stats[:M, :1]) * stats[:M, 1:2]
+    g = d * w
+    dxr = stats[:M, 1:2] * (g - g.mean(-1, keepdim=True) - xh * (g * xh).mean(-1, keepdim=True))
+    if dw is not None:
+        dw += (d * xh).sum(0)
+    if db is not None:
+        db += d.sum(0)
+    dxf = dx.view(-1, D)
+    if map == MAP_SPATIAL:
+        S = 1 + T * HW
+        cls = rows < 0
+        dxf.index_add_(0, ((-rows[cls] - 1) // T) * S, dxr[cls])
+        dxf.index_add_(0, rows[~cls], dxr[~cls])
+    else:
+        dxf.index_add_(0, rows, dxr)
+
+
+def gather_cast(src, out, M, D, map=MAP_IDENT, rowscale=None, rs_div=0, T=1, HW=1):
+    _launches[0] += 1
+    rows = _rows(map, M, T, HW, src.device)
+    sf = src.reshape(-1, D)
+    f = torch.ones(M, device=src.device)
+    if rowscale is not None:
+        f = rowscale[torch.arange(M, device=src.device) // rs_div].clone()
+    if map == MAP_SPATIAL:
+        S = 1 + T * HW
+        cls = rows < 0
+        f = torch.where(cls, f / T, f)
+        rows = torch.where(cls, ((-rows - 1) // T) * S, rows)
+    out[:M] = (sf[rows] * f.unsqueeze(1)).to(out.dtype)
+    return out
+
+
+def cls_merge(x0, side, x2, Bc, T, S, D):
+    _launches[0] += 1
+    x2[:, 0] = x0[:, 0] + side.view(Bc, T, D).sum(1) / T
+
+
+def colsum(a, out, M, N):
+    _launches[0] += 1
+    out += a[:M, :N].float().sum(0)
+
+
+def cast_weight(w, w_out, wT_out):
+    _launches[0] += 1
+    if w_out is not None:
+        w_out.copy_(w.to(w_out.dtype))
+    if wT_out is not None:
+        wT_out.copy_(w.t().to(wT_out.dtype))
+
+
+def split3(a, out, M, K, pattern, along):
+    _launches[0] += 1
+    a = a.reshape(M, K)
+    hi = a.bfloat16()
+    lo = (a - hi.float()).bfloat16()
+    parts = (hi, hi, lo) if pattern == 0 else (hi, lo, hi)
+    out.copy_(torch.cat(parts, dim=1 if along == 1 else 0))
+    return out
+
+
+def embed_bwd(dx, dcls, dpos, dtime, Bc, D, T, HW):
+    _launches[0] += 1
+    tok = dx[:, 1:].reshape(Bc, HW, T, D)
+    c = dx[:, 0].sum(0)
+    if dcls is not None:
+        dcls += c
+    if dpos is not None:
+        dpos[0] += c
+        dpos[1:] += tok.sum((0, 2))
+    if dtime is not None:
+        dtime += tok.sum((0, 1))
+
+
+def _split_heads(qkv, n_seq, seq, H):
+    C = H * 64
+    q, k, v = qkv.float().split(C, dim=1)
+    return [t.reshape(n_seq, seq, H, 64).transpose(1, 2) for t in (q, k, v)]
+
+
+def attn_fwd(qkv, out, lse, n_seq, seq, H, scale):
+    _launches[0] += 1
+    q, k, v = _split_heads(qkv, n_seq, seq, H)
+    s = (q @ k.transpose(-1, -2)) * scale
+    out.copy_((s.softmax(-1) @ v).transpose(1, 2).reshape(n_seq * seq, H * 64).to(out.dtype))
+    if lse is not None:
+        lse.copy_(torch.logsumexp(s, -1))
+    return out
+
+
+def attn_bwd(qkv, out, dout, lse, dqkv, n_seq, seq, H, scale):
+    _launches[0] += 1
+    q, k, v = _split_heads(qkv, n_seq, seq, H)
+    do = dout.float().reshape(n_seq, seq, H, 64).transpose(1, 2)
+    o = out.float().reshape(n_seq, seq, H, 64).transpose(1, 2)
+    p = torch.exp((q @ k.transpose(-1, -2)) * scale - lse.unsqueeze(-1))
+    dv = p.transpose(-1, -2) @ do
+    dp = do @ v.transpose(-1, -2)
+    ds = p * (dp - (do * o).sum(-1, keepdim=True)) * scale
+    dq, dk = ds @ k, ds.transpose(-1, -2) @ q
+    cat = torch.cat([t.transpose(1, 2).reshape(n_seq * seq, H * 64) for t in (dq, dk, dv)], dim=1)
+    dqkv.copy_(cat.to(dqkv.dtype))
+    return dqkv
+
+
+def linear_small_fwd(x, w, b, y):
+    _launches[0] += 1
+    y.copy_(x @ w.t() + (b if b is not None else 0))
+    return y
+
+
+def linear_small_bwd(x, w, dy, dx, dw, db):
+    _launches[0] += 1
+    if dw is not None:
+        dw += dy.t() @ x
+        if db is not None:
+            db += dy.sum(0)
+    if dx is not None:
+        dx.copy_(dy @ w)
+
+
+def l2norm_fwd(x, y, norms):
+    _launches[0] += 1
+    n = x.norm(dim=1)
+    y.copy_(x / n.unsqueeze(1))
+    if norms is not None:
+        norms.copy_(n)
+    return y
+
+
+def l2norm_bwd(y, norms, dy, dx):
+    _launches[0] += 1
+    dx.copy_((dy - y * (y * dy).sum(1, keepdim=True)) / norms.unsqueeze(1))
+    return dx
+
+
+def sim_logits_fwd(emb, label, logits, inv_temp):
+    _launches[0] += 1
+    logits.copy_(emb @ label.t() * inv_temp)
+    return logits
+
+
+def sim_logits_bwd(dlogits, label, demb, inv_temp):
+    _launches[0] += 1
+    demb += dlogits @ label * inv_temp
+    return demb
+
+
+def kl_topk_loss(pred, teacher_logits, row_loss, dpred, teacher_out, topk, gscale=1.0):
+    _launches[0] += 1
+    M = pred.shape[0]
+    t = F.softmax(teacher_logits, 1)
+    if topk != 0:
+        tv = t.topk(k=topk, dim=1)[0]
+        t = (t.unsqueeze(1) * (t.unsqueeze(1) == tv.unsqueeze(2)).float()).sum(1)
+        t = t / t.sum(1, keepdim=True)
+    logp = F.log_softmax(pred, 1)
+    if row_loss is not None:
+        row_loss.copy_(torch.where(t > 0, t * (torch.log(t.clamp_min(1e-45)) - logp), torch.zeros_like(t)).sum(1) / M)
+    if dpred is not None:
+        dpred.copy_((logp.exp() - t) * (gscale / M))
+    if teacher_out is not None:
+        teacher_out.copy_(t)
+
+
+def softmax_rows(x, y):
+    _launches[0] += 1
+    y.copy_(x.softmax(1))
+    return y
+
+
+ALL = [n for n, v in list(globals().items()) if callable(v) and not n.startswith("_") and n not in ("F", "math", "torch")]

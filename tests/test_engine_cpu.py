@@ -1,0 +1,160 @@
+"""Host logic on CPU: the engine's forward/backward schedule, the model mirror's forward() and the state_dict
+schema, with every C-ABI op replaced by its torch restatement (tests/shadow_ops.py), against the golden vectors
+of the unmodified reference.  No GPU, no CUDA library involved -- this checks the composition, not the kernels."""
+import os
+
+import pytest
+import torch
+
+import shadow_ops
+import timesformer_oracle as O
+from procedurevrl_b200 import functional as PF
+from procedurevrl_b200 import ops as real_ops
+from procedurevrl_b200.lib.config import get_cfg
+from procedurevrl_b200.lib.models import MODEL_REGISTRY
+from procedurevrl_b200.lib.models.vit import VisionTransformer
+
+torch.set_num_threads(max(1, os.cpu_count() or 1))
+
+
+@pytest.fixture
+def shadow(monkeypatch):
+    for n in shadow_ops.ALL:
+        monkeypatch.setattr(real_ops, n, getattr(shadow_ops, n))
+    monkeypatch.setattr(VisionTransformer, "_require_cuda", False)
+
+
+def coin_cfg(gold_dir, depth, T, precision):
+    c = get_cfg()
+    c.merge_from_list(["DEV.ENABLE", True, "DEV.MATCH_LANG_EMB", True, "DEV.TEST_LANG_EMB",
+                       os.path.join(gold_dir, "clip_step_emb_coin.pt"), "TRAIN.DATASET", "howto100m_develop",
+                       "TRAIN.LINEAR", True, "MODEL.MODEL_NAME", "vit_base_patch16_224_develop", "MODEL.NUM_CLASSES", 778,
+                       "MODEL.ARCH", "vit", "MODEL.PRETRAINED", False, "MODEL.DROP_PATH", 0.0, "TIMESFORMER.DEPTH", depth,
+                       "DATA.NUM_FRAMES", T, "DATA.TEST_CROP_SIZE", 224, "B200.PRECISION", precision])
+    return c
+
+
+def pretrain_cfg(gold_dir, depth, precision):
+    c = coin_cfg(gold_dir, depth, 8, precision)
+    c.merge_from_list(["DEV.ORDER_PRETRAIN_ENABLED", True, "DEV.ORDER_TFM_LAYERS", 4, "TRAIN.LINEAR", False,
+                       "TRAIN.LABEL_EMB", os.path.join(gold_dir, "clip_step_emb_coin.pt"), "TRAIN.TOPK", 5,
+                       "MODEL.LOSS_FUNC", "kldiv", "MODEL.TEXT_MODEL", "clip_vit_b_16"])
+    return c
+
+
+def check_grads(named, gold, rtol):
+    assert gold
+    for k, g in gold.items():
+        mine = named[k]
+        assert mine is not None, k
+        assert abs(mine.norm().item() - g["norm"]) <= rtol * g["norm"] + 1e-7, (k, mine.norm().item(), g["norm"])
+        torch.testing.assert_close(mine.flatten()[:64].cpu(), g["head"], rtol=rtol,
+                                   atol=rtol * g["norm"] / mine.numel() ** 0.5 + 1e-7, msg=k)
+
+
+def test_state_dict_schema(gold_dir):
+    """identical names and shapes, so reference checkpoints load with strict=True."""
+    m = MODEL_REGISTRY.get("vit_base_patch16_224_develop")(pretrain_cfg(gold_dir, 2, "bf16"))
+    st = O.seeded_state(depth=2, frames=8, seed=1, with_order=True)
+    own = m.state_dict()
+    assert set(own) == set(st), (set(own) ^ set(st))
+    for k in own:
+        assert own[k].shape == st[k].shape, k
+    m.load_state_dict(st, strict=True)
+    # fresh init mirrors the reference quirk: temporal_fc zero in every block (vit.py:273-281)
+    m2 = MODEL_REGISTRY.get("vit_base_patch16_224_develop")(coin_cfg(gold_dir, 2, 8, "bf16"))
+    assert all(b.temporal_fc.weight.abs().sum() == 0 for b in m2.model.blocks)
+    assert not m2.model.head.weight.requires_grad          # fine-tune branch freezes the head (vit.py:241)
+    names = [n for n, _ in m.named_parameters()]
+    assert any("order" in n for n in names) and any(n.startswith("model.head.") for n in names)
+
+
+@pytest.mark.parametrize("name", ["coin_d2_b2.pt", "coin_d2_t4.pt"])
+def test_matchlang_forward_backward(shadow, gold_dir, name):
+    g = torch.load(os.path.join(gold_dir, name))
+    c = g["cfg"]
+    m = MODEL_REGISTRY.get("vit_base_patch16_224_develop")(coin_cfg(gold_dir, c["depth"], c["T"], "bf16x3"))
+    m.load_state_dict(O.seeded_state(depth=c["depth"], frames=c["T"], seed=c["state_seed"]), strict=True)
+    for p in m.parameters():
+        p.requires_grad_(True)
+    x = O.synthetic_clips(c["B"], 3, c["T"], 224, 224, seed=c["clip_seed"])
+    m.train()
+    logits = m(x)
+    torch.testing.assert_close(logits, g["logits"], rtol=1e-3, atol=2e-3)
+    assert torch.equal(logits.argmax(1), g["logits"].argmax(1))
+    loss = torch.nn.functional.cross_entropy(logits, g["labels"])
+    assert abs(loss.item() - g["loss"]) < 1e-3
+    loss.backward()
+    check_grads({k: p.grad for k, p in m.named_parameters()}, g["grads"], rtol=5e-3)
+    m.eval()
+    with torch.no_grad():
+        probs = m(x)
+    torch.testing.assert_close(probs, g["probs"], rtol=5e-3, atol=1e-6)
+
+
+def test_droppath(shadow, gold_dir):
+    g = torch.load(os.path.join(gold_dir, "droppath_d2.pt"))
+    c = g["cfg"]
+    cfg = coin_cfg(gold_dir, c["depth"], c["T"], "bf16x3")
+    cfg.merge_from_list(["MODEL.DROP_PATH", c["rate"]])
+    m = MODEL_REGISTRY.get("vit_base_patch16_224_develop")(cfg)
+    m.load_state_dict(O.seeded_state(depth=c["depth"], frames=c["T"], seed=c["state_seed"]), strict=True)
+    keep = 1.0 - m.model.dpr[1]
+    sc = [torch.floor(keep + t.flatten()) / keep for t in g["rands"]]
+    m.model.fixed_drop_scales = [None, {"temporal": sc[0], "spatial": sc[1], "mlp": sc[2]}]
+    m.train()
+    x = O.synthetic_clips(c["B"], 3, c["T"], 224, 224, seed=c["clip_seed"])
+    with torch.no_grad():
+        logits = m(x)
+    torch.testing.assert_close(logits, g["logits"], rtol=1e-3, atol=2e-3)
+    # the module's own draws have the reference's shapes and values in {0, 1/keep}
+    m.model.fixed_drop_scales = None
+    ds = m.model._drop_scales(c["B"], c["T"], 196, x.device)
+    assert ds[0] is None and ds[1]["temporal"].shape == (c["B"] * 196,) and ds[1]["spatial"].shape == (c["B"] * c["T"],)
+    assert set((ds[1]["temporal"] * keep).round().tolist()) <= {0.0, 1.0}
+
+
+def test_pretrain_step(shadow, gold_dir):
+    g = torch.load(os.path.join(gold_dir, "pretrain_d2_v2.pt"))
+    c = g["cfg"]
+    Bv = c["Bv"]
+    m = MODEL_REGISTRY.get("vit_base_patch16_224_develop")(pretrain_cfg(gold_dir, c["depth"], "bf16x3"))
+    m.load_state_dict(O.seeded_state(depth=c["depth"], frames=c["T"], seed=c["state_seed"], with_order=True), strict=True)
+    gen = torch.Generator().manual_seed(c["emb_seed"])
+    text_emb = 0.4 * torch.randn(Bv * 9, 512, generator=gen)
+    vis_emb = 0.4 * torch.randn(Bv * 9, 512, generator=gen)
+    frames = O.synthetic_clips(Bv, 9, 3, c["T"], 224, 224, seed=c["clip_seed"])
+    d = g["draws"]
+    m.model.order_tfm.fixed_draws = (d["mask_inds"], d["pad_start"], d["noise"])
+    m.model.fixed_rand_inds = d["rand_inds"]
+    m.train()
+    pred, teacher, mse = m([frames, {"clip_text_emb": text_emb, "clip_vis_feat": vis_emb}])
+    torch.testing.assert_close(pred, g["pred"], rtol=1e-3, atol=3e-3)
+    torch.testing.assert_close(teacher, g["teacher"], rtol=1e-4, atol=5e-4)
+    torch.testing.assert_close(mse[0], g["mse0"], rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(mse[1], g["mse1"], rtol=1e-3, atol=1e-3)
+    loss, l1, l2 = PF.pretrain_loss(pred, teacher, mse, topk=5)
+    assert abs(l1.item() - g["loss1"]) < 2e-3 and abs(l2.item() - g["loss2"]) < 2e-3
+    loss.backward()
+    grads = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+    assert len(grads) == g["n_trainable_with_grad"]
+    check_grads(grads, g["grads"], rtol=1e-2)
+    # device-side draws of the order transformer: shapes / ranges of the reference's draws (tfm_model.py:145,279-284)
+    m.model.order_tfm.fixed_draws = None
+    with torch.no_grad():
+        den, mask_inds, pair, inter = m.model.order_tfm(torch.randn(Bv * 9, 512), is_pretrain=True)
+    assert den.shape == (Bv, 512) and inter.shape == (4 * Bv, 512) and int(mask_inds.max()) < 9
+
+
+def test_forecast(shadow, gold_dir):
+    g = torch.load(os.path.join(gold_dir, "forecast_d2.pt"))
+    c = g["cfg"]
+    cfg = coin_cfg(gold_dir, c["depth"], c["T"], "bf16x3")
+    cfg.merge_from_list(["MODEL.NUM_SEG", c["num_seg"], "MODEL.DROP_E", 0.0])
+    m = MODEL_REGISTRY.get("vit_base_patch16_224_develop")(cfg)
+    m.load_state_dict(O.seeded_state(depth=c["depth"], frames=c["T"], seed=c["state_seed"], with_order=True), strict=True)
+    x = O.synthetic_clips(c["B"], 3, c["num_seg"] * c["T"], 224, 224, seed=c["clip_seed"])
+    m.eval()
+    with torch.no_grad():
+        probs = m(x)
+    torch.testing.assert_close(probs, g["probs"], rtol=5e-3, atol=1e-6)
