@@ -1,0 +1,416 @@
+// Spatial attention (seq = 1 + H*W = 197 tokens per frame, head_dim 64) on the 5th-gen tensor cores:
+// TMA loads the per-head Q/K/V (and dO) slices straight out of the fused QKV GEMM output through 3-D tensor
+// maps (no head-split / transpose copies), tcgen05.mma computes Q K^T, P V and the four backward contractions
+// with fp32 accumulators in TMEM, softmax runs one thread per query row on tcgen05.ld'ed scores and writes P
+// (and dS) back to shared memory in the 128B-swizzled layout the next MMA reads.
+// Attention.forward vit.py:84-88 and its autograd.  bf16 only, seq <= 256.
+#include "pvrl_host.h"
+#include "pvrl_ptx.cuh"
+
+namespace pvrl {
+namespace {
+
+constexpr int TILE_BYTES = 128 * 128;  // [128 rows][64 bf16] SWIZZLE_128B tile
+constexpr float LOG2E = 1.4426950408889634f;
+
+// byte offset of 16-byte piece `piece` (8 bf16) of row r inside a [rows][128 B] SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t swz(int r, int piece) { return r * 128 + ((piece ^ (r & 7)) << 4); }
+
+__device__ __forceinline__ void st_piece(uint8_t* tile, int r, int piece, const float* v) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]);
+  u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]);
+  u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(tile + swz(r, piece)) = u;
+}
+
+__device__ __forceinline__ void store_row64_bf16(__nv_bfloat16* dst, const float* v) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint4 u;
+    u.x = pack_bf16x2(v[8 * i], v[8 * i + 1]);
+    u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+    u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+    u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+    reinterpret_cast<uint4*>(dst)[i] = u;
+  }
+}
+
+// =====================================================================================================
+// forward: one CTA per (sequence, head, 128-query tile).  160 threads: warps 0-3 softmax / epilogue (one
+// query row per thread), warp 4 = TMA + MMA issuer.  smem: [Q | K] (overlaid by P once S is done) + V.
+// =====================================================================================================
+__global__ void __launch_bounds__(160)
+attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                   __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int seq, int H, float scale, int npad) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  // layout: P region 4 tiles (64 KB) holding Q at +0 and K at +16 KB until S is done; V after it
+  const uint32_t sQ = base, sK = base + TILE_BYTES, sP = base, sV = base + 4 * TILE_BYTES;
+  const uint32_t bars = sV + 256 * 128;
+  const uint32_t bar_load = bars, bar_s = bars + 8, bar_p = bars + 16, bar_o = bars + 24;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + (bars - base) + 32);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.x, mt = blockIdx.y;
+  const int s_idx = pair / H, h = pair % H;
+  const int C = H * 64;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmKV);
+      mbar_init(bar_load, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_p, 128);
+      mbar_init(bar_o, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<256>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_load, TILE_BYTES + 2 * npad * 128);
+      tma_load_3d(sQ, &tmQ, bar_load, h * 64, mt * 128, s_idx);
+      tma_load_3d(sK, &tmKV, bar_load, C + h * 64, 0, s_idx);
+      tma_load_3d(sV, &tmKV, bar_load, 2 * C + h * 64, 0, s_idx);
+      mbar_wait(bar_load, 0);
+      tc_fence_after();
+      const uint32_t idesc_s = make_idesc_bf16(128, npad, 0, 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tmem, make_smem_desc(sQ + k * 32, 16, 1024), make_smem_desc(sK + k * 32, 16, 1024), idesc_s, k > 0);
+      umma_commit(bar_s);
+      mbar_wait(bar_p, 0);
+      tc_fence_after();
+      const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
+      for (int k = 0; k < npad / 16; ++k)
+        umma_bf16(tmem, make_smem_desc(sP + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024),
+                  make_smem_desc(sV + k * 2048, 8192, 1024), idesc_o, k > 0);
+      umma_commit(bar_o);
+    }
+  } else {
+    const int r = warp * 32 + lane;
+    const int qi = mt * 128 + r;
+    const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    uint32_t raw[32];
+    float mx = -INFINITY;
+    for (int c0 = 0; c0 < npad; c0 += 32) {
+      tmem_ld32(trow + c0, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (c0 + j < seq) mx = fmaxf(mx, __uint_as_float(raw[j]));
+    }
+    const float sl2 = scale * LOG2E;
+    const float mxs = mx * sl2;
+    float sum = 0.f;
+    for (int c0 = 0; c0 < npad; c0 += 32) {
+      tmem_ld32(trow + c0, raw);
+      tmem_ld_wait();
+      float p[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        p[j] = (c0 + j < seq) ? exp2f(__uint_as_float(raw[j]) * sl2 - mxs) : 0.f;
+        sum += p[j];
+      }
+      uint8_t* tile = smem + (c0 >> 6) * TILE_BYTES;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) st_piece(tile, r, ((c0 & 63) >> 3) + q, p + 8 * q);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    mbar_arrive(bar_p);
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    float o[64];
+    tmem_ld32(trow, raw);
+    tmem_ld_wait();
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(raw[j]) * inv;
+    tmem_ld32(trow + 32, raw);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[32 + j] = __uint_as_float(raw[j]) * inv;
+    if (qi < seq) {
+      store_row64_bf16(out + ((long long)s_idx * seq + qi) * C + h * 64, o);
+      if (lse != nullptr) lse[(long long)pair * seq + qi] = mx * scale + __logf(sum);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<256>(tmem);
+}
+
+// =====================================================================================================
+// backward: one CTA per (sequence, head); Q, K, V, dO resident (256 rows each), loop over 128-key tiles kt
+// and 128-query tiles mt:   S = Q K^T, dP = dO V^T  ->  P = exp(S*scale - lse), dS = P*(dP - delta)*scale  ->
+// dQ_mt += dS K,  dV_kt += P^T dO,  dK_kt += dS^T Q.   TMEM: S 0..127 | dP 128..255 | dK 256..319 |
+// dV 320..383 | dQ_0 384..447 | dQ_1 448..511.
+// =====================================================================================================
+__global__ void __launch_bounds__(160, 1)
+attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                   const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
+                   const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, int seq, int H, float scale) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t sQ = base, sK = base + 2 * TILE_BYTES, sV = base + 4 * TILE_BYTES, sdO = base + 6 * TILE_BYTES;
+  const uint32_t sP = base + 8 * TILE_BYTES, sdS = base + 10 * TILE_BYTES;
+  uint8_t* pP = smem + 8 * TILE_BYTES;
+  uint8_t* pdS = smem + 10 * TILE_BYTES;
+  const uint32_t bars = base + 12 * TILE_BYTES;
+  const uint32_t bar_load = bars, bar_sdp = bars + 8, bar_pds = bars + 16, bar_mma2 = bars + 24;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 12 * TILE_BYTES + 32);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.x;
+  const int s_idx = pair / H, h = pair % H;
+  const int C = H * 64;
+  const int n_tiles = (seq + 127) / 128;   // 1 or 2 (seq <= 256)
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQKV);
+      tma_prefetch_desc(&tmDO);
+      mbar_init(bar_load, 1);
+      mbar_init(bar_sdp, 1);
+      mbar_init(bar_pds, 128);
+      mbar_init(bar_mma2, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DK = 256, COL_DV = 320, COL_DQ = 384;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_load, 8 * TILE_BYTES);
+      tma_load_3d(sQ, &tmQKV, bar_load, h * 64, 0, s_idx);
+      tma_load_3d(sK, &tmQKV, bar_load, C + h * 64, 0, s_idx);
+      tma_load_3d(sV, &tmQKV, bar_load, 2 * C + h * 64, 0, s_idx);
+      tma_load_3d(sdO, &tmDO, bar_load, h * 64, 0, s_idx);
+      mbar_wait(bar_load, 0);
+      tc_fence_after();
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);
+      constexpr uint32_t idesc_dkv = make_idesc_bf16(128, 64, 1, 1);
+      uint32_t it = 0;
+      for (int kt = 0; kt < n_tiles; ++kt)
+        for (int mt = 0; mt < n_tiles; ++mt, ++it) {
+          const uint32_t q_t = sQ + mt * TILE_BYTES, do_t = sdO + mt * TILE_BYTES;
+          const uint32_t k_t = sK + kt * TILE_BYTES, v_t = sV + kt * TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + COL_S, make_smem_desc(q_t + k * 32, 16, 1024), make_smem_desc(k_t + k * 32, 16, 1024),
+                      idesc_s, k > 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + COL_DP, make_smem_desc(do_t + k * 32, 16, 1024), make_smem_desc(v_t + k * 32, 16, 1024),
+                      idesc_s, k > 0);
+          umma_commit(bar_sdp);
+          mbar_wait(bar_pds, it & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // dQ_mt += dS[q, keys] K[keys, d]
+            umma_bf16(tmem + COL_DQ + mt * 64, make_smem_desc(sdS + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024),
+                      make_smem_desc(k_t + k * 2048, TILE_BYTES, 1024), idesc_dq, (kt > 0 || k > 0));
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // dV_kt += P^T[keys, q] dO[q, d]
+            umma_bf16(tmem + COL_DV, make_smem_desc(sP + k * 2048, TILE_BYTES, 1024),
+                      make_smem_desc(do_t + k * 2048, TILE_BYTES, 1024), idesc_dkv, (mt > 0 || k > 0));
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // dK_kt += dS^T[keys, q] Q[q, d]
+            umma_bf16(tmem + COL_DK, make_smem_desc(sdS + k * 2048, TILE_BYTES, 1024),
+                      make_smem_desc(q_t + k * 2048, TILE_BYTES, 1024), idesc_dkv, (mt > 0 || k > 0));
+          umma_commit(bar_mma2);
+        }
+    }
+  } else {
+    const int r = warp * 32 + lane;
+    const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    const long long pitch = 3LL * C;
+    // per-row constants for both query tiles: lse and delta = dO . O
+    float lse_l2[2], delta[2];
+    bool qvalid[2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int qi = mt * 128 + r;
+      qvalid[mt] = mt < n_tiles && qi < seq;
+      lse_l2[mt] = 0.f, delta[mt] = 0.f;
+      if (qvalid[mt]) {
+        const uint4* po = reinterpret_cast<const uint4*>(out + ((long long)s_idx * seq + qi) * C + h * 64);
+        const uint4* pd = reinterpret_cast<const uint4*>(dout + ((long long)s_idx * seq + qi) * C + h * 64);
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 a = __ldg(po + i), b = __ldg(pd + i);
+          const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+          const float2 b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y), b2 = unpack_bf16x2(b.z), b3 = unpack_bf16x2(b.w);
+          acc += a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y + a3.x * b3.x +
+                 a3.y * b3.y;
+        }
+        delta[mt] = acc;
+        lse_l2[mt] = lse[(long long)pair * seq + qi] * LOG2E;
+      }
+    }
+    const float sl2 = scale * LOG2E;
+    uint32_t it = 0;
+    for (int kt = 0; kt < n_tiles; ++kt)
+      for (int mt = 0; mt < n_tiles; ++mt, ++it) {
+        mbar_wait(bar_sdp, it & 1);
+        tc_fence_after();
+        if (it > 0) mbar_wait(bar_mma2, (it - 1) & 1);   // previous P / dS tiles fully consumed by the MMAs
+        const bool qv = qvalid[mt];
+        const float l2 = lse_l2[mt], dl = delta[mt];
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t rs[32], rp[32];
+          tmem_ld32(trow + COL_S + c0, rs);
+          tmem_ld32(trow + COL_DP + c0, rp);
+          tmem_ld_wait();
+          float p[32], ds[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const bool v = qv && (kt * 128 + c0 + j < seq);
+            p[j] = v ? exp2f(__uint_as_float(rs[j]) * sl2 - l2) : 0.f;
+            ds[j] = v ? p[j] * (__uint_as_float(rp[j]) - dl) * scale : 0.f;
+          }
+          const int tile = c0 >> 6, piece0 = (c0 & 63) >> 3;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            st_piece(pP + tile * TILE_BYTES, r, piece0 + q, p + 8 * q);
+            st_piece(pdS + tile * TILE_BYTES, r, piece0 + q, ds + 8 * q);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(bar_pds);
+        if (mt == n_tiles - 1) {   // key tile finished: dK_kt / dV_kt rows (this thread = key kt*128 + r)
+          mbar_wait(bar_mma2, it & 1);
+          tc_fence_after();
+          const int kj = kt * 128 + r;
+          uint32_t raw[32];
+          float v[64];
+          tmem_ld32(trow + COL_DK, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          tmem_ld32(trow + COL_DK + 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[32 + j] = __uint_as_float(raw[j]);
+          if (kj < seq) store_row64_bf16(dqkv + ((long long)s_idx * seq + kj) * pitch + C + h * 64, v);
+          tmem_ld32(trow + COL_DV, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          tmem_ld32(trow + COL_DV + 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[32 + j] = __uint_as_float(raw[j]);
+          if (kj < seq) store_row64_bf16(dqkv + ((long long)s_idx * seq + kj) * pitch + 2 * C + h * 64, v);
+          tc_fence_before();
+        }
+      }
+    // dQ tiles (the last bar_mma2 wait above covers every MMA)
+    for (int mt = 0; mt < n_tiles; ++mt) {
+      const int qi = mt * 128 + r;
+      uint32_t raw[32];
+      float v[64];
+      tmem_ld32(trow + COL_DQ + mt * 64, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+      tmem_ld32(trow + COL_DQ + mt * 64 + 32, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[32 + j] = __uint_as_float(raw[j]);
+      if (qi < seq) store_row64_bf16(dqkv + ((long long)s_idx * seq + qi) * pitch + h * 64, v);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<512>(tmem);
+}
+
+// 3-D bf16 tensor map over a row-major [n_seq, seq, cols] view, box [1, box_rows, 64], 128B swizzle, zero OOB fill.
+int make_tmap_3d(CUtensorMap* out, const void* ptr, uint64_t cols, uint64_t seq, uint64_t n_seq, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) return fail(-2, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || (cols * 2) % 16 != 0)
+    return fail(-1, "attention operand must be 16-byte aligned with a row pitch multiple of 8 elements");
+  cuuint64_t dims[3] = {cols, seq, n_seq};
+  cuuint64_t strides[2] = {cols * 2, seq * cols * 2};
+  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(-3, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", static_cast<int>(r));
+  return 0;
+}
+
+}  // namespace
+}  // namespace pvrl
+
+using namespace pvrl;
+
+extern "C" int pvrl_attn_tc_fwd(const void* qkv, void* out, float* lse, int32_t n_seq, int32_t seq, int32_t H,
+                                float scale, void* stream) {
+  PVRL_CHECK_ARG(qkv && out && n_seq > 0 && H > 0, "pvrl_attn_tc_fwd: bad arguments");
+  PVRL_CHECK_ARG(seq > 0 && seq <= 256, "pvrl_attn_tc_fwd: seq=%d must be in [1, 256]", seq);
+  const int npad = ((seq + 31) / 32) * 32;
+  CUtensorMap tq, tkv;
+  int rc;
+  if ((rc = make_tmap_3d(&tq, qkv, 3ull * H * 64, seq, n_seq, 128))) return rc;
+  if ((rc = make_tmap_3d(&tkv, qkv, 3ull * H * 64, seq, n_seq, npad))) return rc;
+  const size_t smem = 4 * TILE_BYTES + 256 * 128 + 64 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    PVRL_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid(n_seq * H, (seq + 127) / 128);
+  attn_tc_fwd_kernel<<<grid, 160, smem, static_cast<cudaStream_t>(stream)>>>(
+      tq, tkv, static_cast<__nv_bfloat16*>(out), lse, seq, H, scale, npad);
+  return launched("attn_tc_fwd_kernel");
+}
+
+extern "C" int pvrl_attn_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                                int32_t n_seq, int32_t seq, int32_t H, float scale, void* stream) {
+  PVRL_CHECK_ARG(qkv && out && dout && lse && dqkv && n_seq > 0 && H > 0, "pvrl_attn_tc_bwd: bad arguments");
+  PVRL_CHECK_ARG(seq > 0 && seq <= 256, "pvrl_attn_tc_bwd: seq=%d must be in [1, 256]", seq);
+  CUtensorMap tqkv, tdo;
+  int rc;
+  if ((rc = make_tmap_3d(&tqkv, qkv, 3ull * H * 64, seq, n_seq, 256))) return rc;
+  if ((rc = make_tmap_3d(&tdo, dout, 1ull * H * 64, seq, n_seq, 256))) return rc;
+  const size_t smem = 12 * TILE_BYTES + 64 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    PVRL_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  attn_tc_bwd_kernel<<<n_seq * H, 160, smem, static_cast<cudaStream_t>(stream)>>>(
+      tqkv, tdo, static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), lse,
+      static_cast<__nv_bfloat16*>(dqkv), seq, H, scale);
+  return launched("attn_tc_bwd_kernel");
+}

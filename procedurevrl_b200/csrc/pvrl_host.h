@@ -1,5 +1,6 @@
 // Host-side helpers shared by the .cu translation units: error reporting and launch accounting.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -40,6 +41,12 @@ inline int launched(const char* what) {
     cudaError_t e__ = (expr);                                                                   \
     if (e__ != cudaSuccess) return ::pvrl::fail(static_cast<int>(e__), "%s: %s", #expr, cudaGetErrorString(e__)); \
   } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn();   // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda)
+int num_sms();
 
 struct Geom {
   int T, HW, L, S;
