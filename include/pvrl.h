@@ -137,6 +137,13 @@ int pvrl_attn_fwd(const void* qkv, void* out, float* lse, int32_t dtype, int32_t
 int pvrl_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int32_t dtype,
                   int32_t n_seq, int32_t seq, int32_t H, float scale, void* stream);
 
+/* Tensor-core (tcgen05 + TMA) attention for the spatial axis: bf16, head_dim 64, seq <= 256.  Same contract as
+ * pvrl_attn_fwd / pvrl_attn_bwd (qkv column order [3][H][64]; lse = log-sum-exp of the scaled scores). */
+int pvrl_attn_tc_fwd(const void* qkv, void* out, float* lse, int32_t n_seq, int32_t seq, int32_t H, float scale,
+                     void* stream);
+int pvrl_attn_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                     int32_t n_seq, int32_t seq, int32_t H, float scale, void* stream);
+
 /* ---- head + similarity + loss (vit.py:300-307, train_net.py:153-162) ----------------------------------- */
 
 /* y[m, j] = sum_k x[m,k] w[j,k] + b[j]   fp32, small M (head 768->512, vit.py:301) */

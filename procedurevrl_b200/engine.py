@@ -43,6 +43,7 @@ class EncoderEngine:
         self.act_dtype = torch.float32 if self.x3 else torch.bfloat16
         self.scale = (embed_dim // num_heads) ** -0.5
         assert embed_dim // num_heads == 64, "kernels are specialised for head_dim 64"
+        self.use_tc_attention = True      # tcgen05 spatial attention in bf16 mode (the fp32 parity mode uses CUDA cores)
         self._wcache = {}      # name -> (version, W operand [N, K'], W^T operand [K, N'])
         self.grad_names = self._grad_names()
 
@@ -232,10 +233,16 @@ class EncoderEngine:
 
     # spatial attention dispatch (the tcgen05 kernel plugs in here)
     def spatial_attn_fwd(self, qkv, out, lse, n_seq, seq):
-        ops.attn_fwd(qkv, out, lse, n_seq, seq, self.H, self.scale)
+        if not self.x3 and seq <= 256 and self.use_tc_attention:
+            ops.attn_tc_fwd(qkv, out, lse, n_seq, seq, self.H, self.scale)
+        else:
+            ops.attn_fwd(qkv, out, lse, n_seq, seq, self.H, self.scale)
 
     def spatial_attn_bwd(self, qkv, out, dout, lse, dqkv, n_seq, seq):
-        ops.attn_bwd(qkv, out, dout, lse, dqkv, n_seq, seq, self.H, self.scale)
+        if not self.x3 and seq <= 256 and self.use_tc_attention:
+            ops.attn_tc_bwd(qkv, out, dout, lse, dqkv, n_seq, seq, self.H, self.scale)
+        else:
+            ops.attn_bwd(qkv, out, dout, lse, dqkv, n_seq, seq, self.H, self.scale)
 
     # ------------------------------------------------------------------------------------------ backward
     def backward(self, st, dfeat):

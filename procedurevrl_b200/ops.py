@@ -51,6 +51,9 @@ _SIGS = {
     "pvrl_attn_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p],
     "pvrl_attn_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float,
                       _c_void_p],
+    "pvrl_attn_tc_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_void_p],
+    "pvrl_attn_tc_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float,
+                         _c_void_p],
     "pvrl_linear_small_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
     "pvrl_linear_small_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int,
                               _c_void_p],
@@ -208,6 +211,19 @@ def attn_fwd(qkv, out, lse, n_seq, seq, H, scale):
 def attn_bwd(qkv, out, dout, lse, dqkv, n_seq, seq, H, scale):
     _check(lib().pvrl_attn_bwd(_p(qkv), _p(out), _p(dout), _p(lse), _p(dqkv), _dt(qkv), n_seq, seq, H, scale,
                                _stream()), "pvrl_attn_bwd")
+    return dqkv
+
+
+def attn_tc_fwd(qkv, out, lse, n_seq, seq, H, scale):
+    assert qkv.dtype == torch.bfloat16
+    _check(lib().pvrl_attn_tc_fwd(_p(qkv), _p(out), _p(lse), n_seq, seq, H, scale, _stream()), "pvrl_attn_tc_fwd")
+    return out
+
+
+def attn_tc_bwd(qkv, out, dout, lse, dqkv, n_seq, seq, H, scale):
+    assert qkv.dtype == torch.bfloat16
+    _check(lib().pvrl_attn_tc_bwd(_p(qkv), _p(out), _p(dout), _p(lse), _p(dqkv), n_seq, seq, H, scale, _stream()),
+           "pvrl_attn_tc_bwd")
     return dqkv
 
 

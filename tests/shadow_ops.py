@@ -235,6 +235,9 @@ def attn_bwd(qkv, out, dout, lse, dqkv, n_seq, seq, H, scale):
     return dqkv
 
 
+attn_tc_fwd, attn_tc_bwd = attn_fwd, attn_bwd
+
+
 def linear_small_fwd(x, w, b, y):
     _launches[0] += 1
     y.copy_(x @ w.t() + (b if b is not None else 0))

@@ -321,3 +321,36 @@ def test_kl_topk_loss(ops, topk):
     sm = torch.empty(M, K, device="cuda")
     ops.softmax_rows(pred, sm)
     assert _report("softmax", sm, pred.softmax(1))[0].max() < 1e-6
+
+
+@pytest.mark.parametrize("n_seq,seq,H", [(3, 197, 12), (2, 128, 4), (2, 50, 2), (1, 256, 2), (144, 197, 12)])
+def test_attn_tensor_core(ops, n_seq, seq, H):
+    """tcgen05 spatial attention (bf16) against the fp32 torch restatement and the CUDA-core kernel."""
+    C = H * 64
+    scale = 64 ** -0.5
+    qkv = _rand(n_seq * seq, 3 * C, seed=1, dtype=torch.bfloat16)
+    qkv_r = qkv.float().requires_grad_(True)
+    qr, kr, vr = (t.reshape(n_seq, seq, H, 64).transpose(1, 2) for t in qkv_r.split(C, dim=1))
+    att = (qr @ kr.transpose(-1, -2)) * scale
+    ref = (att.softmax(-1) @ vr).transpose(1, 2).reshape(n_seq * seq, C)
+    out = torch.full((n_seq * seq, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    lse = torch.full((n_seq, H, seq), float("nan"), device="cuda")
+    ops.attn_tc_fwd(qkv, out, lse, n_seq, seq, H, scale)
+    torch.cuda.synchronize()
+    err, rel = _report(f"attn_tc_fwd {n_seq}x{seq}x{H}", out, ref.detach())
+    if rel > 2e-2:
+        bad = (err > 0.05 * ref.abs().max()).nonzero()
+        print("first bad idx:", bad[:10].tolist(), "n_bad", bad.shape[0], "of", out.numel())
+    assert rel < 2e-2
+    assert _report("attn_tc lse", lse, torch.logsumexp(att.detach(), -1))[0].max() < 2e-3
+    do = _rand(n_seq * seq, C, seed=2, dtype=torch.bfloat16)
+    (g,) = torch.autograd.grad(ref, qkv_r, do.float())
+    dqkv = torch.full_like(qkv, float("nan"))
+    ops.attn_tc_bwd(qkv, out, do, lse, dqkv, n_seq, seq, H, scale)
+    torch.cuda.synchronize()
+    for name, sl in (("dq", slice(0, C)), ("dk", slice(C, 2 * C)), ("dv", slice(2 * C, 3 * C))):
+        err, rel = _report(f"attn_tc_bwd.{name} {n_seq}x{seq}x{H}", dqkv[:, sl], g[:, sl])
+        if rel > 3e-2:
+            bad = (err > 0.05 * g[:, sl].abs().max()).nonzero()
+            print("first bad idx:", bad[:10].tolist(), "n_bad", bad.shape[0])
+        assert rel < 3e-2
