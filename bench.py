@@ -212,9 +212,11 @@ def run_b200(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(0 if args.profile else args.steps):
         frames.copy_(frames_pin, non_blocking=True)
         last = step(frames).item()
+    if args.profile:
+        last = loss.item()
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -225,7 +227,7 @@ def run_b200(args):
         ms, e2e_ms = t.tolist()
     ms_step = ms / args.steps
     value = clips_per_step / (ms_step / 1e3)
-    e2e = clips_per_step / (e2e_ms / args.steps / 1e3)
+    e2e = clips_per_step / (e2e_ms / args.steps / 1e3) if not args.profile else 0.0
 
     if rank == 0:
         peak, _, peak_src = measured_peaks()
@@ -360,8 +362,13 @@ def main():
     ap.add_argument("--videos-per-gpu", type=int, default=2)        # TRAIN.BATCH_SIZE 16 / NUM_GPUS 8
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="short run for ncu: 1 warm-up + --steps timed steps, no e2e / cpu legs (never a bench value)")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "b200":
+        args.warmup = 1 if args.profile else max(args.warmup, 3)
+    if args.profile:
+        args.no_cpu_baseline = True
     if args.impl == "reference":
         run_reference(args)
     else:
