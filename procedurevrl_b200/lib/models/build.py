@@ -42,8 +42,15 @@ def build_model(cfg, gpu_id=None):
     cur_device = torch.cuda.current_device() if gpu_id is None else gpu_id
     model = model.cuda(device=cur_device)
     if cfg.NUM_GPUS > 1 and torch.distributed.is_available() and torch.distributed.is_initialized():
-        bucket_mb = cfg.B200.GRAD_BUCKET_MB if "B200" in cfg else 64
-        model = torch.nn.parallel.DistributedDataParallel(
-            module=model, device_ids=[cur_device], output_device=cur_device, find_unused_parameters=False,
-            gradient_as_bucket_view=True, bucket_cap_mb=bucket_mb, broadcast_buffers=False)
+        model = wrap_data_parallel(model, cfg, cur_device)
     return model
+
+
+def wrap_data_parallel(model, cfg, device=None):
+    """The data-parallel boundary of build.py:49-53: replicas + one bucketed gradient all-reduce (NCCL on GPUs;
+    the CPU tests drive the same wrapper over gloo)."""
+    bucket_mb = cfg.B200.GRAD_BUCKET_MB if "B200" in cfg else 64
+    ids = None if device is None else [device]
+    return torch.nn.parallel.DistributedDataParallel(
+        module=model, device_ids=ids, output_device=device, find_unused_parameters=False,
+        gradient_as_bucket_view=True, bucket_cap_mb=bucket_mb, broadcast_buffers=False)

@@ -1,0 +1,95 @@
+"""N > 1 path on CPU: two gloo ranks, each with a replica of the model mirror behind the data-parallel wrapper of
+lib/models/build.py, shard a batch of clips; the all-reduced gradients must equal the single-process gradients
+of the whole batch.  The C-ABI ops are replaced by their torch restatements (tests/shadow_ops.py) -- this checks
+the host logic of the data-parallel boundary (one autograd node producing every encoder gradient, bucketed
+all-reduce, no unused-parameter walk), not the kernels."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _small_cfg(bank):
+    from procedurevrl_b200.lib.config import get_cfg
+    c = get_cfg()
+    c.merge_from_list(["DEV.MATCH_LANG_EMB", True, "DEV.TEST_LANG_EMB", bank, "MODEL.MODEL_NAME",
+                       "vit_base_patch16_224_develop", "MODEL.PRETRAINED", False, "MODEL.DROP_PATH", 0.0,
+                       "TIMESFORMER.DEPTH", 1, "MODEL.NUM_CLASSES", 778, "DATA.NUM_FRAMES", 2, "DATA.TRAIN_CROP_SIZE", 32,
+                       "B200.PRECISION", "bf16x3", "B200.GRAD_BUCKET_MB", 1, "NUM_GPUS", 2])
+    return c
+
+
+def _setup():
+    for p in (ROOT, HERE, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import shadow_ops
+    from procedurevrl_b200 import ops
+    from procedurevrl_b200.lib.models.vit import VisionTransformer
+    for n in shadow_ops.ALL:
+        setattr(ops, n, getattr(shadow_ops, n))
+    VisionTransformer._require_cuda = False
+
+
+def _model(bank):
+    from procedurevrl_b200.lib.models import MODEL_REGISTRY
+    torch.manual_seed(3)
+    m = MODEL_REGISTRY.get("vit_base_patch16_224_develop")(_small_cfg(bank))
+    with torch.no_grad():
+        for blk in m.model.blocks:
+            torch.nn.init.normal_(blk.temporal_fc.weight, std=0.02)
+        torch.nn.init.normal_(m.model.time_embed, std=0.02)
+    for p in m.parameters():
+        p.requires_grad_(True)
+    return m.train()
+
+
+def _batch():
+    g = torch.Generator().manual_seed(5)
+    return torch.randn(4, 3, 2, 32, 32, generator=g), torch.tensor([1, 50, 300, 700])
+
+
+def _worker(rank, world, port, bank, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(2)
+    _setup()
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from procedurevrl_b200.lib.models.build import wrap_data_parallel
+    m = wrap_data_parallel(_model(bank), _small_cfg(bank))
+    x, y = _batch()
+    shard = slice(rank * 2, rank * 2 + 2)
+    torch.nn.functional.cross_entropy(m(x[shard]), y[shard]).backward()
+    if rank == 0:
+        torch.save({k: p.grad.clone() for k, p in m.module.named_parameters()}, out_path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradients_match_full_batch(gold_dir, tmp_path):
+    bank = os.path.join(gold_dir, "clip_step_emb_coin.pt")
+    out_path = str(tmp_path / "grads.pt")
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(2, port, bank, out_path), nprocs=2, join=True)
+    ddp = torch.load(out_path)
+    _setup()
+    try:
+        m = _model(bank)
+        x, y = _batch()
+        torch.nn.functional.cross_entropy(m(x), y).backward()
+        ref = {k: p.grad for k, p in m.named_parameters()}
+        assert set(ref) == set(ddp)
+        for k in ref:
+            # bf16x3 products are exact to ~2^-17; shard-vs-full differs only by summation order
+            assert (ddp[k] - ref[k]).abs().max().item() <= 1e-4 * ref[k].abs().max().item() + 1e-7, k
+    finally:
+        import importlib
+        from procedurevrl_b200 import ops
+        from procedurevrl_b200.lib.models.vit import VisionTransformer
+        importlib.reload(ops)
+        VisionTransformer._require_cuda = True
