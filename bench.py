@@ -141,7 +141,7 @@ def run_b200(args):
     bank = synthetic_label_bank(os.path.join(tempfile.gettempdir(), f"pvrl_synthetic_step_bank_{os.getpid()}.pt"))
     torch.manual_seed(0)
     cfg = pretrain_cfg(T, args.depth, bank, args.precision)
-    cfg.NUM_GPUS = world
+    cfg.NUM_GPUS = world if args.ddp else 1        # the flat-gradient trainer does its own all-reduce (no DDP wrapper)
     model = build_model(cfg)
     inner = (model.module if hasattr(model, "module") else model).model
     with torch.no_grad():                       # a fresh reference init has all-zero temporal_fc / time_embed
@@ -149,8 +149,6 @@ def run_b200(args):
             torch.nn.init.trunc_normal_(blk.temporal_fc.weight, std=0.02)
         torch.nn.init.trunc_normal_(inner.time_embed, std=0.02)
     model.train()
-    params = [p for p in model.parameters() if p.requires_grad]
-    opt = torch.optim.AdamW(params, lr=5e-5, weight_decay=1e-4, fused=True)     # procedurevrl_adamw.yaml SOLVER
 
     frames_h, meta_h = synthetic_batch(Bv, T, seed=cfg.RNG_SEED + rank)
     frames_pin = frames_h.pin_memory()
@@ -158,13 +156,28 @@ def run_b200(args):
     meta = {k: v.to(dev) for k, v in meta_h.items()}
     clips_per_step = Bv * 9 * world
 
-    def step(fr):
-        pred, teacher, mse = model([fr, meta])
-        loss, _, _ = PF.pretrain_loss(pred, teacher, mse, topk=cfg.TRAIN.TOPK)
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        opt.step()
-        return loss
+    if args.ddp:        # reference-style driver loop: DistributedDataParallel wrapper + per-op dispatch (train_net.py:146-191)
+        params = [p for p in model.parameters() if p.requires_grad]
+        opt = torch.optim.AdamW(params, lr=5e-5, weight_decay=1e-4, fused=True)     # procedurevrl_adamw.yaml SOLVER
+
+        def step(fr):
+            pred, teacher, mse = model([fr, meta])
+            loss, _, _ = PF.pretrain_loss(pred, teacher, mse, topk=cfg.TRAIN.TOPK)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            return loss
+        mode = "ddp-eager"
+    else:               # flat-gradient step, single NCCL all-reduce, optionally replayed from a CUDA graph
+        from procedurevrl_b200.trainer import PretrainStep
+        trainer = PretrainStep(model, cfg, lr=5e-5, weight_decay=1e-4,
+                               process_group=dist.group.WORLD if world > 1 else None, use_graph=not args.no_graph)
+        if not args.no_graph and not args.profile:
+            trainer.capture(frames, meta, warmup=2)
+
+        def step(fr):
+            return trainer(fr, meta)
+        mode = "graph" if trainer.graph is not None else "eager"
 
     # CUDA events around every GEMM launch (the dominant kernel family) for the roofline
     gemm_events, real_gemm = [], ops.gemm
@@ -189,9 +202,9 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ops.gemm = timed_gemm
-    import procedurevrl_b200.engine as eng_mod
-    assert eng_mod.ops is ops
+    graphed = mode == "graph"
+    if not graphed:
+        ops.gemm = timed_gemm
     launches0 = ops.launch_count()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -201,9 +214,21 @@ def run_b200(args):
     t1.record()
     barrier()
     launches = ops.launch_count() - launches0
-    ops.gemm = real_gemm
     ms = t0.elapsed_time(t1)
     clocks = sampler.stop() if rank == 0 else None
+    if graphed:
+        # graph replays launch the recorded kernels without going through the C ABI: count them from one eager step,
+        # which also carries the CUDA events around every GEMM launch (events cannot time nodes inside a graph)
+        ops.gemm = timed_gemm
+        launches0 = ops.launch_count()
+        te0, te1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        te0.record()
+        trainer._eager(frames, meta)
+        te1.record()
+        barrier()
+        launches = (ops.launch_count() - launches0) * args.steps
+        eager_ms = te0.elapsed_time(te1)
+    ops.gemm = real_gemm
     gemm_ms = sum(a.elapsed_time(b) for a, b, _ in gemm_events)
     gemm_flops = sum(f for _, _, f in gemm_events)
     n_gemm = len(gemm_events)
@@ -244,7 +269,7 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "bf16x3", "data": "synthetic",
             "config": {"workload": f"TimeSformer-B {T}x224 HowTo100M stage-2 pretrain step (fwd+KL/MSE loss+bwd+"
                                    f"allreduce+AdamW), {Bv} videos x 9 clips per GPU, DROP_PATH 0.1",
-                       "depth": args.depth, "clips_per_gpu": Bv * 9, "parallelism": f"dp{world}",
+                       "depth": args.depth, "clips_per_gpu": Bv * 9, "parallelism": f"dp{world}", "dispatch": mode,
                        "l2": "per-step working set ~14 GB >> 126 MB L2 (no flush needed)",
                        "loss": round(float(last), 4)},
             "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": frames_pin.numel() * 4 * 1,
@@ -255,7 +280,8 @@ def run_b200(args):
                          "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "TFLOP/s",
                          "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic,
                          "peak_source": f"bf16_tflops_sustained, {peak_src}",
-                         "launches": n_gemm, "gemm_share_of_step": round(gemm_ms / ms, 4),
+                         "launches": n_gemm, "gemm_share_of_step": round(gemm_ms / (eager_ms if graphed else ms), 4),
+                         "timed_in": "one eager step after the graph-replayed timed region" if graphed else "timed region",
                          "step_mfu": round(step_flops / (ms_step / 1e3) / 1e12 / peak, 4)},
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -362,6 +388,8 @@ def main():
     ap.add_argument("--videos-per-gpu", type=int, default=2)        # TRAIN.BATCH_SIZE 16 / NUM_GPUS 8
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="dispatch every kernel from Python instead of replaying a CUDA graph")
+    ap.add_argument("--ddp", action="store_true", help="reference-style DistributedDataParallel wrapper (eager)")
     ap.add_argument("--profile", action="store_true",
                     help="short run for ncu: 1 warm-up + --steps timed steps, no e2e / cpu legs (never a bench value)")
     args = ap.parse_args()

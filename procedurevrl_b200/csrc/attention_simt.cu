@@ -270,7 +270,11 @@ static int attn_fwd_launch(const void* qkv, void* out, float* lse, int n_seq, in
   const int kb = seq < KEY_BLOCK ? seq : KEY_BLOCK;
   const size_t smem = 2 * (size_t)pairs * kb * ROW * sizeof(float);
   auto kern = attn_fwd_kernel<T>;
-  PVRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  static bool configured = false;   // per instantiation; not repeated so launches stay CUDA-graph capturable
+  if (!configured) {
+    PVRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
   const long long n_pairs = (long long)n_seq * H;
   dim3 grid(static_cast<unsigned>((n_pairs + pairs - 1) / pairs), (seq + q_per_pair - 1) / q_per_pair);
   kern<<<grid, pairs * q_per_pair, smem, stream>>>(static_cast<const T*>(qkv), static_cast<T*>(out), lse, n_seq, seq, H,
@@ -285,7 +289,11 @@ static int attn_bwd_launch(const void* qkv, const void* out, const void* dout, c
   const int threads = ((pairs * seq + 31) / 32) * 32;
   const size_t smem = (4 * (size_t)pairs * seq * ROW + 2 * (size_t)pairs * seq) * sizeof(float);
   auto kern = attn_bwd_kernel<T>;
-  PVRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  static bool configured = false;
+  if (!configured) {
+    PVRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
   const long long n_pairs = (long long)n_seq * H;
   kern<<<static_cast<unsigned>((n_pairs + pairs - 1) / pairs), threads, smem, stream>>>(
       static_cast<const T*>(qkv), static_cast<const T*>(out), static_cast<const T*>(dout), lse, static_cast<T*>(dqkv),

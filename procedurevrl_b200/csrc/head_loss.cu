@@ -339,7 +339,11 @@ extern "C" int pvrl_kl_topk_loss(const float* pred, const float* teacher_logits,
   PVRL_CHECK_ARG(topk >= 0 && topk <= TOPK_MAX, "pvrl_kl_topk_loss: topk=%d out of [0, %d]", topk, TOPK_MAX);
   const size_t smem = 2 * (size_t)K * sizeof(float);
   PVRL_CHECK_ARG(smem <= 200 * 1024, "pvrl_kl_topk_loss: K=%d too large for the single-block-per-row kernel", K);
-  PVRL_CUDA(cudaFuncSetAttribute(kl_topk_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  static bool configured = false;
+  if (!configured) {
+    PVRL_CUDA(cudaFuncSetAttribute(kl_topk_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
   kl_topk_loss_kernel<<<M, 256, smem, STREAM>>>(pred, teacher_logits, row_loss, dpred, teacher_out, M, K, topk, gscale);
   return launched("kl_topk_loss_kernel");
 }

@@ -44,6 +44,8 @@ class EncoderEngine:
         self.scale = (embed_dim // num_heads) ** -0.5
         assert embed_dim // num_heads == 64, "kernels are specialised for head_dim 64"
         self.use_tc_attention = True      # tcgen05 spatial attention in bf16 mode (the fp32 parity mode uses CUDA cores)
+        self._wepoch = 0
+        self.grad_sink = None             # optional dict name -> fp32 tensor: backward accumulates straight into it
         self._wcache = {}      # name -> (version, W operand [N, K'], W^T operand [K, N'])
         self.grad_names = self._grad_names()
 
@@ -63,26 +65,33 @@ class EncoderEngine:
     def _weight_ops(self, name):
         """GEMM operand copies of linear weight `name` ([N, K] fp32 master): (W for y = x W^T, W^T for dX)."""
         w = self.p[name]
-        ver = (w._version, w.data_ptr())
+        ver = (w._version, w.data_ptr(), self._wepoch)
         hit = self._wcache.get(name)
         if hit is not None and hit[0] == ver:
             return hit[1], hit[2]
         w2 = w.detach().reshape(w.shape[0], -1)
         N, K = w2.shape
         dev = w2.device
+        mul = 3 if self.x3 else 1
+        if hit is not None and hit[1].device == dev:
+            wb, wt = hit[1], hit[2]                 # refresh in place: operand addresses stay stable (CUDA graphs)
+        else:
+            wb = torch.empty(N, mul * K, device=dev, dtype=torch.bfloat16)
+            wt = torch.empty(K, mul * N, device=dev, dtype=torch.bfloat16)
         if not self.x3:
-            wb = torch.empty(N, K, device=dev, dtype=torch.bfloat16)
-            wt = torch.empty(K, N, device=dev, dtype=torch.bfloat16)
             ops.cast_weight(w2, wb, wt)
         else:
             wt32 = torch.empty(K, N, device=dev, dtype=torch.float32)
             ops.cast_weight(w2, None, wt32)
-            wb = torch.empty(N, 3 * K, device=dev, dtype=torch.bfloat16)
-            wt = torch.empty(K, 3 * N, device=dev, dtype=torch.bfloat16)
             ops.split3(w2.contiguous(), wb, N, K, 1, 1)
             ops.split3(wt32, wt, K, N, 1, 1)
         self._wcache[name] = (ver, wb, wt)
         return wb, wt
+
+    def invalidate_weights(self):
+        """Force the bf16 operand copies to be re-cast on next use (call once per optimizer step when the step is
+        captured in a CUDA graph: the cast kernels must be part of every replay)."""
+        self._wepoch += 1
 
     # ------------------------------------------------------------------------------------------ GEMM helpers
     def _A(self, a, M, K):
@@ -253,12 +262,15 @@ class EncoderEngine:
         dev = dfeat.device
         g = dict(T=T, HW=HW)
         P = self.p
-        sizes = [P[n].numel() for n in self.grad_names]
-        flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
-        G, off = {}, 0
-        for n, sz in zip(self.grad_names, sizes):
-            G[n] = flat[off:off + sz].view(P[n].shape)
-            off += sz
+        if self.grad_sink is not None:
+            G = self.grad_sink                     # kernels accumulate (+=) into the caller's gradient buffers
+        else:
+            sizes = [P[n].numel() for n in self.grad_names]
+            flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+            G, off = {}, 0
+            for n, sz in zip(self.grad_names, sizes):
+                G[n] = flat[off:off + sz].view(P[n].shape)
+                off += sz
 
         dx = torch.zeros(Bc, S, D, device=dev, dtype=torch.float32)
         ops.layernorm_bwd(dfeat.contiguous(), st["x_last"], P[self.pre + "norm.weight"], st["st_f"], dx,
@@ -355,6 +367,8 @@ class EncoderFunction(torch.autograd.Function):
             raise RuntimeError("EncoderFunction.backward called without saved activations")
         G = eng.backward(ctx.saved, dfeat)
         ctx.saved = None
+        if eng.grad_sink is not None:              # already accumulated in place
+            return (None, None, None, None) + (None,) * len(eng.grad_names)
         return (None, None, None, None) + tuple(G[n] for n in eng.grad_names)
 
 

@@ -292,7 +292,8 @@ class VisionTransformer(nn.Module):
             if self.fixed_rand_inds is not None:
                 rand_inds = self.fixed_rand_inds.to(x.device)[:batch_size * self.order_recog_batch]
             else:
-                rand_inds = torch.randperm(x.shape[0], device=x.device)[:batch_size * self.order_recog_batch]
+                # uniform random permutation (vit.py:345) drawn as argsort of uniforms: sync-free and capturable
+                rand_inds = torch.rand(x.shape[0], device=x.device).argsort()[:batch_size * self.order_recog_batch]
             x = torch.cat((x[rand_inds], inter_pred), dim=0)
             teacher_x = torch.cat((teacher_x[rand_inds], inter_teacher), dim=0)
             return x, teacher_x, mse_loss
