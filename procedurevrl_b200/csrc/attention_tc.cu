@@ -37,6 +37,18 @@ __device__ __forceinline__ void store_row64_bf16(__nv_bfloat16* dst, const float
   }
 }
 
+__device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const float* v) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 u;
+    u.x = pack_bf16x2(v[8 * i], v[8 * i + 1]);
+    u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+    u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+    u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+    reinterpret_cast<uint4*>(dst)[i] = u;
+  }
+}
+
 // =====================================================================================================
 // forward: one CTA per (sequence, head, 128-query tile).  160 threads: warps 0-3 softmax / epilogue (one
 // query row per thread), warp 4 = TMA + MMA issuer.  smem: [Q | K] (overlaid by P once S is done) + V.
@@ -155,12 +167,16 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 // =====================================================================================================
-// backward: one CTA per (sequence, head); Q, K, V, dO resident (256 rows each), loop over 128-key tiles kt
-// and 128-query tiles mt:   S = Q K^T, dP = dO V^T  ->  P = exp(S*scale - lse), dS = P*(dP - delta)*scale  ->
+// backward: one CTA per (sequence, head); Q, K, V, dO resident (two 128-row tiles each), loop over 128-key tiles
+// kt and 128-query tiles mt:   S = Q K^T, dP = dO V^T  ->  P = exp(S*scale - lse), dS = P*(dP - delta)*scale  ->
 // dQ_mt += dS K,  dV_kt += P^T dO,  dK_kt += dS^T Q.   TMEM: S 0..127 | dP 128..255 | dK 256..319 |
 // dV 320..383 | dQ_0 384..447 | dQ_1 448..511.
+// 288 threads: warps 0-7 = softmax-gradient threads (TMEM quarter = warp % 4, column half = warp / 4),
+// warp 8 = TMA + MMA issuer.  The S/dP MMAs of iteration it+1 are issued before the dQ/dV/dK MMAs of iteration
+// it, so the threads' TMEM loads and exp/FMA work overlap the tensor-core work of the previous tile pair.
 // =====================================================================================================
-__global__ void __launch_bounds__(160, 1)
+constexpr int BWD_THREADS = 288;
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                    const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
                    const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, int seq, int H, float scale) {
@@ -173,22 +189,24 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   uint8_t* pP = smem + 8 * TILE_BYTES;
   uint8_t* pdS = smem + 10 * TILE_BYTES;
   const uint32_t bars = base + 12 * TILE_BYTES;
-  const uint32_t bar_load = bars, bar_sdp = bars + 8, bar_pds = bars + 16, bar_mma2 = bars + 24;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 12 * TILE_BYTES + 32);
+  const uint32_t bar_load0 = bars, bar_load1 = bars + 8, bar_sdp = bars + 16, bar_pds = bars + 24, bar_mma2 = bars + 32;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 12 * TILE_BYTES + 48);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = blockIdx.x;
   const int s_idx = pair / H, h = pair % H;
   const int C = H * 64;
   const int n_tiles = (seq + 127) / 128;   // 1 or 2 (seq <= 256)
+  const int n_iter = n_tiles * n_tiles;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQKV);
       tma_prefetch_desc(&tmDO);
-      mbar_init(bar_load, 1);
+      mbar_init(bar_load0, 1);
+      mbar_init(bar_load1, 1);
       mbar_init(bar_sdp, 1);
-      mbar_init(bar_pds, 128);
+      mbar_init(bar_pds, 256);
       mbar_init(bar_mma2, 1);
       fence_mbar_init();
     }
@@ -201,52 +219,71 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   const uint32_t tmem = *tmem_slot;
   constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DK = 256, COL_DV = 320, COL_DQ = 384;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
-      mbar_expect_tx(bar_load, 8 * TILE_BYTES);
-      tma_load_3d(sQ, &tmQKV, bar_load, h * 64, 0, s_idx);
-      tma_load_3d(sK, &tmQKV, bar_load, C + h * 64, 0, s_idx);
-      tma_load_3d(sV, &tmQKV, bar_load, 2 * C + h * 64, 0, s_idx);
-      tma_load_3d(sdO, &tmDO, bar_load, h * 64, 0, s_idx);
-      mbar_wait(bar_load, 0);
-      tc_fence_after();
+      // tile 0 of every operand first (all the first iteration needs), tile 1 behind it
+      mbar_expect_tx(bar_load0, 4 * TILE_BYTES);
+      tma_load_3d(sQ, &tmQKV, bar_load0, h * 64, 0, s_idx);
+      tma_load_3d(sK, &tmQKV, bar_load0, C + h * 64, 0, s_idx);
+      tma_load_3d(sV, &tmQKV, bar_load0, 2 * C + h * 64, 0, s_idx);
+      tma_load_3d(sdO, &tmDO, bar_load0, h * 64, 0, s_idx);
+      if (n_tiles > 1) {
+        mbar_expect_tx(bar_load1, 4 * TILE_BYTES);
+        tma_load_3d(sQ + TILE_BYTES, &tmQKV, bar_load1, h * 64, 128, s_idx);
+        tma_load_3d(sK + TILE_BYTES, &tmQKV, bar_load1, C + h * 64, 128, s_idx);
+        tma_load_3d(sV + TILE_BYTES, &tmQKV, bar_load1, 2 * C + h * 64, 128, s_idx);
+        tma_load_3d(sdO + TILE_BYTES, &tmDO, bar_load1, h * 64, 128, s_idx);
+      }
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);
       constexpr uint32_t idesc_dkv = make_idesc_bf16(128, 64, 1, 1);
-      uint32_t it = 0;
-      for (int kt = 0; kt < n_tiles; ++kt)
-        for (int mt = 0; mt < n_tiles; ++mt, ++it) {
-          const uint32_t q_t = sQ + mt * TILE_BYTES, do_t = sdO + mt * TILE_BYTES;
-          const uint32_t k_t = sK + kt * TILE_BYTES, v_t = sV + kt * TILE_BYTES;
+      auto issue_sdp = [&](int kt, int mt) {
+        const uint32_t q_t = sQ + mt * TILE_BYTES, do_t = sdO + mt * TILE_BYTES;
+        const uint32_t k_t = sK + kt * TILE_BYTES, v_t = sV + kt * TILE_BYTES;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem + COL_S, make_smem_desc(q_t + k * 32, 16, 1024), make_smem_desc(k_t + k * 32, 16, 1024),
-                      idesc_s, k > 0);
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem + COL_S, make_smem_desc(q_t + k * 32, 16, 1024), make_smem_desc(k_t + k * 32, 16, 1024),
+                    idesc_s, k > 0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem + COL_DP, make_smem_desc(do_t + k * 32, 16, 1024), make_smem_desc(v_t + k * 32, 16, 1024),
-                      idesc_s, k > 0);
-          umma_commit(bar_sdp);
-          mbar_wait(bar_pds, it & 1);
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < 8; ++k)   // dQ_mt += dS[q, keys] K[keys, d]
-            umma_bf16(tmem + COL_DQ + mt * 64, make_smem_desc(sdS + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024),
-                      make_smem_desc(k_t + k * 2048, TILE_BYTES, 1024), idesc_dq, (kt > 0 || k > 0));
-#pragma unroll
-          for (int k = 0; k < 8; ++k)   // dV_kt += P^T[keys, q] dO[q, d]
-            umma_bf16(tmem + COL_DV, make_smem_desc(sP + k * 2048, TILE_BYTES, 1024),
-                      make_smem_desc(do_t + k * 2048, TILE_BYTES, 1024), idesc_dkv, (mt > 0 || k > 0));
-#pragma unroll
-          for (int k = 0; k < 8; ++k)   // dK_kt += dS^T[keys, q] Q[q, d]
-            umma_bf16(tmem + COL_DK, make_smem_desc(sdS + k * 2048, TILE_BYTES, 1024),
-                      make_smem_desc(q_t + k * 2048, TILE_BYTES, 1024), idesc_dkv, (mt > 0 || k > 0));
-          umma_commit(bar_mma2);
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem + COL_DP, make_smem_desc(do_t + k * 32, 16, 1024), make_smem_desc(v_t + k * 32, 16, 1024),
+                    idesc_s, k > 0);
+        umma_commit(bar_sdp);
+      };
+      mbar_wait(bar_load0, 0);
+      tc_fence_after();
+      issue_sdp(0, 0);
+      for (int it = 0; it < n_iter; ++it) {
+        const int kt = it / n_tiles, mt = it % n_tiles;
+        const uint32_t q_t = sQ + mt * TILE_BYTES, do_t = sdO + mt * TILE_BYTES, k_t = sK + kt * TILE_BYTES;
+        mbar_wait(bar_pds, it & 1);      // P / dS of this iteration are in smem, S / dP columns are free again
+        tc_fence_after();
+        if (it + 1 < n_iter) {
+          if (it == 0) {                 // first touch of the second tiles
+            mbar_wait(bar_load1, 0);
+            tc_fence_after();
+          }
+          issue_sdp((it + 1) / n_tiles, (it + 1) % n_tiles);
         }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dQ_mt += dS[q, keys] K[keys, d]
+          umma_bf16(tmem + COL_DQ + mt * 64, make_smem_desc(sdS + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024),
+                    make_smem_desc(k_t + k * 2048, TILE_BYTES, 1024), idesc_dq, (kt > 0 || k > 0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dV_kt += P^T[keys, q] dO[q, d]
+          umma_bf16(tmem + COL_DV, make_smem_desc(sP + k * 2048, TILE_BYTES, 1024),
+                    make_smem_desc(do_t + k * 2048, TILE_BYTES, 1024), idesc_dkv, (mt > 0 || k > 0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dK_kt += dS^T[keys, q] Q[q, d]
+          umma_bf16(tmem + COL_DK, make_smem_desc(sdS + k * 2048, TILE_BYTES, 1024),
+                    make_smem_desc(q_t + k * 2048, TILE_BYTES, 1024), idesc_dkv, (mt > 0 || k > 0));
+        umma_commit(bar_mma2);
+      }
     }
   } else {
-    const int r = warp * 32 + lane;
-    const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    const int quarter = warp & 3, half = warp >> 2;
+    const int r = quarter * 32 + lane;
+    const uint32_t trow = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
     const long long pitch = 3LL * C;
     // per-row constants for both query tiles: lse and delta = dO . O
     float lse_l2[2], delta[2];
@@ -273,83 +310,71 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       }
     }
     const float sl2 = scale * LOG2E;
-    uint32_t it = 0;
-    for (int kt = 0; kt < n_tiles; ++kt)
-      for (int mt = 0; mt < n_tiles; ++mt, ++it) {
-        mbar_wait(bar_sdp, it & 1);
-        tc_fence_after();
-        if (it > 0) mbar_wait(bar_mma2, (it - 1) & 1);   // previous P / dS tiles fully consumed by the MMAs
-        const bool qv = qvalid[mt];
-        const float l2 = lse_l2[mt], dl = delta[mt];
+    for (int it = 0; it < n_iter; ++it) {
+      const int kt = it / n_tiles, mt = it % n_tiles;
+      mbar_wait(bar_sdp, it & 1);
+      tc_fence_after();
+      const bool qv = qvalid[mt];
+      const float l2 = lse_l2[mt], dl = delta[mt];
 #pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t rs[32], rp[32];
-          tmem_ld32(trow + COL_S + c0, rs);
-          tmem_ld32(trow + COL_DP + c0, rp);
-          tmem_ld_wait();
-          float p[32], ds[32];
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c0 = half * 64 + cc * 32;
+        uint32_t rs[32], rp[32];
+        tmem_ld32(trow + COL_S + c0, rs);
+        tmem_ld32(trow + COL_DP + c0, rp);
+        tmem_ld_wait();
+        float p[32], ds[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const bool v = qv && (kt * 128 + c0 + j < seq);
-            p[j] = v ? exp2f(__uint_as_float(rs[j]) * sl2 - l2) : 0.f;
-            ds[j] = v ? p[j] * (__uint_as_float(rp[j]) - dl) * scale : 0.f;
-          }
-          const int tile = c0 >> 6, piece0 = (c0 & 63) >> 3;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            st_piece(pP + tile * TILE_BYTES, r, piece0 + q, p + 8 * q);
-            st_piece(pdS + tile * TILE_BYTES, r, piece0 + q, ds + 8 * q);
-          }
+        for (int j = 0; j < 32; ++j) {
+          const bool v = qv && (kt * 128 + c0 + j < seq);
+          p[j] = v ? exp2f(__uint_as_float(rs[j]) * sl2 - l2) : 0.f;
+          ds[j] = v ? p[j] * (__uint_as_float(rp[j]) - dl) * scale : 0.f;
         }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        mbar_arrive(bar_pds);
-        if (mt == n_tiles - 1) {   // key tile finished: dK_kt / dV_kt rows (this thread = key kt*128 + r)
-          mbar_wait(bar_mma2, it & 1);
-          tc_fence_after();
-          const int kj = kt * 128 + r;
-          uint32_t raw[32];
-          float v[64];
-          tmem_ld32(trow + COL_DK, raw);
-          tmem_ld_wait();
+        if (cc == 0 && it > 0) mbar_wait(bar_mma2, (it - 1) & 1);   // previous P / dS tiles consumed by the MMAs
+        const int tile = c0 >> 6, piece0 = (c0 & 63) >> 3;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-          tmem_ld32(trow + COL_DK + 32, raw);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[32 + j] = __uint_as_float(raw[j]);
-          if (kj < seq) store_row64_bf16(dqkv + ((long long)s_idx * seq + kj) * pitch + C + h * 64, v);
-          tmem_ld32(trow + COL_DV, raw);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-          tmem_ld32(trow + COL_DV + 32, raw);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[32 + j] = __uint_as_float(raw[j]);
-          if (kj < seq) store_row64_bf16(dqkv + ((long long)s_idx * seq + kj) * pitch + 2 * C + h * 64, v);
-          tc_fence_before();
+        for (int q = 0; q < 4; ++q) {
+          st_piece(pP + tile * TILE_BYTES, r, piece0 + q, p + 8 * q);
+          st_piece(pdS + tile * TILE_BYTES, r, piece0 + q, ds + 8 * q);
         }
       }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_pds);
+      if (mt == n_tiles - 1) {   // key tile finished: dK_kt / dV_kt, this thread = key kt*128 + r, 32 of the 64 dims
+        mbar_wait(bar_mma2, it & 1);
+        tc_fence_after();
+        const int kj = kt * 128 + r;
+        uint32_t raw[32];
+        float v[32];
+        tmem_ld32(trow + COL_DK + half * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+        if (kj < seq) store_row32_bf16(dqkv + ((long long)s_idx * seq + kj) * pitch + C + h * 64 + half * 32, v);
+        tmem_ld32(trow + COL_DV + half * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+        if (kj < seq) store_row32_bf16(dqkv + ((long long)s_idx * seq + kj) * pitch + 2 * C + h * 64 + half * 32, v);
+        tc_fence_before();
+      }
+    }
     // dQ tiles (the last bar_mma2 wait above covers every MMA)
     for (int mt = 0; mt < n_tiles; ++mt) {
       const int qi = mt * 128 + r;
       uint32_t raw[32];
-      float v[64];
-      tmem_ld32(trow + COL_DQ + mt * 64, raw);
+      float v[32];
+      tmem_ld32(trow + COL_DQ + mt * 64 + half * 32, raw);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-      tmem_ld32(trow + COL_DQ + mt * 64 + 32, raw);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[32 + j] = __uint_as_float(raw[j]);
-      if (qi < seq) store_row64_bf16(dqkv + ((long long)s_idx * seq + qi) * pitch + h * 64, v);
+      if (qi < seq) store_row32_bf16(dqkv + ((long long)s_idx * seq + qi) * pitch + h * 64 + half * 32, v);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<512>(tmem);
+  if (warp == 8) tmem_dealloc<512>(tmem);
 }
 
 // 3-D bf16 tensor map over a row-major [n_seq, seq, cols] view, box [1, box_rows, 64], 128B swizzle, zero OOB fill.
@@ -401,15 +426,15 @@ extern "C" int pvrl_attn_tc_bwd(const void* qkv, const void* out, const void* do
   PVRL_CHECK_ARG(seq > 0 && seq <= 256, "pvrl_attn_tc_bwd: seq=%d must be in [1, 256]", seq);
   CUtensorMap tqkv, tdo;
   int rc;
-  if ((rc = make_tmap_3d(&tqkv, qkv, 3ull * H * 64, seq, n_seq, 256))) return rc;
-  if ((rc = make_tmap_3d(&tdo, dout, 1ull * H * 64, seq, n_seq, 256))) return rc;
+  if ((rc = make_tmap_3d(&tqkv, qkv, 3ull * H * 64, seq, n_seq, 128))) return rc;
+  if ((rc = make_tmap_3d(&tdo, dout, 1ull * H * 64, seq, n_seq, 128))) return rc;
   const size_t smem = 12 * TILE_BYTES + 64 + 1024;
   static bool configured = false;
   if (!configured) {
     PVRL_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  attn_tc_bwd_kernel<<<n_seq * H, 160, smem, static_cast<cudaStream_t>(stream)>>>(
+  attn_tc_bwd_kernel<<<n_seq * H, BWD_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
       tqkv, tdo, static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), lse,
       static_cast<__nv_bfloat16*>(dqkv), seq, H, scale);
   return launched("attn_tc_bwd_kernel");

@@ -119,73 +119,92 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ x_cl
 }
 
 // dx[src(m)] += rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * w;  dw += dy * xhat;  db += dy.
-template <typename InT>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+// One warp per row, NVEC float4 per lane (D = 128 * NVEC); per-lane column sums of dy*xhat / dy live in registers
+// across the rows a warp visits and are folded block-wide through shared memory, then one atomicAdd per column.
+template <typename InT, int NVEC>
+__global__ void __launch_bounds__(LN_WARPS * 32, 2)
 layernorm_bwd_kernel(const InT* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ x_cls,
                      const float* __restrict__ w, const float* __restrict__ stats, float* __restrict__ dx,
-                     float* __restrict__ dw, float* __restrict__ db, int M, int D, int map, Geom g) {
-  extern __shared__ float sacc[];  // [2][D]
+                     float* __restrict__ dw, float* __restrict__ db, int M, int map, Geom g) {
+  constexpr int D = NVEC * 128;
+  __shared__ float sacc[2 * D];
   for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nvec = D >> 7;
-  float4 aw[LN_MAX_VEC], ab[LN_MAX_VEC], wv[LN_MAX_VEC];
+  float4 aw[NVEC], ab[NVEC];
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
-    aw[i] = make_float4(0.f, 0.f, 0.f, 0.f), ab[i] = aw[i];
-    if (i < nvec) wv[i] = __ldg(reinterpret_cast<const float4*>(w) + i * 32 + lane);
-  }
+  for (int i = 0; i < NVEC; ++i) aw[i] = make_float4(0.f, 0.f, 0.f, 0.f), ab[i] = aw[i];
   for (int m = blockIdx.x * LN_WARPS + warp; m < M; m += gridDim.x * LN_WARPS) {
     const long long r = map_row(map, m, g);
     const bool cls = r < 0;
     const long long xr = cls ? ((-r - 1) / g.T) * (long long)g.S : r;
     const float* xp = (cls ? x_cls : x) + xr * D;
     const float2 st = reinterpret_cast<const float2*>(stats)[m];
-    float4 xh[LN_MAX_VEC], gg[LN_MAX_VEC];
+    float4 xh[NVEC], gg[NVEC];
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {   // all loads of the row in flight before any use
+      xh[i] = __ldg(reinterpret_cast<const float4*>(xp) + i * 32 + lane);
+      gg[i] = load4<InT>(dy + (long long)m * D + (i * 32 + lane) * 4);
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i)
-      if (i < nvec) {
-        const float4 xv = __ldg(reinterpret_cast<const float4*>(xp) + i * 32 + lane);
-        const float4 d = load4<InT>(dy + (long long)m * D + (i * 32 + lane) * 4);
-        xh[i] = make_float4((xv.x - st.x) * st.y, (xv.y - st.x) * st.y, (xv.z - st.x) * st.y, (xv.w - st.x) * st.y);
-        gg[i] = make_float4(d.x * wv[i].x, d.y * wv[i].y, d.z * wv[i].z, d.w * wv[i].w);
-        s1 += gg[i].x + gg[i].y + gg[i].z + gg[i].w;
-        s2 += gg[i].x * xh[i].x + gg[i].y * xh[i].y + gg[i].z * xh[i].z + gg[i].w * xh[i].w;
-        aw[i].x += d.x * xh[i].x, aw[i].y += d.y * xh[i].y, aw[i].z += d.z * xh[i].z, aw[i].w += d.w * xh[i].w;
-        ab[i].x += d.x, ab[i].y += d.y, ab[i].z += d.z, ab[i].w += d.w;
-      }
-    const float c1 = warp_sum(s1) / D, c2 = warp_sum(s2) / D;
+    for (int i = 0; i < NVEC; ++i) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w) + i * 32 + lane);
+      const float4 d = gg[i];
+      xh[i] = make_float4((xh[i].x - st.x) * st.y, (xh[i].y - st.x) * st.y, (xh[i].z - st.x) * st.y,
+                          (xh[i].w - st.x) * st.y);
+      aw[i].x = fmaf(d.x, xh[i].x, aw[i].x), aw[i].y = fmaf(d.y, xh[i].y, aw[i].y);
+      aw[i].z = fmaf(d.z, xh[i].z, aw[i].z), aw[i].w = fmaf(d.w, xh[i].w, aw[i].w);
+      ab[i].x += d.x, ab[i].y += d.y, ab[i].z += d.z, ab[i].w += d.w;
+      gg[i] = make_float4(d.x * wv.x, d.y * wv.y, d.z * wv.z, d.w * wv.w);
+      s1 += gg[i].x + gg[i].y + gg[i].z + gg[i].w;
+      s2 += gg[i].x * xh[i].x + gg[i].y * xh[i].y + gg[i].z * xh[i].z + gg[i].w * xh[i].w;
+    }
+    const float c1 = warp_sum(s1) * (1.0f / D), c2 = warp_sum(s2) * (1.0f / D);
     float* dp = dx + xr * D;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i)
-      if (i < nvec) {
-        const float4 o = make_float4(st.y * (gg[i].x - c1 - xh[i].x * c2), st.y * (gg[i].y - c1 - xh[i].y * c2),
-                                     st.y * (gg[i].z - c1 - xh[i].z * c2), st.y * (gg[i].w - c1 - xh[i].w * c2));
-        float* p = dp + (i * 32 + lane) * 4;
-        if (cls) {  // T frames of one clip share the cls row (vit.py:138-140)
-          atomicAdd(p, o.x), atomicAdd(p + 1, o.y), atomicAdd(p + 2, o.z), atomicAdd(p + 3, o.w);
-        } else {
-          float4 cur = *reinterpret_cast<float4*>(p);
-          cur.x += o.x, cur.y += o.y, cur.z += o.z, cur.w += o.w;
-          *reinterpret_cast<float4*>(p) = cur;
-        }
+    for (int i = 0; i < NVEC; ++i) {
+      const float4 o = make_float4(st.y * (gg[i].x - c1 - xh[i].x * c2), st.y * (gg[i].y - c1 - xh[i].y * c2),
+                                   st.y * (gg[i].z - c1 - xh[i].z * c2), st.y * (gg[i].w - c1 - xh[i].w * c2));
+      float* p = dp + (i * 32 + lane) * 4;
+      if (cls) {  // T frames of one clip share the cls row (vit.py:138-140)
+        atomicAdd(p, o.x), atomicAdd(p + 1, o.y), atomicAdd(p + 2, o.z), atomicAdd(p + 3, o.w);
+      } else {
+        float4 cur = *reinterpret_cast<float4*>(p);
+        cur.x += o.x, cur.y += o.y, cur.z += o.z, cur.w += o.w;
+        *reinterpret_cast<float4*>(p) = cur;
       }
+    }
   }
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i)
-    if (i < nvec) {
-      const int c = (i * 32 + lane) * 4;
-      atomicAdd(&sacc[c], aw[i].x), atomicAdd(&sacc[c + 1], aw[i].y), atomicAdd(&sacc[c + 2], aw[i].z),
-          atomicAdd(&sacc[c + 3], aw[i].w);
-      atomicAdd(&sacc[D + c], ab[i].x), atomicAdd(&sacc[D + c + 1], ab[i].y), atomicAdd(&sacc[D + c + 2], ab[i].z),
-          atomicAdd(&sacc[D + c + 3], ab[i].w);
-    }
+  for (int i = 0; i < NVEC; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    atomicAdd(&sacc[c], aw[i].x), atomicAdd(&sacc[c + 1], aw[i].y), atomicAdd(&sacc[c + 2], aw[i].z),
+        atomicAdd(&sacc[c + 3], aw[i].w);
+    atomicAdd(&sacc[D + c], ab[i].x), atomicAdd(&sacc[D + c + 1], ab[i].y), atomicAdd(&sacc[D + c + 2], ab[i].z),
+        atomicAdd(&sacc[D + c + 3], ab[i].w);
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < D; i += blockDim.x) {
     if (dw != nullptr) atomicAdd(dw + i, sacc[i]);
     if (db != nullptr) atomicAdd(db + i, sacc[D + i]);
   }
+}
+
+template <typename InT>
+int layernorm_bwd_launch(const void* dy, const float* x, const float* x_cls, const float* w, const float* stats,
+                         float* dx, float* dw, float* db, int M, int D, int map, Geom gg, cudaStream_t stream) {
+  int grid = (M + LN_WARPS - 1) / LN_WARPS;
+  if (grid > 148 * 4) grid = 148 * 4;
+  const InT* d = static_cast<const InT*>(dy);
+  switch (D / 128) {
+    case 2: layernorm_bwd_kernel<InT, 2><<<grid, LN_WARPS * 32, 0, stream>>>(d, x, x_cls, w, stats, dx, dw, db, M, map, gg); break;
+    case 4: layernorm_bwd_kernel<InT, 4><<<grid, LN_WARPS * 32, 0, stream>>>(d, x, x_cls, w, stats, dx, dw, db, M, map, gg); break;
+    case 6: layernorm_bwd_kernel<InT, 6><<<grid, LN_WARPS * 32, 0, stream>>>(d, x, x_cls, w, stats, dx, dw, db, M, map, gg); break;
+    case 8: layernorm_bwd_kernel<InT, 8><<<grid, LN_WARPS * 32, 0, stream>>>(d, x, x_cls, w, stats, dx, dw, db, M, map, gg); break;
+    default: return fail(-1, "pvrl_layernorm_bwd: D=%d not in {256, 512, 768, 1024}", D);
+  }
+  return launched("layernorm_bwd_kernel");
 }
 
 // ---------------------------------------------------------------------------------------- gather + cast
@@ -370,16 +389,9 @@ extern "C" int pvrl_layernorm_bwd(const void* dy, int32_t dy_dtype, const float*
   PVRL_CHECK_ARG(D % 128 == 0 && D <= 128 * LN_MAX_VEC, "pvrl_layernorm_bwd: D=%d must be a multiple of 128, <= 1024", D);
   PVRL_CHECK_ARG(map != PVRL_MAP_SPATIAL || x_cls != nullptr, "pvrl_layernorm_bwd: MAP_SPATIAL needs x_cls");
   const Geom gg(g.T > 0 ? g.T : 1, g.HW > 0 ? g.HW : 1);
-  int grid = (M + LN_WARPS - 1) / LN_WARPS;
-  if (grid > 148 * 4) grid = 148 * 4;
-  const size_t smem = 2 * D * sizeof(float);
-  if (dy_dtype == PVRL_F32)
-    layernorm_bwd_kernel<float><<<grid, LN_WARPS * 32, smem, STREAM>>>(static_cast<const float*>(dy), x, x_cls, w,
-                                                                        stats, dx, dw, db, M, D, map, gg);
-  else
-    layernorm_bwd_kernel<__nv_bfloat16><<<grid, LN_WARPS * 32, smem, STREAM>>>(
-        static_cast<const __nv_bfloat16*>(dy), x, x_cls, w, stats, dx, dw, db, M, D, map, gg);
-  return launched("layernorm_bwd_kernel");
+  return dy_dtype == PVRL_F32
+             ? layernorm_bwd_launch<float>(dy, x, x_cls, w, stats, dx, dw, db, M, D, map, gg, STREAM)
+             : layernorm_bwd_launch<__nv_bfloat16>(dy, x, x_cls, w, stats, dx, dw, db, M, D, map, gg, STREAM);
 }
 
 extern "C" int pvrl_gather_cast(const float* src, void* out, int32_t out_dtype, const float* rowscale, int32_t rs_div,

@@ -149,6 +149,25 @@ __device__ __forceinline__ void epilogue_row(const GemmArgs& p, int m, int n0, f
   store_row32<OutT>(reinterpret_cast<OutT*>(p.out) + orow * p.ldo + n0, acc);
 }
 
+// tile index -> (m block, n block, k split).  NT: n fastest, so the CTAs of a wave share A tiles through L2 and the
+// (small) weight matrix stays resident.  TN (dW, split-K): the k split is the SLOWEST index, so at any time the
+// resident CTAs cover all output tiles of one or two contraction slices and every slice of dY / X is fetched from
+// HBM once instead of once per output tile.
+template <bool TN>
+__device__ __forceinline__ void decode_tile(int tile, int m_tiles, int n_tiles, int k_splits, int& m_blk, int& n_blk,
+                                            int& ks) {
+  if (TN) {
+    const int per = m_tiles * n_tiles;
+    ks = tile / per;
+    const int rest = tile - ks * per;
+    n_blk = rest % n_tiles, m_blk = rest / n_tiles;
+  } else {
+    ks = tile % k_splits;
+    const int rest = tile / k_splits;
+    n_blk = rest % n_tiles, m_blk = rest / n_tiles;
+  }
+}
+
 template <int EPI, typename OutT, bool TN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
@@ -200,9 +219,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int ks = tile % p.k_splits;
-        const int rest = tile / p.k_splits;
-        const int n_blk = rest % n_tiles, m_blk = rest / n_tiles;
+        int m_blk, n_blk, ks;
+        decode_tile<TN>(tile, m_tiles, n_tiles, p.k_splits, m_blk, n_blk, ks);
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(num_kb, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -237,7 +255,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int ks = tile % p.k_splits;
+        int m_blk, n_blk, ks;
+        decode_tile<TN>(tile, m_tiles, n_tiles, p.k_splits, m_blk, n_blk, ks);
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(num_kb, kb0 + p.kb_per_split);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -268,8 +287,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int rest = tile / p.k_splits;
-      const int n_blk = rest % n_tiles, m_blk = rest / n_tiles;
+      int m_blk, n_blk, ks;
+      decode_tile<TN>(tile, m_tiles, n_tiles, p.k_splits, m_blk, n_blk, ks);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int m = m_blk * BM + quarter * 32 + lane;
