@@ -6,6 +6,7 @@
 // Covers every dense contraction of the TimeSformer block (SURVEY.md 2a K1,K4,K6,K8,K10 and their
 // backward K15): "NT" for y = x W^T (+ dX through pre-transposed weights) and "TN" (MN-major operands,
 // split-K + fp32 red.add) for dW = dY^T X.
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -15,14 +16,19 @@
 namespace pvrl {
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int BM = 128, BK = 64, STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;          // 16 KB
-constexpr int B_BYTES = BN * BK * 2;          // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int CHUNK_BYTES = 64 * BK * 2;      // one 64-wide MN chunk of a TN tile (8 KB)
 constexpr int NUM_THREADS = 384;
 constexpr int NUM_EPI_WARPS = 8;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 128 /*barriers*/;
+constexpr int EPI_STAGE_BYTES = 32 * 128;     // per epilogue warp: 32 rows x 32 fp32 columns, 16 B pieces xor-swizzled
+template <int BN>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 2;                // 32 KB (BN 256) / 24 KB (BN 192)
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = PIPE_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align*/ + 128 /*barriers*/;
+};
 
 struct GemmArgs {
   int M, N, K;
@@ -42,111 +48,97 @@ struct GemmArgs {
   Geom g;
 };
 
-// ---- epilogue helpers: one thread owns one output row and 32 consecutive columns -------------------
-template <typename OutT>
-__device__ __forceinline__ void store_row32(OutT* dst, const float (&v)[32]);
+// ---- epilogue helpers --------------------------------------------------------------------------------
+// The accumulator leaves TMEM one row per thread (tcgen05.ld 32x32b); a row-per-thread global access would touch 32
+// different 128-byte lines per instruction, so every 32x32 fp32 block is transposed through a 4 KB per-warp staging
+// buffer first: afterwards a lane owns 4 consecutive columns of one row, 8 lanes cover a full 128-byte line and every
+// global load / store / red of the epilogue (output, residual, DGELU pre-activations) is coalesced.
+template <typename T>
+__device__ __forceinline__ void st_vec4(T* dst, const float4& v);
 template <>
-__device__ __forceinline__ void store_row32<float>(float* dst, const float (&v)[32]) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-    reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+__device__ __forceinline__ void st_vec4<float>(float* dst, const float4& v) {
+  *reinterpret_cast<float4*>(dst) = v;
 }
 template <>
-__device__ __forceinline__ void store_row32<__nv_bfloat16>(__nv_bfloat16* dst, const float (&v)[32]) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint4 u;
-    u.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
-    u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-    u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-    u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-    reinterpret_cast<uint4*>(dst)[j] = u;
-  }
+__device__ __forceinline__ void st_vec4<__nv_bfloat16>(__nv_bfloat16* dst, const float4& v) {
+  uint2 u;
+  u.x = pack_bf16x2(v.x, v.y);
+  u.y = pack_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(dst) = u;
 }
 template <typename T>
-__device__ __forceinline__ void load_row32(const T* src, float (&v)[32]);
+__device__ __forceinline__ float4 ld_vec4(const T* src);
 template <>
-__device__ __forceinline__ void load_row32<float>(const float* src, float (&v)[32]) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float4 f = __ldg(reinterpret_cast<const float4*>(src) + j);
-    v[4 * j] = f.x, v[4 * j + 1] = f.y, v[4 * j + 2] = f.z, v[4 * j + 3] = f.w;
-  }
+__device__ __forceinline__ float4 ld_vec4<float>(const float* src) {
+  return __ldg(reinterpret_cast<const float4*>(src));
 }
 template <>
-__device__ __forceinline__ void load_row32<__nv_bfloat16>(const __nv_bfloat16* src, float (&v)[32]) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + j);
-    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-    v[8 * j] = a.x, v[8 * j + 1] = a.y, v[8 * j + 2] = b.x, v[8 * j + 3] = b.y;
-    v[8 * j + 4] = c.x, v[8 * j + 5] = c.y, v[8 * j + 6] = d.x, v[8 * j + 7] = d.y;
+__device__ __forceinline__ float4 ld_vec4<__nv_bfloat16>(const __nv_bfloat16* src) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(src));
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w; }
+__device__ __forceinline__ void mul4(float4& a, float s) { a.x *= s, a.y *= s, a.z *= s, a.w *= s; }
+
+// what the transposed epilogue needs to know about one output row (computed once per tile by the lane that owns the
+// row in TMEM order, then handed to the lanes that own it in the transposed order by warp shuffles)
+struct RowCtx {
+  int orow;         // residual-stream / output row (map_row); < 0 = cls row of a spatial sequence
+  float rs;         // DropPath factor of the row (1 when none)
+};
+
+// "side" operand of one 4-column piece: the fp32 residual (RESID) or the saved pre-activations (DGELU).  It does not
+// depend on the accumulator, so the epilogue fetches it one 32-column chunk ahead (see the kernel) and the HBM latency
+// of these loads overlaps the MMAs / the previous chunk instead of sitting between the TMEM read and the store.
+template <int EPI, typename OutT>
+__device__ __forceinline__ float4 load_side(const GemmArgs& p, int m, const RowCtx& rc, int n) {
+  if (EPI == PVRL_EPI_RESID) {
+    if (p.resid != nullptr && m < p.M && rc.orow >= 0) return ld_vec4<float>(p.resid + (long long)rc.orow * p.ldo + n);
+  } else if (EPI == PVRL_EPI_DGELU) {
+    if (m < p.M) return ld_vec4<OutT>(reinterpret_cast<const OutT*>(p.aux) + (long long)m * p.ld_aux + n);
   }
+  return make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 template <int EPI, typename OutT>
-__device__ __forceinline__ void epilogue_row(const GemmArgs& p, int m, int n0, float (&acc)[32]) {
+__device__ __forceinline__ void epilogue_vec4(const GemmArgs& p, int m, const RowCtx& rc, int n, float4 v,
+                                              const float4& bias4, const float4& side) {
   if (EPI == PVRL_EPI_ATOMIC) {
-    float* dst = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + n0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j), "f"(acc[4 * j]),
-                   "f"(acc[4 * j + 1]), "f"(acc[4 * j + 2]), "f"(acc[4 * j + 3])
-                   : "memory");
+    float* dst = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + n;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
     return;
   }
-  if (p.bias != nullptr) {
-    float b[32];
-    load_row32<float>(p.bias + n0, b);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] += b[j];
-  }
+  add4(v, bias4);
   if (EPI == PVRL_EPI_GELU) {
-    store_row32<OutT>(reinterpret_cast<OutT*>(p.out) + (long long)m * p.ldo + n0, acc);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = gelu_erf(acc[j]);
-    store_row32<OutT>(reinterpret_cast<OutT*>(p.out2) + (long long)m * p.ldo + n0, acc);
+    st_vec4<OutT>(reinterpret_cast<OutT*>(p.out) + (long long)m * p.ldo + n, v);
+    v.x = gelu_fwd<OutT>(v.x), v.y = gelu_fwd<OutT>(v.y), v.z = gelu_fwd<OutT>(v.z), v.w = gelu_fwd<OutT>(v.w);
+    st_vec4<OutT>(reinterpret_cast<OutT*>(p.out2) + (long long)m * p.ldo + n, v);
     return;
   }
   if (EPI == PVRL_EPI_DGELU) {
-    float a[32];
-    load_row32<OutT>(reinterpret_cast<const OutT*>(p.aux) + (long long)m * p.ld_aux + n0, a);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] *= gelu_erf_grad(a[j]);
+    v.x *= gelu_bwd<OutT>(side.x), v.y *= gelu_bwd<OutT>(side.y), v.z *= gelu_bwd<OutT>(side.z),
+        v.w *= gelu_bwd<OutT>(side.w);
   }
-  if (p.rowscale != nullptr) {
-    const float s = __ldg(p.rowscale + m / p.rs_div);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] *= s;
-  }
-  const long long orow = map_row(p.map, m, p.g);
+  mul4(v, rc.rs);
   if (EPI == PVRL_EPI_RESID) {
     float* out = reinterpret_cast<float*>(p.out);
-    if (orow < 0) {  // cls row of a spatial sequence: park it for the mean over frames (vit.py:147-149)
-      store_row32<float>(reinterpret_cast<float*>(p.out2) + (-orow - 1) * p.ldo + n0, acc);
+    if (rc.orow < 0) {  // cls row of a spatial sequence: park it for the mean over frames (vit.py:147-149)
+      st_vec4<float>(reinterpret_cast<float*>(p.out2) + (long long)(-rc.orow - 1) * p.ldo + n, v);
       return;
     }
-    if (p.resid != nullptr) {
-      float r[32];
-      load_row32<float>(p.resid + orow * p.ldo + n0, r);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] += r[j];
+    add4(v, side);
+    if (p.add_pos != nullptr) {  // MAP_PATCH (patch embedding only): + pos_embed[1+n] + time_embed[t]  (vit.py:373-404)
+      const int bt = m / p.g.HW;
+      add4(v, ld_vec4<float>(p.add_pos + (long long)(1 + m - bt * p.g.HW) * p.N + n));
+      add4(v, ld_vec4<float>(p.add_time + (long long)(bt % p.g.T) * p.N + n));
     }
-    if (p.add_pos != nullptr) {  // MAP_PATCH: + pos_embed[1+n] + time_embed[t]  (vit.py:373-404)
-      const int bt = m / p.g.HW, n = m - bt * p.g.HW, t = bt % p.g.T;
-      float r[32];
-      load_row32<float>(p.add_pos + (long long)(1 + n) * p.N + n0, r);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] += r[j];
-      load_row32<float>(p.add_time + (long long)t * p.N + n0, r);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] += r[j];
-    }
-    store_row32<float>(out + orow * p.ldo + n0, acc);
+    st_vec4<float>(out + (long long)rc.orow * p.ldo + n, v);
     return;
   }
   // STORE / DGELU
-  store_row32<OutT>(reinterpret_cast<OutT*>(p.out) + orow * p.ldo + n0, acc);
+  st_vec4<OutT>(reinterpret_cast<OutT*>(p.out) + (long long)rc.orow * p.ldo + n, v);
 }
 
 // tile index -> (m block, n block, k split).  NT: n fastest, so the CTAs of a wave share A tiles through L2 and the
@@ -168,15 +160,19 @@ __device__ __forceinline__ void decode_tile(int tile, int m_tiles, int n_tiles, 
   }
 }
 
-template <int EPI, typename OutT, bool TN>
+template <int EPI, typename OutT, bool TN, int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
+  using C = Cfg<BN>;
+  constexpr int STAGE_BYTES = C::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
   uint8_t* smem = smem_raw + (tiles_addr - raw_addr);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  const uint32_t bars_addr = tiles_addr + STAGES * STAGE_BYTES;
+  const uint32_t epi_addr = tiles_addr + C::PIPE_BYTES;
+  constexpr int BAR_OFF = C::PIPE_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
+  const uint32_t bars_addr = tiles_addr + BAR_OFF;
   // barrier slots: full[0..3], empty[4..7], tmem_full[8..9], tmem_empty[10..11], tmem ptr at slot 12
   auto full_bar = [&](int s) { return bars_addr + 8u * s; };
   auto empty_bar = [&](int s) { return bars_addr + 8u * (STAGES + s); };
@@ -281,30 +277,73 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue: TMEM -> regs -> global
+    // ------------------------------------------------------------------ epilogue: TMEM -> regs -> smem transpose -> global
     const int quarter = warp & 3;          // TMEM lanes [32*quarter, +32) are the only ones this warp may read
-    const int half = (warp - 4) >> 2;      // column half of the 256-wide accumulator
+    const int half = (warp - 4) >> 2;      // column half of the BN-wide accumulator
+    constexpr int HALF_COLS = BN / 2;
+    uint8_t* stg = smem + C::PIPE_BYTES + (warp - 4) * EPI_STAGE_BYTES;
+    const int rsub = lane >> 3, piece = lane & 7;   // transposed ownership: row 4*i + rsub, columns [4*piece, +4)
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int m_blk, n_blk, ks;
       decode_tile<TN>(tile, m_tiles, n_tiles, p.k_splits, m_blk, n_blk, ks);
+      const int m_base = m_blk * BM + quarter * 32;
+      // per-row context, computed by the lane that owns the row in TMEM order ...
+      RowCtx own;
+      {
+        const int m = min(m_base + lane, p.M - 1);
+        own.orow = (EPI == PVRL_EPI_ATOMIC || EPI == PVRL_EPI_GELU) ? m : static_cast<int>(map_row(p.map, m, p.g));
+        own.rs = (EPI != PVRL_EPI_ATOMIC && EPI != PVRL_EPI_GELU && p.rowscale != nullptr)
+                     ? __ldg(p.rowscale + m / p.rs_div) : 1.0f;
+      }
+      // ... and handed to the transposed owners
+      RowCtx rc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int src = 4 * i + rsub;
+        rc[i].orow = __shfl_sync(0xffffffffu, own.orow, src);
+        rc[i].rs = (EPI != PVRL_EPI_ATOMIC && EPI != PVRL_EPI_GELU) ? __shfl_sync(0xffffffffu, own.rs, src) : 1.0f;
+      }
+      constexpr int NCH = HALF_COLS / 32;
+      constexpr bool HAS_SIDE = EPI == PVRL_EPI_RESID || EPI == PVRL_EPI_DGELU;
+      const int n_first = n_blk * BN + half * HALF_COLS + piece * 4;   // this lane's columns in chunk 0
+      float4 side[2][8];
+      if (HAS_SIDE && n_first < p.N) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) side[0][i] = load_side<EPI, OutT>(p, m_base + 4 * i + rsub, rc[i], n_first);
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int m = m_blk * BM + quarter * 32 + lane;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int col0 = half * 128 + c * 32;
-        const int n0 = n_blk * BN + col0;
-        if (n0 >= p.N) break;  // warp-uniform
-        uint32_t raw[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col0, raw);
-        tmem_ld_wait();
-        if (m < p.M) {
-          float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-          epilogue_row<EPI, OutT>(p, m, n0, v);
+      for (int c = 0; c < NCH; ++c) {
+        const int col0 = half * HALF_COLS + c * 32;
+        const int n0 = n_blk * BN + col0;
+        if (n0 < p.N) {  // warp-uniform
+          if (HAS_SIDE && c + 1 < NCH && n0 + 32 < p.N) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              side[(c + 1) & 1][i] = load_side<EPI, OutT>(p, m_base + 4 * i + rsub, rc[i], n0 + 32 + piece * 4);
+          }
+          uint32_t raw[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col0, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
+          __syncwarp();
+          const int n = n0 + piece * 4;
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (EPI != PVRL_EPI_ATOMIC && p.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = 4 * i + rsub;
+            const float4 v = *reinterpret_cast<const float4*>(stg + row * 128 + ((piece ^ (row & 7)) << 4));
+            const int m = m_base + row;
+            if (m < p.M) epilogue_vec4<EPI, OutT>(p, m, rc[i], n, v, bias4, HAS_SIDE ? side[c & 1][i] : bias4);
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -400,9 +439,10 @@ int num_sms() {
 
 namespace {
 
-template <int EPI, typename OutT, bool TN>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t stream) {
-  auto kern = gemm_bf16_kernel<EPI, OutT, TN>;
+template <int EPI, typename OutT, bool TN, int BN>
+int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t stream) {
+  auto kern = gemm_bf16_kernel<EPI, OutT, TN, BN>;
+  constexpr int SMEM_BYTES = Cfg<BN>::SMEM_BYTES;
   static bool configured = false;
   if (!configured) {
     PVRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -413,6 +453,35 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a,
   const int grid = total < num_sms() ? total : num_sms();
   kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, a);
   return launched("gemm_bf16_kernel");
+}
+
+template <int EPI, typename OutT, bool TN>
+int launch_gemm(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t stream) {
+  return bn == 192 ? launch_gemm_bn<EPI, OutT, TN, 192>(ta, tb, a, stream)
+                   : launch_gemm_bn<EPI, OutT, TN, 256>(ta, tb, a, stream);
+}
+
+// Tile width and split-K count for one problem: the (BN, splits) pair whose tiles fill whole waves of SMs best
+// (useful columns / padded columns x busy SM slots / scheduled SM slots).  Ties go to the wider tile (fewer A re-reads).
+void pick_tiling(int M, int N, int num_kb, bool splitk, int forced_splits, int forced_bn, int* bn_out, int* splits_out) {
+  const int sms = num_sms();
+  if (forced_splits > num_kb) forced_splits = num_kb;
+  double best = -1.0;
+  *bn_out = 256, *splits_out = 1;
+  for (int bn : {256, 192}) {
+    if (forced_bn != 0 && bn != forced_bn) continue;
+    const int n_tiles = (N + bn - 1) / bn;
+    const int tiles = ((M + BM - 1) / BM) * n_tiles;
+    // measured: the 192-wide tile moves ~5 % more operand bytes per FLOP through L2 -> it must win that back in waves
+    const double col_eff = static_cast<double>(N) / (n_tiles * bn) * (bn == 192 ? 0.95 : 1.0);
+    const int s_max = splitk ? (forced_splits > 0 ? forced_splits : 64) : 1;
+    for (int s = (splitk && forced_splits > 0) ? forced_splits : 1; s <= s_max && s <= num_kb; ++s) {
+      if (forced_splits <= 0 && s > 1 && (num_kb + s - 1) / s < 4) break;
+      const int work = tiles * s;
+      const double util = col_eff * work / (static_cast<double>((work + sms - 1) / sms) * sms);
+      if (util > best + 0.02) best = util, *bn_out = bn, *splits_out = s;
+    }
+  }
 }
 
 }  // namespace
@@ -444,23 +513,13 @@ extern "C" int pvrl_gemm_bf16(const pvrl_gemm_t* d, void* stream_) {
   a.g = Geom(d->g.T > 0 ? d->g.T : 1, d->g.HW > 0 ? d->g.HW : 1);
 
   const int num_kb = (d->K + BK - 1) / BK;
-  int splits = 1;
-  if (d->epilogue == PVRL_EPI_ATOMIC) {
-    splits = d->k_splits;
-    if (splits <= 0) {  // pick the split count that fills whole waves of SMs
-      const int tiles = ((d->M + BM - 1) / BM) * ((d->N + BN - 1) / BN);
-      const int sms = num_sms();
-      double best = -1.0;
-      splits = 1;
-      for (int s = 1; s <= 64 && s <= num_kb; ++s) {
-        if ((num_kb + s - 1) / s < 4 && s > 1) break;
-        const int work = tiles * s;
-        const double util = static_cast<double>(work) / (((work + sms - 1) / sms) * sms);
-        if (util > best + 0.02) best = util, splits = s;
-      }
-    }
-    if (splits > num_kb) splits = num_kb;
-  }
+  int splits = 1, bn = 256;
+  static const int forced_bn = [] {
+    const char* e = getenv("PVRL_GEMM_BN");   // development knob: pin the tile width (192 / 256)
+    return e ? atoi(e) : 0;
+  }();
+  pick_tiling(d->M, d->N, num_kb, d->epilogue == PVRL_EPI_ATOMIC, d->k_splits, forced_bn, &bn, &splits);
+  if (splits > num_kb) splits = num_kb;
   a.kb_per_split = (num_kb + splits - 1) / splits;
   a.k_splits = (num_kb + a.kb_per_split - 1) / a.kb_per_split;  // no empty split
 
@@ -468,7 +527,7 @@ extern "C" int pvrl_gemm_bf16(const pvrl_gemm_t* d, void* stream_) {
   int rc;
   if (d->trans == 0) {
     if ((rc = make_tmap_2d_bf16(&ta, d->A, d->K, d->M, d->lda, BK, BM))) return rc;
-    if ((rc = make_tmap_2d_bf16(&tb, d->B, d->K, d->N, d->ldb, BK, BN))) return rc;
+    if ((rc = make_tmap_2d_bf16(&tb, d->B, d->K, d->N, d->ldb, BK, bn))) return rc;
   } else {
     if ((rc = make_tmap_2d_bf16(&ta, d->A, d->M, d->K, d->lda, 64, BK))) return rc;
     if ((rc = make_tmap_2d_bf16(&tb, d->B, d->N, d->K, d->ldb, 64, BK))) return rc;
@@ -477,18 +536,18 @@ extern "C" int pvrl_gemm_bf16(const pvrl_gemm_t* d, void* stream_) {
   const bool f32 = d->out_dtype == PVRL_F32;
   switch (d->epilogue) {
     case PVRL_EPI_STORE:
-      return f32 ? launch_gemm<PVRL_EPI_STORE, float, false>(ta, tb, a, stream)
-                 : launch_gemm<PVRL_EPI_STORE, __nv_bfloat16, false>(ta, tb, a, stream);
+      return f32 ? launch_gemm<PVRL_EPI_STORE, float, false>(bn, ta, tb, a, stream)
+                 : launch_gemm<PVRL_EPI_STORE, __nv_bfloat16, false>(bn, ta, tb, a, stream);
     case PVRL_EPI_GELU:
-      return f32 ? launch_gemm<PVRL_EPI_GELU, float, false>(ta, tb, a, stream)
-                 : launch_gemm<PVRL_EPI_GELU, __nv_bfloat16, false>(ta, tb, a, stream);
+      return f32 ? launch_gemm<PVRL_EPI_GELU, float, false>(bn, ta, tb, a, stream)
+                 : launch_gemm<PVRL_EPI_GELU, __nv_bfloat16, false>(bn, ta, tb, a, stream);
     case PVRL_EPI_DGELU:
-      return f32 ? launch_gemm<PVRL_EPI_DGELU, float, false>(ta, tb, a, stream)
-                 : launch_gemm<PVRL_EPI_DGELU, __nv_bfloat16, false>(ta, tb, a, stream);
+      return f32 ? launch_gemm<PVRL_EPI_DGELU, float, false>(bn, ta, tb, a, stream)
+                 : launch_gemm<PVRL_EPI_DGELU, __nv_bfloat16, false>(bn, ta, tb, a, stream);
     case PVRL_EPI_RESID:
-      return launch_gemm<PVRL_EPI_RESID, float, false>(ta, tb, a, stream);
+      return launch_gemm<PVRL_EPI_RESID, float, false>(bn, ta, tb, a, stream);
     default:
-      return d->trans ? launch_gemm<PVRL_EPI_ATOMIC, float, true>(ta, tb, a, stream)
-                      : launch_gemm<PVRL_EPI_ATOMIC, float, false>(ta, tb, a, stream);
+      return d->trans ? launch_gemm<PVRL_EPI_ATOMIC, float, true>(bn, ta, tb, a, stream)
+                      : launch_gemm<PVRL_EPI_ATOMIC, float, false>(bn, ta, tb, a, stream);
   }
 }

@@ -147,4 +147,35 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
 
+// bf16-output epilogues: erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below bf16 rounding) -- two MUFU ops
+// (rcp, ex2) and six FMAs instead of erff's ~25 instructions; exp(-z^2) doubles as the Gaussian of the derivative.
+__device__ __forceinline__ float erf_as(float x, float& gauss) {   // erf(x / sqrt 2), gauss = exp(-x^2 / 2)
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  gauss = __expf(-z * z);
+  float q = fmaf(t, 1.061405429f, -1.453152027f);
+  q = fmaf(t, q, 1.421413741f);
+  q = fmaf(t, q, -0.284496736f);
+  q = fmaf(t, q, 0.254829592f);
+  return copysignf(fmaf(-q * t, gauss, 1.0f), x);
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float g;
+  return 0.5f * x * (1.0f + erf_as(x, g));
+}
+__device__ __forceinline__ float gelu_fast_grad(float x) {
+  float g;
+  const float e = erf_as(x, g);
+  return fmaf(x * 0.3989422804014327f, g, 0.5f * (1.0f + e));
+}
+template <typename OutT>
+__device__ __forceinline__ float gelu_fwd(float x) {
+  return sizeof(OutT) == 2 ? gelu_fast(x) : gelu_erf(x);
+}
+template <typename OutT>
+__device__ __forceinline__ float gelu_bwd(float x) {
+  return sizeof(OutT) == 2 ? gelu_fast_grad(x) : gelu_erf_grad(x);
+}
+
 }  // namespace pvrl

@@ -13,7 +13,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from procedurevrl_b200 import ops  # noqa: E402
 
 
-def timeit(fn, iters, warm=3):
+WARM = 3
+
+
+def timeit(fn, iters, warm=None):
+    warm = WARM if warm is None else warm
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -32,8 +36,11 @@ def main():
     ap.add_argument("--clips", type=int, default=18)
     ap.add_argument("--frames", type=int, default=8)
     ap.add_argument("--only", default="")
+    ap.add_argument("--warm", type=int, default=3)
     ap.add_argument("--json", default="")
     a = ap.parse_args()
+    global WARM
+    WARM = a.warm
     dev = torch.device("cuda")
     Bc, T, HW, D, H, Hd = a.clips, a.frames, 196, 768, 12, 3072
     L, S = HW * T, 1 + HW * T
