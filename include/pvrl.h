@@ -39,8 +39,8 @@ extern "C" {
 
 /* GEMM epilogues */
 #define PVRL_EPI_STORE 0  /* out[map(m)] = rowscale*(acc + bias)                     -> act dtype        */
-#define PVRL_EPI_GELU 1   /* out = acc + bias ; out2 = gelu_erf(out)                 -> act dtype (vit.py:54-60) */
-#define PVRL_EPI_DGELU 2  /* out = acc * gelu_erf'(aux[m])                           -> act dtype        */
+#define PVRL_EPI_GELU 1   /* z = acc + bias ; out2 = gelu_erf(z) ; out = gelu_erf'(z) -> act dtype (vit.py:54-60) */
+#define PVRL_EPI_DGELU 2  /* out = acc * aux[m]   (aux = the gelu_erf' saved by EPI_GELU)   -> act dtype        */
 #define PVRL_EPI_RESID 3  /* out[map(m)] = resid[map(m)] + rowscale*(acc + bias) (+pos+time) -> fp32     */
 #define PVRL_EPI_ATOMIC 4 /* out[m] += acc  (fp32 red.add; split-K weight gradients)                     */
 
@@ -70,7 +70,7 @@ typedef struct pvrl_gemm {
   const float* rowscale; /* DropPath factors mask/keep, indexed m / rs_div, or NULL (vit_utils.py:140-155) */
   int32_t rs_div;
   int32_t map;       /* PVRL_MAP_* applied to out / resid rows            */
-  const void* aux;   /* DGELU: pre-activations [M, ld_aux], act dtype = out_dtype */
+  const void* aux;   /* DGELU: saved GELU derivative [M, ld_aux], act dtype = out_dtype */
   int64_t ld_aux;
   const float* resid;    /* RESID: fp32 residual, same row map / ldo as out */
   const float* add_pos;  /* RESID+MAP_PATCH: pos_embed [(1+HW), N]  (vit.py:373-389) */

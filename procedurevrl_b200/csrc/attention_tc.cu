@@ -116,46 +116,82 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
     mbar_wait(bar_s, 0);
     tc_fence_after();
-    uint32_t raw[32];
-    float mx = -INFINITY;
-    for (int c0 = 0; c0 < npad; c0 += 32) {
-      tmem_ld32(trow + c0, raw);
-      tmem_ld_wait();
+    // Only the last 32-column chunk can hold padded keys (zero-filled K rows -> score 0): the full chunks run without
+    // any per-element predicate, and four independent max / sum accumulators keep the FMNMX / FADD chains short.
+    // TMEM reads are software-pipelined: the load of chunk c+1 is in flight while chunk c is processed.
+    const int nch = npad >> 5, nfull = seq >> 5;
+    uint32_t raw[2][32];
+    float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    tmem_ld32(trow, raw[0]);
+#pragma unroll 1
+    for (int c = 0; c < nch; c += 2) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (c0 + j < seq) mx = fmaxf(mx, __uint_as_float(raw[j]));
+      for (int u = 0; u < 2; ++u) {
+        if (c + u < nch) {
+          tmem_ld_wait_on(raw[u]);
+          if (c + u + 1 < nch) tmem_ld32(trow + (c + u + 1) * 32, raw[u ^ 1]);
+          if (c + u < nfull) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(raw[u][j]));
+          } else {
+            const int rem = seq - (c + u) * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < rem) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(raw[u][j]));
+          }
+        }
+      }
     }
+    const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
     const float sl2 = scale * LOG2E;
     const float mxs = mx * sl2;
-    float sum = 0.f;
-    for (int c0 = 0; c0 < npad; c0 += 32) {
-      tmem_ld32(trow + c0, raw);
-      tmem_ld_wait();
-      float p[32];
+    float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+    tmem_ld32(trow, raw[0]);
+#pragma unroll 1
+    for (int c = 0; c < nch; c += 2) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        p[j] = (c0 + j < seq) ? exp2f(__uint_as_float(raw[j]) * sl2 - mxs) : 0.f;
-        sum += p[j];
+      for (int u = 0; u < 2; ++u) {
+        if (c + u < nch) {
+          tmem_ld_wait_on(raw[u]);
+          if (c + u + 1 < nch) tmem_ld32(trow + (c + u + 1) * 32, raw[u ^ 1]);
+          float p[32];
+          if (c + u < nfull) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              p[j] = ex2_approx(fmaf(__uint_as_float(raw[u][j]), sl2, -mxs));
+              sum4[j & 3] += p[j];
+            }
+          } else {
+            const int rem = seq - (c + u) * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              p[j] = j < rem ? ex2_approx(fmaf(__uint_as_float(raw[u][j]), sl2, -mxs)) : 0.f;
+              sum4[j & 3] += p[j];
+            }
+          }
+          const int c0 = (c + u) * 32;
+          uint8_t* tile = smem + (c0 >> 6) * TILE_BYTES;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) st_piece(tile, r, ((c0 & 63) >> 3) + q, p + 8 * q);
+        }
       }
-      uint8_t* tile = smem + (c0 >> 6) * TILE_BYTES;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) st_piece(tile, r, ((c0 & 63) >> 3) + q, p + 8 * q);
     }
+    const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
     fence_proxy_async_smem();
     tc_fence_before();
     mbar_arrive(bar_p);
     mbar_wait(bar_o, 0);
     tc_fence_after();
     float o[64];
-    tmem_ld32(trow, raw);
-    tmem_ld_wait();
+    tmem_ld32(trow, raw[0]);
+    tmem_ld32(trow + 32, raw[1]);
+    tmem_ld_wait_on(raw[0]);
+    tmem_ld_wait_on(raw[1]);
     const float inv = 1.0f / sum;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(raw[j]) * inv;
-    tmem_ld32(trow + 32, raw);
-    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(raw[0][j]) * inv;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) o[32 + j] = __uint_as_float(raw[j]) * inv;
+    for (int j = 0; j < 32; ++j) o[32 + j] = __uint_as_float(raw[1][j]) * inv;
     if (qi < seq) {
       store_row64_bf16(out + ((long long)s_idx * seq + qi) * C + h * 64, o);
       if (lse != nullptr) lse[(long long)pair * seq + qi] = mx * scale + __logf(sum);
@@ -314,21 +350,23 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       const int kt = it / n_tiles, mt = it % n_tiles;
       mbar_wait(bar_sdp, it & 1);
       tc_fence_after();
-      const bool qv = qvalid[mt];
-      const float l2 = lse_l2[mt], dl = delta[mt];
+      // No per-element masks: padded query rows have Q = dO = 0 (TMA zero fill) and lse = delta = 0, so P = 1 but
+      // dS = 0 and P^T dO = 0; padded key columns have K = V = 0, so their dS meets K = 0 in dQ and their dK / dV rows
+      // are never stored.
+      const float l2 = lse_l2[mt], dls = delta[mt] * scale;
 #pragma unroll 1
       for (int cc = 0; cc < 2; ++cc) {
         const int c0 = half * 64 + cc * 32;
         uint32_t rs[32], rp[32];
         tmem_ld32(trow + COL_S + c0, rs);
         tmem_ld32(trow + COL_DP + c0, rp);
-        tmem_ld_wait();
+        tmem_ld_wait_on(rs);
+        tmem_ld_wait_on(rp);
         float p[32], ds[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const bool v = qv && (kt * 128 + c0 + j < seq);
-          p[j] = v ? exp2f(__uint_as_float(rs[j]) * sl2 - l2) : 0.f;
-          ds[j] = v ? p[j] * (__uint_as_float(rp[j]) - dl) * scale : 0.f;
+          p[j] = ex2_approx(fmaf(__uint_as_float(rs[j]), sl2, -l2));
+          ds[j] = p[j] * fmaf(__uint_as_float(rp[j]), scale, -dls);
         }
         if (cc == 0 && it > 0) mbar_wait(bar_mma2, (it - 1) & 1);   // previous P / dS tiles consumed by the MMAs
         const int tile = c0 >> 6, piece0 = (c0 & 63) >> 3;

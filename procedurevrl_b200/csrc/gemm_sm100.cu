@@ -88,7 +88,7 @@ struct RowCtx {
   float rs;         // DropPath factor of the row (1 when none)
 };
 
-// "side" operand of one 4-column piece: the fp32 residual (RESID) or the saved pre-activations (DGELU).  It does not
+// "side" operand of one 4-column piece: the fp32 residual (RESID) or the saved GELU derivative (DGELU).  It does not
 // depend on the accumulator, so the epilogue fetches it one 32-column chunk ahead (see the kernel) and the HBM latency
 // of these loads overlaps the MMAs / the previous chunk instead of sitting between the TMEM read and the store.
 template <int EPI, typename OutT>
@@ -111,16 +111,15 @@ __device__ __forceinline__ void epilogue_vec4(const GemmArgs& p, int m, const Ro
     return;
   }
   add4(v, bias4);
-  if (EPI == PVRL_EPI_GELU) {
-    st_vec4<OutT>(reinterpret_cast<OutT*>(p.out) + (long long)m * p.ldo + n, v);
-    v.x = gelu_fwd<OutT>(v.x), v.y = gelu_fwd<OutT>(v.y), v.z = gelu_fwd<OutT>(v.z), v.w = gelu_fwd<OutT>(v.w);
-    st_vec4<OutT>(reinterpret_cast<OutT*>(p.out2) + (long long)m * p.ldo + n, v);
+  if (EPI == PVRL_EPI_GELU) {   // out2 = gelu(z), out = gelu'(z): the backward GEMM then only multiplies (EPI_DGELU)
+    float4 a, d;
+    gelu_both<OutT>(v.x, a.x, d.x), gelu_both<OutT>(v.y, a.y, d.y), gelu_both<OutT>(v.z, a.z, d.z),
+        gelu_both<OutT>(v.w, a.w, d.w);
+    st_vec4<OutT>(reinterpret_cast<OutT*>(p.out) + (long long)m * p.ldo + n, d);
+    st_vec4<OutT>(reinterpret_cast<OutT*>(p.out2) + (long long)m * p.ldo + n, a);
     return;
   }
-  if (EPI == PVRL_EPI_DGELU) {
-    v.x *= gelu_bwd<OutT>(side.x), v.y *= gelu_bwd<OutT>(side.y), v.z *= gelu_bwd<OutT>(side.z),
-        v.w *= gelu_bwd<OutT>(side.w);
-  }
+  if (EPI == PVRL_EPI_DGELU) v.x *= side.x, v.y *= side.y, v.z *= side.z, v.w *= side.w;
   mul4(v, rc.rs);
   if (EPI == PVRL_EPI_RESID) {
     float* out = reinterpret_cast<float*>(p.out);

@@ -112,6 +112,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Same wait, but naming the destination registers of an earlier tmem_ld32 as read-write operands: uses of v[] cannot be
+// scheduled above the wait even when other work sits between the load and the wait (software-pipelined TMEM reads).
+__device__ __forceinline__ void tmem_ld_wait_on(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                 "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {   // single MUFU.EX2 (flushes denormal results to 0)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // Shared-memory matrix descriptor, SWIZZLE_128B.
 //   bits [0,14)  start address >> 4      bits [16,30) leading-dim byte offset >> 4
@@ -169,13 +185,20 @@ __device__ __forceinline__ float gelu_fast_grad(float x) {
   const float e = erf_as(x, g);
   return fmaf(x * 0.3989422804014327f, g, 0.5f * (1.0f + e));
 }
+// gelu(x) and gelu'(x) together (they share erf and the Gaussian): exact erff for fp32 outputs (parity mode), the
+// Abramowitz-Stegun form for bf16 outputs.
 template <typename OutT>
-__device__ __forceinline__ float gelu_fwd(float x) {
-  return sizeof(OutT) == 2 ? gelu_fast(x) : gelu_erf(x);
-}
-template <typename OutT>
-__device__ __forceinline__ float gelu_bwd(float x) {
-  return sizeof(OutT) == 2 ? gelu_fast_grad(x) : gelu_erf_grad(x);
+__device__ __forceinline__ void gelu_both(float x, float& act, float& dact) {
+  float e, g;
+  if (sizeof(OutT) == 2) {
+    e = erf_as(x, g);
+  } else {
+    e = erff(x * 0.70710678118654752f);
+    g = __expf(-0.5f * x * x);
+  }
+  const float cdf = 0.5f * (1.0f + e);
+  act = x * cdf;
+  dact = fmaf(x * 0.3989422804014327f, g, cdf);
 }
 
 }  // namespace pvrl

@@ -228,8 +228,8 @@ class EncoderEngine:
         # ---- MLP (vit.py:157)
         ln_m, st_m = self._act(Mm, D, dev), torch.empty(Mm, 2, **f32)
         ops.layernorm_fwd(x2, P[b + "norm2.weight"], P[b + "norm2.bias"], ln_m, st_m, Mm, D, self.eps, ops.MAP_IDENT)
-        pre, hid = self._act(Mm, Hd, dev), self._act(Mm, Hd, dev)
-        self.linear(ln_m, b + "mlp.fc1.weight", pre, Mm, Hd, D, epilogue=ops.EPI_GELU, bias=P[b + "mlp.fc1.bias"],
+        dact, hid = self._act(Mm, Hd, dev), self._act(Mm, Hd, dev)      # gelu'(fc1) (for the backward), gelu(fc1)
+        self.linear(ln_m, b + "mlp.fc1.weight", dact, Mm, Hd, D, epilogue=ops.EPI_GELU, bias=P[b + "mlp.fc1.bias"],
                     out2=hid)
         x3 = torch.empty(Bc, S, D, **f32)
         self.linear(hid, b + "mlp.fc2.weight", x3, Mm, D, Hd, epilogue=ops.EPI_RESID, bias=P[b + "mlp.fc2.bias"],
@@ -237,7 +237,7 @@ class EncoderEngine:
         if not save:
             return x3, None
         return x3, dict(x0=x0, x1=x1, x2=x2, ln_t=ln_t, st_t=st_t, qkv_t=qkv_t, o_t=o_t, lse_t=lse_t, p_t=p_t,
-                        ln_s=ln_s, st_s=st_s, qkv_s=qkv_s, o_s=o_s, lse_s=lse_s, ln_m=ln_m, st_m=st_m, pre=pre,
+                        ln_s=ln_s, st_s=st_s, qkv_s=qkv_s, o_s=o_s, lse_s=lse_s, ln_m=ln_m, st_m=st_m, dact=dact,
                         hid=hid, dp=dp)
 
     # spatial attention dispatch (the tcgen05 kernel plugs in here)
@@ -311,7 +311,7 @@ class EncoderEngine:
         ops.gather_cast(dx, dY, Mm, D, ops.MAP_IDENT, rowscale=dp.get("mlp"), rs_div=S)
         self.linear_dw(dY, sv["hid"], G[b + "mlp.fc2.weight"], G[b + "mlp.fc2.bias"], Mm, D, Hd)
         d_pre = self._act(Mm, Hd, dev)
-        self.linear_dx(dY, b + "mlp.fc2.weight", d_pre, Mm, Hd, D, epilogue=ops.EPI_DGELU, aux=sv["pre"])
+        self.linear_dx(dY, b + "mlp.fc2.weight", d_pre, Mm, Hd, D, epilogue=ops.EPI_DGELU, aux=sv["dact"])
         self.linear_dw(d_pre, sv["ln_m"], G[b + "mlp.fc1.weight"], G[b + "mlp.fc1.bias"], Mm, Hd, D)
         d_ln = self._act(Mm, D, dev)
         self.linear_dx(d_pre, b + "mlp.fc1.weight", d_ln, Mm, D, Hd)

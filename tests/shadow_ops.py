@@ -58,13 +58,12 @@ def gemm(A, B, out, *, M, N, K, trans=0, epilogue=EPI_STORE, out2=None, bias=Non
         return out
     if bias is not None:
         acc = acc + bias
-    if epilogue == EPI_GELU:
-        out[:M] = acc.to(out.dtype)
+    if epilogue == EPI_GELU:      # out = gelu'(z), out2 = gelu(z)
+        out[:M] = (0.5 * (1 + torch.erf(acc / math.sqrt(2))) + acc * torch.exp(-0.5 * acc * acc) / math.sqrt(2 * math.pi)).to(out.dtype)
         out2[:M] = F.gelu(acc).to(out2.dtype)
         return out
     if epilogue == EPI_DGELU:
-        p = aux[:M].float()
-        acc = acc * (0.5 * (1 + torch.erf(p / math.sqrt(2))) + p * torch.exp(-0.5 * p * p) / math.sqrt(2 * math.pi))
+        acc = acc * aux[:M].float()
     if rowscale is not None:
         acc = acc * rowscale[torch.arange(M, device=dev) // rs_div].unsqueeze(1)
     rows = _rows(map, M, T, HW, dev)

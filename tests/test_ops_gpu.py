@@ -80,18 +80,20 @@ def test_gemm_gelu_dgelu(ops):
     bias = _rand(N, seed=3, scale=0.1)
     pre_ref = A.float() @ B.float().t() + bias
     for dt in (torch.float32, torch.bfloat16):
-        pre = torch.empty(M, N, device="cuda", dtype=dt)
+        dact = torch.empty(M, N, device="cuda", dtype=dt)
         act = torch.empty(M, N, device="cuda", dtype=dt)
-        ops.gemm(A, B, pre, M=M, N=N, K=K, bias=bias, epilogue=ops.EPI_GELU, out2=act)
+        ops.gemm(A, B, dact, M=M, N=N, K=K, bias=bias, epilogue=ops.EPI_GELU, out2=act)
         tol = 2e-3 if dt == torch.float32 else 1e-2
-        assert _report("gelu.pre", pre, pre_ref)[1] < tol
+        z = pre_ref.clone().requires_grad_(True)
+        torch.nn.functional.gelu(z).sum().backward()
+        assert _report("gelu.dact", dact, z.grad)[1] < tol          # out = gelu'(z), saved for the backward GEMM
         assert _report("gelu.act", act, torch.nn.functional.gelu(pre_ref))[1] < tol
-        # dgelu: out = (dY @ W) * gelu'(pre)
+        # dgelu: out = (dY @ W) * gelu'(z) with the saved derivative as aux
         dY = _rand(M, 768, seed=7, dtype=torch.bfloat16)
         Wt = _rand(N, 768, seed=8, scale=0.05, dtype=torch.bfloat16)     # [N_out=3072, K=768]
         out = torch.empty(M, N, device="cuda", dtype=dt)
-        ops.gemm(dY, Wt, out, M=M, N=N, K=768, epilogue=ops.EPI_DGELU, aux=pre)
-        p = pre.float().requires_grad_(True)
+        ops.gemm(dY, Wt, out, M=M, N=N, K=768, epilogue=ops.EPI_DGELU, aux=dact)
+        p = pre_ref.clone().requires_grad_(True)
         torch.nn.functional.gelu(p).backward(dY.float() @ Wt.float().t())
         assert _report("dgelu", out, p.grad)[1] < tol
 
