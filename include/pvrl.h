@@ -169,6 +169,44 @@ int pvrl_kl_topk_loss(const float* pred, const float* teacher_logits, float* row
 /* eval-mode softmax over rows (vit.py:355-356) */
 int pvrl_softmax_rows(const float* x, float* y, int32_t M, int32_t K, void* stream);
 
+/* ---- clip-order ("diffusion") transformer of the pre-training branch, fp32 -------------------------------------
+ * Replaces the op-by-op eager execution of DiffusionTransformer (tfm_model.py:70-289; call site vit.py:330):
+ * ResidualAttentionBlock :32-53 = LayerNorm -> nn.MultiheadAttention(8 heads of 64, key_padding_mask) -> residual ->
+ * LayerNorm -> Linear -> QuickGELU -> Linear -> residual, run per denoising level over M = B*S rows (a few dozen).
+ * Rows are b-major: token (b, s) is row b*S + s.  Every pointer is fp32 unless noted. */
+
+/* y[M,N] = (resid ? resid : 0) + prologue(x)[M,K] W[N,K]^T + bias.  x_mode 0: x; 1: LayerNorm(x) with ln_w/ln_b/eps
+ * (also writes xhat[M,K] and rstd[M] when non-NULL, for pvrl_ot_ln_bwd / pvrl_ot_linear_dw); 2: QuickGELU(x)
+ * (tfm_model.py:27-29).  K % 128 == 0, K <= 2048. */
+int pvrl_ot_linear_fwd(const float* x, int32_t x_mode, const float* ln_w, const float* ln_b, float eps, float* xhat_out,
+                       float* rstd_out, const float* W, const float* bias, const float* resid, float* y, int32_t M,
+                       int32_t N, int32_t K, void* stream);
+/* dA[M,K] = dY[M,N] W[N,K], times QuickGELU'(pre[M,K]) when pre != NULL. */
+int pvrl_ot_linear_dx(const float* dY, const float* W, const float* pre, float* dA, int32_t M, int32_t N, int32_t K,
+                      void* stream);
+/* dW[N,K] += dY[M,N]^T a[M,K]; db[N] += colsum(dY) (db may be NULL).  a_mode 0: a = A; 1: a = A*ln_w + ln_b (A = xhat
+ * saved by pvrl_ot_linear_fwd); 2: a = QuickGELU(A). */
+int pvrl_ot_linear_dw(const float* dY, const float* A, int32_t a_mode, const float* ln_w, const float* ln_b, float* dW,
+                      float* db, int32_t M, int32_t N, int32_t K, void* stream);
+/* LayerNorm backward on saved xhat / rstd: dh[M,C] += dx, dw[C] += sum dA*xhat, db[C] += sum dA. */
+int pvrl_ot_ln_bwd(const float* dA, const float* xhat, const float* rstd, const float* w, float* dh, float* dw,
+                   float* db, int32_t M, int32_t C, void* stream);
+/* Multi-head attention over S <= 16 tokens per sequence, head_dim 64: qkv[M, 3*H*64] ([q | k | v], heads contiguous, as
+ * nn.MultiheadAttention.in_proj), keys s >= pad_start[b] masked (pad_start int64[B], NULL = no padding);
+ * probs[B,H,S,S] saved for the backward; o[M, H*64]. */
+int pvrl_ot_attn_fwd(const float* qkv, const int64_t* pad_start, float* probs, float* o, int32_t B, int32_t S, int32_t H,
+                     void* stream);
+int pvrl_ot_attn_bwd(const float* qkv, const float* probs, const float* dO, float* dqkv, int32_t B, int32_t S, int32_t H,
+                     void* stream);
+/* Level input (tfm_model.py:171-191, ennoise :291-302): h[(b,s)] = in + type_emb[s == mask_b] + pos_emb[s] + tvec with
+ * in = ca*src[b] + cb*noise[b] at the mask position, pad_emb at s >= pad_start[b], video[(b,s)] elsewhere. */
+int pvrl_ot_embed_fwd(const float* video, const float* src, const float* noise, float ca, float cb,
+                      const int64_t* mask_inds, const int64_t* pad_start, const float* type_w, const float* pos_w,
+                      const float* pad_w, const float* tvec, float* h, int32_t B, int32_t S, int32_t C, void* stream);
+/* Its backward: dvideo[M,C] / dtype[2,C] / dpos[S,C] / dpad[C] are accumulated (+=), dtvec[C] is written. */
+int pvrl_ot_embed_bwd(const float* dh, const int64_t* mask_inds, const int64_t* pad_start, float* dvideo, float* dtype,
+                      float* dpos, float* dpad, float* dtvec, int32_t B, int32_t S, int32_t C, void* stream);
+
 /* ---- misc ----------------------------------------------------------------------------------------------- */
 const char* pvrl_last_error(void);
 int pvrl_abi_version(void);

@@ -16,6 +16,7 @@ namespace {
 
 constexpr int OT_MT = 32;      // activation rows per block tile
 constexpr int OT_KC = 512;     // contraction chunk held in shared memory
+constexpr int OT_KMAX = 2048;  // largest contraction of the forward kernel (weight row cached in registers)
 constexpr int OT_THREADS = 256;
 
 __device__ __forceinline__ float quick_gelu(float u) { return u / (1.0f + __expf(-1.702f * u)); }
@@ -30,60 +31,72 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // ----------------------------------------------------------------------------------------------------- linear forward
-// grid (ceil(N / 8), ceil(M / 32)), 256 threads: warp w owns output column n = 8 * blockIdx.x + w.
-// x_mode: 0 = x as is, 1 = LayerNorm(x) (K <= 512; block column 0 also writes xhat / rstd for the backward), 2 = QuickGELU(x).
-__global__ void __launch_bounds__(OT_THREADS)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// grid (ceil(N / 8), ceil(M / mt)), 256 threads: warp w owns output column n = 8 * blockIdx.x + w.
+// x_mode: 0 = x as is, 1 = LayerNorm(x) (block column 0 also writes xhat / rstd for the backward), 2 = QuickGELU(x).
+// These kernels are latency-bound (a few dozen rows): the row tile [mt][K] is fetched with cp.async (every 16-byte
+// piece in flight at once, no register staging) while the warp's whole weight row streams into registers.
+__global__ void __launch_bounds__(OT_THREADS, 1)
 ot_linear_fwd_kernel(const float* __restrict__ x, int x_mode, const float* __restrict__ ln_w,
                      const float* __restrict__ ln_b, float eps, float* __restrict__ xhat_out,
                      float* __restrict__ rstd_out, const float* __restrict__ W, const float* __restrict__ bias,
-                     const float* __restrict__ resid, float* __restrict__ y, int M, int N, int K) {
-  extern __shared__ float xs[];   // [OT_MT][OT_KC]
+                     const float* __restrict__ resid, float* __restrict__ y, int M, int N, int K, int mt) {
+  extern __shared__ __align__(16) float xs[];   // [mt][K]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * OT_MT;
-  const int rows = min(OT_MT, M - m0);
+  const int m0 = blockIdx.y * mt;
+  const int rows = min(mt, M - m0);
   const int n = blockIdx.x * 8 + warp;
+  const int k4n = K >> 2;
+  for (int i = threadIdx.x; i < rows * k4n; i += OT_THREADS) cp_async16(xs + 4 * i, x + (long long)m0 * K + 4 * i);
+  float4 wreg[OT_KMAX / 128];
+#pragma unroll
+  for (int j = 0; j < OT_KMAX / 128; ++j)
+    if (n < N && j * 128 < K) wreg[j] = __ldg(reinterpret_cast<const float4*>(W + (long long)n * K + j * 128 + lane * 4));
   float acc[OT_MT];
 #pragma unroll
   for (int m = 0; m < OT_MT; ++m) acc[m] = 0.f;
-
-  for (int kc = 0; kc < K; kc += OT_KC) {
-    const int kw = min(OT_KC, K - kc);            // multiple of 128
-    __syncthreads();
-    for (int i = threadIdx.x; i < rows * (kw >> 2); i += OT_THREADS) {
-      const int m = i / (kw >> 2), k4 = (i - m * (kw >> 2)) << 2;
-      float4 v = __ldg(reinterpret_cast<const float4*>(x + (long long)(m0 + m) * K + kc + k4));
-      if (x_mode == 2) v.x = quick_gelu(v.x), v.y = quick_gelu(v.y), v.z = quick_gelu(v.z), v.w = quick_gelu(v.w);
-      *reinterpret_cast<float4*>(xs + m * OT_KC + k4) = v;
+  cp_async_wait_all();
+  if (x_mode == 2)   // QuickGELU on the pieces this thread fetched itself (visible to it after the wait)
+    for (int i = threadIdx.x; i < rows * k4n; i += OT_THREADS) {
+      float4 v = *reinterpret_cast<float4*>(xs + 4 * i);
+      v.x = quick_gelu(v.x), v.y = quick_gelu(v.y), v.z = quick_gelu(v.z), v.w = quick_gelu(v.w);
+      *reinterpret_cast<float4*>(xs + 4 * i) = v;
     }
-    __syncthreads();
-    if (x_mode == 1) {                            // LayerNorm over the K (<= 512) features of each row, one warp per row
-      for (int m = warp; m < rows; m += OT_THREADS / 32) {
-        float s = 0.f;
-        for (int k = lane; k < kw; k += 32) s += xs[m * OT_KC + k];
-        const float mean = warp_sum(s) / kw;
-        float q = 0.f;
-        for (int k = lane; k < kw; k += 32) {
-          const float d = xs[m * OT_KC + k] - mean;
-          q += d * d;
-        }
-        const float rstd = rsqrtf(warp_sum(q) / kw + eps);
-        for (int k = lane; k < kw; k += 32) {
-          const float xh = (xs[m * OT_KC + k] - mean) * rstd;
-          xs[m * OT_KC + k] = xh * __ldg(ln_w + k) + __ldg(ln_b + k);
-          if (blockIdx.x == 0 && xhat_out != nullptr) xhat_out[(long long)(m0 + m) * K + k] = xh;
-        }
-        if (blockIdx.x == 0 && lane == 0 && rstd_out != nullptr) rstd_out[m0 + m] = rstd;
+  __syncthreads();
+  if (x_mode == 1) {                              // LayerNorm over the K features of each row, one warp per row
+    for (int m = warp; m < rows; m += OT_THREADS / 32) {
+      float* xr = xs + m * K;
+      float s = 0.f;
+      for (int k = lane; k < K; k += 32) s += xr[k];
+      const float mean = warp_sum(s) / K;
+      float q = 0.f;
+      for (int k = lane; k < K; k += 32) {
+        const float d = xr[k] - mean;
+        q += d * d;
       }
-      __syncthreads();
+      const float rstd = rsqrtf(warp_sum(q) / K + eps);
+      for (int k = lane; k < K; k += 32) {
+        const float xh = (xr[k] - mean) * rstd;
+        xr[k] = xh * __ldg(ln_w + k) + __ldg(ln_b + k);
+        if (blockIdx.x == 0 && xhat_out != nullptr) xhat_out[(long long)(m0 + m) * K + k] = xh;
+      }
+      if (blockIdx.x == 0 && lane == 0 && rstd_out != nullptr) rstd_out[m0 + m] = rstd;
     }
-    if (n < N) {
-      const float* wrow = W + (long long)n * K + kc;
-      for (int j = 0; j < (kw >> 7); ++j) {
-        const float4 w4 = __ldg(reinterpret_cast<const float4*>(wrow + j * 128 + lane * 4));
+    __syncthreads();
+  }
+  if (n < N) {
+#pragma unroll
+    for (int j = 0; j < OT_KMAX / 128; ++j) {
+      if (j * 128 < K) {
+        const float4 w4 = wreg[j];
 #pragma unroll
         for (int m = 0; m < OT_MT; ++m)
           if (m < rows) {
-            const float4 a4 = *reinterpret_cast<const float4*>(xs + m * OT_KC + j * 128 + lane * 4);
+            const float4 a4 = *reinterpret_cast<const float4*>(xs + m * K + j * 128 + lane * 4);
             acc[m] = fmaf(w4.x, a4.x, fmaf(w4.y, a4.y, fmaf(w4.z, a4.z, fmaf(w4.w, a4.w, acc[m]))));
           }
       }
@@ -110,34 +123,44 @@ ot_linear_fwd_kernel(const float* __restrict__ x, int x_mode, const float* __res
 
 // ----------------------------------------------------------------------------------------------------- linear dX
 // dA[m, k] = (sum_n dY[m, n] W[n, k]) * (pre ? QuickGELU'(pre[m, k]) : 1).
-// grid (K / 32, ceil(M / 32)), 256 threads = 32 k-columns x 8 n-slices (warp = slice): a warp reads 128 contiguous
-// bytes of one weight row per step, dY rows are broadcast from shared memory.
+// grid (K / 32, ceil(M / 32), n_splits), 256 threads = 32 k-columns x 8 n-slices (warp = slice): a warp reads 128
+// contiguous bytes of one weight row per step (16 rows in flight per thread), dY rows are broadcast from shared memory.
+// With n_splits > 1 every block covers N / n_splits weight rows and the partial sums meet in fp32 atomics on a
+// zeroed dA (only without `pre`): enough blocks to cover the L2 latency instead of 16 blocks walking 2048 rows each.
 __global__ void __launch_bounds__(OT_THREADS)
 ot_linear_dx_kernel(const float* __restrict__ dY, const float* __restrict__ W, const float* __restrict__ pre,
-                    float* __restrict__ dA, int M, int N, int K) {
-  extern __shared__ float ys[];   // [OT_MT][OT_KC] chunk of dY; reused as [8][OT_MT][32] for the slice reduction
+                    float* __restrict__ dA, int M, int N, int K, int n_per_split) {
+  extern __shared__ __align__(16) float ys[];   // [OT_MT][OT_KC] chunk of dY; reused as [8][OT_MT][32] for the slice reduction
   const int slice = threadIdx.x >> 5, kcol = threadIdx.x & 31;
   const int m0 = blockIdx.y * OT_MT;
   const int rows = min(OT_MT, M - m0);
   const int k = blockIdx.x * 32 + kcol;
+  const int n_begin = blockIdx.z * n_per_split;
+  const int n_end = min(N, n_begin + n_per_split);
   float acc[OT_MT];
 #pragma unroll
   for (int m = 0; m < OT_MT; ++m) acc[m] = 0.f;
-  for (int nc = 0; nc < N; nc += OT_KC) {
-    const int nw = min(OT_KC, N - nc);
+  for (int nc = n_begin; nc < n_end; nc += OT_KC) {
+    const int nw = min(OT_KC, n_end - nc);
     __syncthreads();
     for (int i = threadIdx.x; i < rows * (nw >> 2); i += OT_THREADS) {
       const int m = i / (nw >> 2), n4 = (i - m * (nw >> 2)) << 2;
-      *reinterpret_cast<float4*>(ys + m * OT_KC + n4) =
-          __ldg(reinterpret_cast<const float4*>(dY + (long long)(m0 + m) * N + nc + n4));
+      cp_async16(ys + m * OT_KC + n4, dY + (long long)(m0 + m) * N + nc + n4);
     }
+    cp_async_wait_all();
     __syncthreads();
     if (k < K)
-      for (int n = slice; n < nw; n += 8) {
-        const float w = __ldg(W + (long long)(nc + n) * K + k);
+      for (int nb = slice; nb < nw; nb += 128) {
+        float w[16];
 #pragma unroll
-        for (int m = 0; m < OT_MT; ++m)
-          if (m < rows) acc[m] = fmaf(ys[m * OT_KC + n], w, acc[m]);
+        for (int u = 0; u < 16; ++u) w[u] = nb + 8 * u < nw ? __ldg(W + (long long)(nc + nb + 8 * u) * K + k) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int n = min(nb + 8 * u, nw - 1);
+#pragma unroll
+          for (int m = 0; m < OT_MT; ++m)
+            if (m < rows) acc[m] = fmaf(ys[m * OT_KC + n], w[u], acc[m]);
+        }
       }
   }
   __syncthreads();
@@ -150,8 +173,12 @@ ot_linear_dx_kernel(const float* __restrict__ dY, const float* __restrict__ W, c
     for (int sl = 0; sl < 8; ++sl) s += ys[(sl * OT_MT + m) * 32 + kcol];
     if (k < K) {
       const long long o = (long long)(m0 + m) * K + k;
-      if (pre != nullptr) s *= quick_gelu_grad(__ldg(pre + o));
-      dA[o] = s;
+      if (gridDim.z > 1) {
+        atomicAdd(dA + o, s);
+      } else {
+        if (pre != nullptr) s *= quick_gelu_grad(__ldg(pre + o));
+        dA[o] = s;
+      }
     }
   }
 }
@@ -171,16 +198,27 @@ ot_linear_dw_kernel(const float* __restrict__ dY, const float* __restrict__ A, i
   if (a_mode == 1) w4 = __ldg(reinterpret_cast<const float4*>(ln_w + k)), b4 = __ldg(reinterpret_cast<const float4*>(ln_b + k));
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   float sb = 0.f;
-  for (int m = 0; m < M; ++m) {
-    const float dy = __ldg(dY + (long long)m * N + n);
-    float4 a = __ldg(reinterpret_cast<const float4*>(A + (long long)m * K + k));
-    if (a_mode == 1) a.x = fmaf(a.x, w4.x, b4.x), a.y = fmaf(a.y, w4.y, b4.y), a.z = fmaf(a.z, w4.z, b4.z), a.w = fmaf(a.w, w4.w, b4.w);
-    if (a_mode == 2) a.x = quick_gelu(a.x), a.y = quick_gelu(a.y), a.z = quick_gelu(a.z), a.w = quick_gelu(a.w);
-    acc.x = fmaf(dy, a.x, acc.x), acc.y = fmaf(dy, a.y, acc.y), acc.z = fmaf(dy, a.z, acc.z), acc.w = fmaf(dy, a.w, acc.w);
-    sb += dy;
-  }
   float4* dst = reinterpret_cast<float4*>(dW + (long long)n * K + k);
-  float4 cur = *dst;
+  const float4 cur0 = *dst;                        // in flight together with the first batch of rows
+  for (int mb = 0; mb < M; mb += 8) {              // 8 rows per batch: 16 independent loads in flight per thread
+    float dy[8];
+    float4 a[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int m = min(mb + u, M - 1);
+      dy[u] = mb + u < M ? __ldg(dY + (long long)m * N + n) : 0.f;
+      a[u] = __ldg(reinterpret_cast<const float4*>(A + (long long)m * K + k));
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      float4 v = a[u];
+      if (a_mode == 1) v.x = fmaf(v.x, w4.x, b4.x), v.y = fmaf(v.y, w4.y, b4.y), v.z = fmaf(v.z, w4.z, b4.z), v.w = fmaf(v.w, w4.w, b4.w);
+      if (a_mode == 2) v.x = quick_gelu(v.x), v.y = quick_gelu(v.y), v.z = quick_gelu(v.z), v.w = quick_gelu(v.w);
+      acc.x = fmaf(dy[u], v.x, acc.x), acc.y = fmaf(dy[u], v.y, acc.y), acc.z = fmaf(dy[u], v.z, acc.z), acc.w = fmaf(dy[u], v.w, acc.w);
+      sb += dy[u];
+    }
+  }
+  float4 cur = cur0;
   cur.x += acc.x, cur.y += acc.y, cur.z += acc.z, cur.w += acc.w;
   *dst = cur;
   if (db != nullptr && blockIdx.x == 0 && lane == 0) db[n] += sb;
@@ -365,18 +403,22 @@ extern "C" int pvrl_ot_linear_fwd(const float* x, int32_t x_mode, const float* l
                                   float* xhat_out, float* rstd_out, const float* W, const float* bias,
                                   const float* resid, float* y, int32_t M, int32_t N, int32_t K, void* stream) {
   PVRL_CHECK_ARG(x && W && y && M > 0 && N > 0 && K > 0, "pvrl_ot_linear_fwd: bad arguments");
-  PVRL_CHECK_ARG(K % 128 == 0, "pvrl_ot_linear_fwd: K=%d must be a multiple of 128", K);
+  PVRL_CHECK_ARG(K % 128 == 0 && K <= OT_KMAX, "pvrl_ot_linear_fwd: K=%d must be a multiple of 128, <= 2048", K);
   PVRL_CHECK_ARG(x_mode >= 0 && x_mode <= 2, "pvrl_ot_linear_fwd: bad x_mode %d", x_mode);
-  if (x_mode == 1) PVRL_CHECK_ARG(ln_w && ln_b && K <= OT_KC, "pvrl_ot_linear_fwd: LayerNorm prologue needs weights and K <= 512");
-  const int smem = OT_MT * OT_KC * 4;
+  if (x_mode == 1) PVRL_CHECK_ARG(ln_w && ln_b, "pvrl_ot_linear_fwd: the LayerNorm prologue needs ln_w / ln_b");
+  // rows per block tile: as many as fit next to each other in 200 KB of shared memory (32 for K <= 1536, 25 for K = 2048)
+  int mt = (200 * 1024) / (K * 4);
+  mt = mt > OT_MT ? OT_MT : mt;
+  mt = mt > M ? M : mt;
+  const int smem = mt * K * 4;
   static bool configured = false;
   if (!configured) {
-    PVRL_CUDA(cudaFuncSetAttribute(ot_linear_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PVRL_CUDA(cudaFuncSetAttribute(ot_linear_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
-  dim3 grid((N + 7) / 8, (M + OT_MT - 1) / OT_MT);
+  dim3 grid((N + 7) / 8, (M + mt - 1) / mt);
   ot_linear_fwd_kernel<<<grid, OT_THREADS, smem, STREAM>>>(x, x_mode, ln_w, ln_b, eps, xhat_out, rstd_out, W, bias, resid,
-                                                           y, M, N, K);
+                                                           y, M, N, K, mt);
   return launched("ot_linear_fwd_kernel");
 }
 
@@ -390,8 +432,15 @@ extern "C" int pvrl_ot_linear_dx(const float* dY, const float* W, const float* p
     PVRL_CUDA(cudaFuncSetAttribute(ot_linear_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid((K + 31) / 32, (M + OT_MT - 1) / OT_MT);
-  ot_linear_dx_kernel<<<grid, OT_THREADS, smem, STREAM>>>(dY, W, pre, dA, M, N, K);
+  // split N across blocks until ~256 blocks are in flight (never with the QuickGELU' epilogue, which needs full sums)
+  const int kb = (K + 31) / 32, mb = (M + OT_MT - 1) / OT_MT;
+  int splits = 1;
+  if (pre == nullptr)
+    while (kb * mb * splits < 256 && N / (splits * 2) >= 128 && (N % (splits * 2 * 4)) == 0) splits *= 2;
+  const int n_per_split = (N + splits - 1) / splits;
+  if (splits > 1) PVRL_CUDA(cudaMemsetAsync(dA, 0, sizeof(float) * (size_t)M * K, STREAM));
+  dim3 grid(kb, mb, splits);
+  ot_linear_dx_kernel<<<grid, OT_THREADS, smem, STREAM>>>(dY, W, pre, dA, M, N, K, n_per_split);
   return launched("ot_linear_dx_kernel");
 }
 

@@ -1,15 +1,18 @@
 """Clip-level order / diffusion transformer (reference lib/models/tfm_model.py:70-289), SURVEY.md 8f-1.
 
-Kept in PyTorch for now (4 layers x 9 tokens x 512: < 0.1 % of the step's FLOPs) but re-expressed without the
-reference's host synchronisations: mask positions, pad starts and noise are drawn on the device and applied
-with masks instead of `.item()` loops (tfm_model.py:279-287) and `.cpu()` lookups (diffusion_model.py:346),
-so the whole pretrain step stays asynchronous.  Parameter names match the reference state_dict
+The pre-training path (`_pretrain`) runs on the `pvrl_ot_*` kernels through procedurevrl_b200.order_engine (5 launches
+per block forward, 11 backward, instead of ~1500 eager kernels per step) and has no host synchronisation: mask
+positions, pad starts and noise are drawn on the device instead of the reference's `.item()` loops
+(tfm_model.py:279-287) and `.cpu()` lookups (diffusion_model.py:346).  The forecasting path (`_forecast`, fine-tuning /
+evaluation only) is still expressed with torch modules.  Parameter names match the reference state_dict
 (`order_tfm.pad_embedding.weight`, `...temporalModelling.resblocks.i.attn.in_proj_weight`, `...time_mlp.1.weight`)."""
 import math
 from collections import OrderedDict
 
 import torch
 from torch import nn
+
+from ...order_engine import order_levels
 
 
 class QuickGELU(nn.Module):
@@ -81,6 +84,7 @@ class DiffusionTransformer(nn.Module):
         ac = torch.cumprod(1.0 - betas, dim=0)
         self.register_buffer("sqrt_alphas_cumprod", torch.sqrt(ac), persistent=False)
         self.register_buffer("sqrt_one_minus_alphas_cumprod", torch.sqrt(1.0 - ac), persistent=False)
+        self._sqrt_ac, self._sqrt_1mac = torch.sqrt(ac).tolist(), torch.sqrt(1.0 - ac).tolist()   # host copies: no sync
         self.fixed_draws = None      # tests inject (mask_inds, pad_start, noise[levels,B,C]) to replay the reference's draws
 
     def initialize_parameters(self):
@@ -114,8 +118,8 @@ class DiffusionTransformer(nn.Module):
     def _pretrain(self, x):
         """tfm_model.py:137-156,165-204: mask one clip per video, pad a random tail, denoise over the levels."""
         S, C = self.max_len, x.shape[1]
-        feats = x.reshape(-1, S, C).transpose(0, 1)                       # '(b t) c -> t b c'
-        B, dev = feats.shape[1], x.device
+        B, dev = x.shape[0] // S, x.device                                # rows of x are '(b t)': token (b, t) = row b*S + t
+        x = x.float().contiguous()
         if self.fixed_draws is not None:
             mask_inds, pad_start, noise = (t.to(dev) for t in self.fixed_draws)
         else:
@@ -125,22 +129,19 @@ class DiffusionTransformer(nn.Module):
             pad_start = mask_inds + 1 + (torch.rand(B, device=dev) * span).long().clamp(max=S)
             pad_start = torch.where(mask_inds + 1 == S, torch.full_like(mask_inds, S), pad_start.clamp(max=S - 1))
             noise = torch.randn(self.tfm_layers, B, C, device=dev)
-        pos = torch.arange(S, device=dev).unsqueeze(1)
-        is_mask = pos == mask_inds.unsqueeze(0)                           # [S, B]
-        pad = pos >= pad_start.unsqueeze(0)                               # [S, B]
-        x0 = (feats * is_mask.unsqueeze(-1)).sum(0)                       # clip embeddings that get masked out
-        feats = torch.where(pad.unsqueeze(-1), self.pad_embedding.weight[0], feats)
-        pad_mask = pad.t()
-        outs, den = [], None
-        for lvl in range(self.tfm_layers):
-            t_index = self.total_levels - 1 - lvl
-            src = (x0 if lvl == 0 else den).detach()
-            noisy = self.sqrt_alphas_cumprod[t_index] * src + self.sqrt_one_minus_alphas_cumprod[t_index] * noise[lvl]
-            lvl_feats = torch.where(is_mask.unsqueeze(-1), noisy.unsqueeze(0), feats)
-            den = self._level(lvl_feats, is_mask, t_index, pad_mask)
-            outs.append(den)
+        mask_inds, pad_start = mask_inds.long().contiguous(), pad_start.long().contiguous()
+        L = self.tfm_layers
+        rows = torch.arange(B, device=dev) * S + mask_inds
+        x0 = x.index_select(0, rows)                                      # clip embeddings that get masked out
+        # diffusion-time embeddings of all levels in one batched call (level lvl runs at t = L - 1 - lvl)
+        tvecs = self.time_mlp(torch.arange(L - 1, -1, -1, device=dev))
+        coef = [(float(self._sqrt_ac[L - 1 - lvl]), float(self._sqrt_1mac[L - 1 - lvl])) for lvl in range(L)]
+        inter = order_levels(self.temporalModelling.resblocks, x, tvecs, self.type_embedding.weight,
+                             self.temporalEmbedding.weight[:S], self.pad_embedding.weight, x0.detach(),
+                             noise.float().contiguous(), mask_inds, pad_start, B, S, self.tfm_heads, coef,
+                             eps=self.temporalModelling.resblocks[0].ln_1.eps)
+        den = inter[(L - 1) * B:]
         x0_target = x0.unsqueeze(0).expand(self.total_levels, -1, -1).reshape(-1, C)
-        inter = torch.cat(outs)
         return den, mask_inds, [x0_target, inter], inter
 
     def _forecast(self, x):

@@ -64,6 +64,19 @@ _SIGS = {
     "pvrl_kl_topk_loss": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float,
                           _c_void_p],
     "pvrl_softmax_rows": [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p],
+    "pvrl_ot_linear_fwd": [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_float, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                           _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
+    "pvrl_ot_linear_dx": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
+    "pvrl_ot_linear_dw": [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int,
+                          _c_void_p],
+    "pvrl_ot_ln_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
+                       _c_void_p],
+    "pvrl_ot_attn_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
+    "pvrl_ot_attn_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
+    "pvrl_ot_embed_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_float, _c_float, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                          _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
+    "pvrl_ot_embed_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int,
+                          _c_int, _c_int, _c_void_p],
 }
 
 _lib = None
@@ -280,3 +293,73 @@ def softmax_rows(x, y):
     M, K = x.shape
     _check(lib().pvrl_softmax_rows(_p(x), _p(y), M, K, _stream()), "pvrl_softmax_rows")
     return y
+
+
+# ---------------------------------------------------------------------------------------------- order transformer
+OT_X_PLAIN, OT_X_LN, OT_X_QGELU = 0, 1, 2
+
+
+def _f32c(*ts):
+    for t in ts:
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous()), "order-transformer ops take contiguous fp32"
+
+
+def ot_linear_fwd(x, W, bias, y, x_mode=OT_X_PLAIN, ln_w=None, ln_b=None, eps=1e-5, xhat=None, rstd=None, resid=None):
+    M, K = x.shape
+    N = W.shape[0]
+    _f32c(x, W, bias, y, ln_w, ln_b, xhat, rstd, resid)
+    _check(lib().pvrl_ot_linear_fwd(_p(x), x_mode, _p(ln_w), _p(ln_b), eps, _p(xhat), _p(rstd), _p(W), _p(bias), _p(resid),
+                                    _p(y), M, N, K, _stream()), "pvrl_ot_linear_fwd")
+    return y
+
+
+def ot_linear_dx(dY, W, dA, pre=None):
+    M, N = dY.shape
+    K = W.shape[1]
+    _f32c(dY, W, dA, pre)
+    _check(lib().pvrl_ot_linear_dx(_p(dY), _p(W), _p(pre), _p(dA), M, N, K, _stream()), "pvrl_ot_linear_dx")
+    return dA
+
+
+def ot_linear_dw(dY, A, dW, db, a_mode=OT_X_PLAIN, ln_w=None, ln_b=None):
+    M, N = dY.shape
+    K = A.shape[1]
+    _f32c(dY, A, dW, db, ln_w, ln_b)
+    _check(lib().pvrl_ot_linear_dw(_p(dY), _p(A), a_mode, _p(ln_w), _p(ln_b), _p(dW), _p(db), M, N, K, _stream()),
+           "pvrl_ot_linear_dw")
+
+
+def ot_ln_bwd(dA, xhat, rstd, w, dh, dw, db):
+    M, C = dA.shape
+    _f32c(dA, xhat, rstd, w, dh, dw, db)
+    _check(lib().pvrl_ot_ln_bwd(_p(dA), _p(xhat), _p(rstd), _p(w), _p(dh), _p(dw), _p(db), M, C, _stream()),
+           "pvrl_ot_ln_bwd")
+
+
+def ot_attn_fwd(qkv, pad_start, probs, o, B, S, H):
+    _f32c(qkv, probs, o)
+    assert pad_start is None or pad_start.dtype == torch.int64
+    _check(lib().pvrl_ot_attn_fwd(_p(qkv), _p(pad_start), _p(probs), _p(o), B, S, H, _stream()), "pvrl_ot_attn_fwd")
+    return o
+
+
+def ot_attn_bwd(qkv, probs, dO, dqkv, B, S, H):
+    _f32c(qkv, probs, dO, dqkv)
+    _check(lib().pvrl_ot_attn_bwd(_p(qkv), _p(probs), _p(dO), _p(dqkv), B, S, H, _stream()), "pvrl_ot_attn_bwd")
+    return dqkv
+
+
+def ot_embed_fwd(video, src, noise, ca, cb, mask_inds, pad_start, type_w, pos_w, pad_w, tvec, h, B, S):
+    C = video.shape[1]
+    _f32c(video, src, noise, type_w, pos_w, pad_w, tvec, h)
+    assert mask_inds.dtype == torch.int64 and pad_start.dtype == torch.int64
+    _check(lib().pvrl_ot_embed_fwd(_p(video), _p(src), _p(noise), ca, cb, _p(mask_inds), _p(pad_start), _p(type_w),
+                                   _p(pos_w), _p(pad_w), _p(tvec), _p(h), B, S, C, _stream()), "pvrl_ot_embed_fwd")
+    return h
+
+
+def ot_embed_bwd(dh, mask_inds, pad_start, dvideo, dtype, dpos, dpad, dtvec, B, S):
+    C = dh.shape[1]
+    _f32c(dh, dvideo, dtype, dpos, dpad, dtvec)
+    _check(lib().pvrl_ot_embed_bwd(_p(dh), _p(mask_inds), _p(pad_start), _p(dvideo), _p(dtype), _p(dpos), _p(dpad),
+                                   _p(dtvec), B, S, C, _stream()), "pvrl_ot_embed_bwd")

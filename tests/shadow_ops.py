@@ -303,4 +303,116 @@ def softmax_rows(x, y):
     return y
 
 
+# ---------------------------------------------------------------------------------------------- order transformer
+def _qgelu(u):
+    return u * torch.sigmoid(1.702 * u)
+
+
+def ot_linear_fwd(x, W, bias, y, x_mode=0, ln_w=None, ln_b=None, eps=1e-5, xhat=None, rstd=None, resid=None):
+    _launches[0] += 1
+    a = x
+    if x_mode == 1:
+        mean, var = x.mean(1, keepdim=True), x.var(1, unbiased=False, keepdim=True)
+        r = torch.rsqrt(var + eps)
+        xh = (x - mean) * r
+        a = xh * ln_w + ln_b
+        if xhat is not None:
+            xhat.copy_(xh)
+        if rstd is not None:
+            rstd.copy_(r.squeeze(1))
+    elif x_mode == 2:
+        a = _qgelu(x)
+    out = a @ W.t()
+    if bias is not None:
+        out = out + bias
+    if resid is not None:
+        out = out + resid
+    y.copy_(out)
+    return y
+
+
+def ot_linear_dx(dY, W, dA, pre=None):
+    _launches[0] += 1
+    g = dY @ W
+    if pre is not None:
+        s = torch.sigmoid(1.702 * pre)
+        g = g * (s * (1 + 1.702 * pre * (1 - s)))
+    dA.copy_(g)
+    return dA
+
+
+def ot_linear_dw(dY, A, dW, db, a_mode=0, ln_w=None, ln_b=None):
+    _launches[0] += 1
+    a = A * ln_w + ln_b if a_mode == 1 else (_qgelu(A) if a_mode == 2 else A)
+    dW += dY.t() @ a
+    if db is not None:
+        db += dY.sum(0)
+
+
+def ot_ln_bwd(dA, xhat, rstd, w, dh, dw, db):
+    _launches[0] += 1
+    g = dA * w
+    dh += rstd.unsqueeze(1) * (g - g.mean(1, keepdim=True) - xhat * (g * xhat).mean(1, keepdim=True))
+    dw += (dA * xhat).sum(0)
+    db += dA.sum(0)
+
+
+def _ot_split(qkv, B, S, H):
+    C = H * 64
+    q, k, v = (qkv[:, i * C:(i + 1) * C].reshape(B, S, H, 64).permute(0, 2, 1, 3) for i in range(3))
+    return q, k, v
+
+
+def ot_attn_fwd(qkv, pad_start, probs, o, B, S, H):
+    _launches[0] += 1
+    q, k, v = _ot_split(qkv, B, S, H)
+    s = (q * 0.125) @ k.transpose(-1, -2)
+    if pad_start is not None:
+        pad = torch.arange(S, device=qkv.device).view(1, 1, 1, S) >= pad_start.view(B, 1, 1, 1)
+        s = s.masked_fill(pad, float("-inf"))
+    p = s.softmax(-1)
+    probs.copy_(p)
+    o.copy_((p @ v).permute(0, 2, 1, 3).reshape(B * S, H * 64))
+    return o
+
+
+def ot_attn_bwd(qkv, probs, dO, dqkv, B, S, H):
+    _launches[0] += 1
+    q, k, v = _ot_split(qkv, B, S, H)
+    do = dO.reshape(B, S, H, 64).permute(0, 2, 1, 3)
+    dp = do @ v.transpose(-1, -2)
+    ds = probs * (dp - (probs * dp).sum(-1, keepdim=True))
+    dq, dk, dv = ds @ k * 0.125, ds.transpose(-1, -2) @ q * 0.125, probs.transpose(-1, -2) @ do
+    dqkv.copy_(torch.cat([t.permute(0, 2, 1, 3).reshape(B * S, H * 64) for t in (dq, dk, dv)], dim=1))
+    return dqkv
+
+
+def ot_embed_fwd(video, src, noise, ca, cb, mask_inds, pad_start, type_w, pos_w, pad_w, tvec, h, B, S):
+    _launches[0] += 1
+    C = video.shape[1]
+    s_idx = torch.arange(S, device=video.device).view(1, S)
+    is_mask = (s_idx == mask_inds.view(B, 1)).unsqueeze(-1)
+    is_pad = (s_idx >= pad_start.view(B, 1)).unsqueeze(-1)
+    x = torch.where(is_pad, pad_w.view(1, 1, C), video.view(B, S, C))
+    x = torch.where(is_mask, (ca * src + cb * noise).view(B, 1, C), x)
+    x = x + torch.where(is_mask, type_w[1].view(1, 1, C), type_w[0].view(1, 1, C)) + pos_w.view(1, S, C) + tvec.view(1, 1, C)
+    h.copy_(x.reshape(B * S, C))
+    return h
+
+
+def ot_embed_bwd(dh, mask_inds, pad_start, dvideo, dtype, dpos, dpad, dtvec, B, S):
+    _launches[0] += 1
+    C = dh.shape[1]
+    g = dh.view(B, S, C)
+    s_idx = torch.arange(S, device=dh.device).view(1, S)
+    is_mask = (s_idx == mask_inds.view(B, 1)).unsqueeze(-1)
+    is_pad = (s_idx >= pad_start.view(B, 1)).unsqueeze(-1) & ~is_mask
+    dtvec.copy_(g.sum((0, 1)))
+    dpos += g.sum(0)
+    dtype[1] += (g * is_mask).sum((0, 1))
+    dtype[0] += (g * ~is_mask).sum((0, 1))
+    dpad.view(-1).add_((g * is_pad).sum((0, 1)))
+    dvideo += (g * (~is_mask & ~is_pad)).reshape(B * S, C)
+
+
 ALL = [n for n, v in list(globals().items()) if callable(v) and not n.startswith("_") and n not in ("F", "math", "torch")]

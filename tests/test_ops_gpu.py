@@ -256,7 +256,7 @@ def test_gather_cast_clsmerge_colsum_castweight_embedbwd(ops):
 
 
 # ------------------------------------------------------------------------------------------------ attention
-@pytest.mark.parametrize("n_seq,seq,H", [(37, 8, 12), (5, 4, 12), (3, 32, 12), (4, 197, 12), (1, 460, 2)])
+@pytest.mark.parametrize("n_seq,seq,H", [(37, 8, 12), (5, 4, 12), (3, 7, 5), (1, 1, 1), (3528, 8, 12), (3, 32, 12), (4, 197, 12), (1, 460, 2)])
 def test_attn_simt(ops, n_seq, seq, H):
     C = H * 64
     scale = 64 ** -0.5
@@ -356,3 +356,128 @@ def test_attn_tensor_core(ops, n_seq, seq, H):
             bad = (err > 0.05 * g[:, sl].abs().max()).nonzero()
             print("first bad idx:", bad[:10].tolist(), "n_bad", bad.shape[0])
         assert rel < 3e-2
+
+
+# ------------------------------------------------------------------------------------------------ order transformer
+# Each pvrl_ot_* kernel against its torch restatement (tests/shadow_ops.py, run on the same device), fp32, rtol 1e-4;
+# then one ResidualAttentionBlock level end to end against torch.nn.MultiheadAttention / LayerNorm autograd.
+def _close(name, got, ref, tol=2e-4):
+    err, rel = _report(name, got, ref)
+    assert rel < tol, name
+
+
+@pytest.mark.parametrize("M,N,K", [(18, 1536, 512), (18, 512, 2048), (45, 2048, 512), (3, 512, 128)])
+def test_ot_linear(ops, M, N, K):
+    import shadow_ops as S
+    x, W, b, res = _rand(M, K, seed=1), _rand(N, K, seed=2, scale=0.05), _rand(N, seed=3), _rand(M, N, seed=4)
+    lw, lb = 1 + 0.1 * _rand(K, seed=5), 0.1 * _rand(K, seed=6)
+    for mode in (0, 1, 2):
+        if mode == 1 and K > 512:
+            continue
+        y, yr = torch.empty(M, N, device="cuda"), torch.empty(M, N, device="cuda")
+        xh, rs = torch.empty(M, K, device="cuda"), torch.empty(M, device="cuda")
+        xhr, rsr = torch.empty_like(xh), torch.empty_like(rs)
+        ops.ot_linear_fwd(x, W, b, y, mode, lw, lb, 1e-5, xh, rs, resid=res)
+        S.ot_linear_fwd(x, W, b, yr, mode, lw, lb, 1e-5, xhr, rsr, resid=res)
+        _close(f"ot_linear_fwd mode{mode}", y, yr)
+        if mode == 1:
+            _close("ot xhat", xh, xhr), _close("ot rstd", rs, rsr)
+    dY = _rand(M, N, seed=7)
+    pre = _rand(M, K, seed=8)
+    for p in (None, pre):
+        dA, dAr = torch.empty(M, K, device="cuda"), torch.empty(M, K, device="cuda")
+        ops.ot_linear_dx(dY, W, dA, pre=p)
+        S.ot_linear_dx(dY, W, dAr, pre=p)
+        _close("ot_linear_dx", dA, dAr)
+    for mode in (0, 1, 2):
+        dW, db = _rand(N, K, seed=9), _rand(N, seed=10)
+        dWr, dbr = dW.clone(), db.clone()
+        ops.ot_linear_dw(dY, x, dW, db, mode, lw, lb)
+        S.ot_linear_dw(dY, x, dWr, dbr, mode, lw, lb)
+        _close(f"ot_linear_dw mode{mode}", dW, dWr), _close("ot db", db, dbr)
+
+
+def test_ot_ln_attn_embed(ops):
+    import shadow_ops as S
+    B, Sq, H, C = 3, 9, 8, 512
+    M = B * Sq
+    dA, xh, rs, w = _rand(M, C, seed=1), _rand(M, C, seed=2), _rand(M, seed=3).abs() + 0.5, 1 + 0.1 * _rand(C, seed=4)
+    outs = []
+    for fn in (ops.ot_ln_bwd, S.ot_ln_bwd):
+        dh, dw, db = _rand(M, C, seed=5), _rand(C, seed=6), _rand(C, seed=7)
+        fn(dA, xh, rs, w, dh, dw, db)
+        outs.append((dh, dw, db))
+    for a, b, n in zip(outs[0], outs[1], ("dh", "dw", "db")):
+        _close("ot_ln_bwd " + n, a, b)
+    qkv, dO = _rand(M, 3 * C, seed=8), _rand(M, C, seed=9)
+    pad = torch.tensor([9, 4, 6], device="cuda")
+    res = []
+    for mod in (ops, S):
+        probs, o, dqkv = torch.empty(B, H, Sq, Sq, device="cuda"), torch.empty(M, C, device="cuda"), torch.empty(M, 3 * C, device="cuda")
+        mod.ot_attn_fwd(qkv, pad, probs, o, B, Sq, H)
+        mod.ot_attn_bwd(qkv, probs, dO, dqkv, B, Sq, H)
+        res.append((probs, o, dqkv))
+    for a, b, n in zip(res[0], res[1], ("probs", "o", "dqkv")):
+        _close("ot_attn " + n, a, b)
+    # attention against torch.nn.functional.multi_head_attention-style autograd
+    q, k, v = (qkv[:, i * C:(i + 1) * C].reshape(B, Sq, H, 64).permute(0, 2, 1, 3).clone().requires_grad_(True) for i in range(3))
+    msk = (torch.arange(Sq, device="cuda").view(1, 1, 1, Sq) >= pad.view(B, 1, 1, 1))
+    oo = torch.nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=~msk)
+    oo.backward(dO.reshape(B, Sq, H, 64).permute(0, 2, 1, 3))
+    _close("ot_attn o vs sdpa", res[0][1], oo.permute(0, 2, 1, 3).reshape(M, C))
+    _close("ot_attn dq vs sdpa", res[0][2][:, :C], q.grad.permute(0, 2, 1, 3).reshape(M, C))
+    _close("ot_attn dv vs sdpa", res[0][2][:, 2 * C:], v.grad.permute(0, 2, 1, 3).reshape(M, C))
+    # level input and its backward
+    video, src, noise = _rand(M, C, seed=11), _rand(B, C, seed=12), _rand(B, C, seed=13)
+    tw, pw, padw, tv = _rand(2, C, seed=14), _rand(Sq, C, seed=15), _rand(1, C, seed=16), _rand(C, seed=17)
+    mk = torch.tensor([8, 1, 3], device="cuda")
+    res = []
+    for mod in (ops, S):
+        h = torch.empty(M, C, device="cuda")
+        mod.ot_embed_fwd(video, src, noise, 0.9, 0.3, mk, pad, tw, pw, padw, tv, h, B, Sq)
+        dv_, dt_, dp_, dpad_, dtv_ = _rand(M, C, seed=18), _rand(2, C, seed=19), _rand(Sq, C, seed=20), _rand(1, C, seed=21), torch.empty(C, device="cuda")
+        mod.ot_embed_bwd(dA, mk, pad, dv_, dt_, dp_, dpad_, dtv_, B, Sq)
+        res.append((h, dv_, dt_, dp_, dpad_, dtv_))
+    for a, b, n in zip(res[0], res[1], ("h", "dvideo", "dtype", "dpos", "dpad", "dtvec")):
+        _close("ot_embed " + n, a, b)
+
+
+def test_order_levels_vs_torch_modules(ops):
+    """The whole pre-training branch of the order transformer on the kernels vs the same module evaluated with torch's
+    own MultiheadAttention / LayerNorm / autograd (the op-by-op expression the reference uses, tfm_model.py:165-204)."""
+    from procedurevrl_b200.lib.config import get_cfg
+    from procedurevrl_b200.lib.models.order_tfm import DiffusionTransformer
+    torch.manual_seed(3)
+    m = DiffusionTransformer(num_seg=8, tfm_layers=4, hidden_size=512, cfg=get_cfg()).cuda().train()
+    B, S, C, L = 2, m.max_len, 512, 4
+    x = torch.nn.functional.normalize(_rand(B * S, C, seed=1), dim=1).requires_grad_(True)
+    mask, pad, noise = torch.tensor([2, 8], device="cuda"), torch.tensor([5, 9], device="cuda"), _rand(L, B, C, seed=2)
+    m.fixed_draws = (mask, pad, noise)
+    wts = _rand(L * B, C, seed=5)
+    den, _, mse, inter = m(x, is_pretrain=True)
+    ((inter * wts).sum() + torch.nn.functional.mse_loss(mse[0], mse[1])).backward()
+    got = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+    gx = x.grad.clone()
+    # torch-module restatement of the same levels
+    m.zero_grad(set_to_none=True)
+    x2 = x.detach().clone().requires_grad_(True)
+    feats = x2.reshape(B, S, C).transpose(0, 1)
+    pos = torch.arange(S, device="cuda").unsqueeze(1)
+    is_mask, padm = pos == mask.unsqueeze(0), pos >= pad.unsqueeze(0)
+    x0 = (feats * is_mask.unsqueeze(-1)).sum(0)
+    feats = torch.where(padm.unsqueeze(-1), m.pad_embedding.weight[0], feats)
+    outs, d = [], None
+    for lvl in range(L):
+        t = L - 1 - lvl
+        src = (x0 if lvl == 0 else d).detach()
+        noisy = m.sqrt_alphas_cumprod[t] * src + m.sqrt_one_minus_alphas_cumprod[t] * noise[lvl]
+        d = m._level(torch.where(is_mask.unsqueeze(-1), noisy.unsqueeze(0), feats), is_mask, t, padm.t())
+        outs.append(d)
+    inter_ref = torch.cat(outs)
+    x0t = x0.unsqueeze(0).expand(L, -1, -1).reshape(-1, C)
+    ((inter_ref * wts).sum() + torch.nn.functional.mse_loss(x0t, inter_ref)).backward()
+    _close("order inter", inter, inter_ref, 5e-4)
+    _close("order dx", gx, x2.grad, 2e-3)
+    for n, p in m.named_parameters():
+        if p.grad is not None:
+            _close("order grad " + n, got[n], p.grad, 2e-3)
