@@ -77,6 +77,7 @@ typedef struct pvrl_gemm {
   const float* add_time; /* RESID+MAP_PATCH: time_embed [T, N]      (vit.py:393-404) */
   pvrl_geom_t g;
   int32_t k_splits;  /* ATOMIC only: 0 = auto                             */
+  float* colsum;     /* STORE / DGELU: NULL or fp32 [N] += column sums of the stored output (fused bias gradient) */
 } pvrl_gemm_t;
 
 int pvrl_gemm_bf16(const pvrl_gemm_t* d, void* stream);
@@ -102,9 +103,10 @@ int pvrl_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const f
                        pvrl_geom_t g, void* stream);
 
 /* out[m] = act( rowscale[m/rs_div] * clsf(m) * src[map(m)] ), fp32 -> act dtype.  clsf = 1/T on the cls rows of
- * MAP_SPATIAL (backward of the mean over frames, vit.py:147-149), else 1. */
+ * MAP_SPATIAL (backward of the mean over frames, vit.py:147-149), else 1.  colsum (NULL or fp32 [D]) += sum_m out[m]:
+ * the bias gradient of the Linear whose dY this is, fused so that dY is not read a second time. */
 int pvrl_gather_cast(const float* src, void* out, int32_t out_dtype, const float* rowscale, int32_t rs_div,
-                     int32_t M, int32_t D, int32_t map, pvrl_geom_t g, void* stream);
+                     int32_t M, int32_t D, int32_t map, pvrl_geom_t g, float* colsum, void* stream);
 
 /* x2[b,0,:] = x0[b,0,:] + mean_t side[b*T+t,:]   (vit.py:147-149,156) */
 int pvrl_cls_merge(const float* x0, const float* side, float* x2, int32_t Bc, int32_t T, int32_t S, int32_t D,

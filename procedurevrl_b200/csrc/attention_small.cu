@@ -150,8 +150,9 @@ attn_small_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ out, cons
     if (qq < seq) {
       ld8<T>(qb + qq * pitch, t8);                  // q_q
       ld8<T>(dob + (long long)qq * C, u8);          // dO_q
-      const float p = __expf(octet_sum(dot8(t8, kj)) * scale - s_lse[lp * seq + qq]);
-      const float ds = p * (octet_sum(dot8(u8, vj)) - s_delta[lp * seq + qq]) * scale;
+      const int sr = active ? lp * seq + qq : 0;   // idle octets (rows past the last whole sequence) stay in bounds
+      const float p = __expf(octet_sum(dot8(t8, kj)) * scale - s_lse[sr]);
+      const float ds = p * (octet_sum(dot8(u8, vj)) - s_delta[sr]) * scale;
 #pragma unroll
       for (int d = 0; d < 8; ++d) {
         dv[d] = fmaf(p, u8[d], dv[d]);

@@ -208,23 +208,40 @@ int layernorm_bwd_launch(const void* dy, const float* x, const float* x_cls, con
 }
 
 // ---------------------------------------------------------------------------------------- gather + cast
+// One block = D/4 threads, thread c owns 4 feature columns and walks the block's rows (4 rows in flight): every row
+// access is one contiguous D*4-byte burst, and because a thread keeps its columns the bias gradient colsum(out) comes
+// for free (registers -> one fp32 atomic per column and block) -- the separate pvrl_colsum pass over dY disappears.
 template <typename OutT>
 __global__ void gather_cast_kernel(const float* __restrict__ src, OutT* __restrict__ out,
-                                   const float* __restrict__ rowscale, int rs_div, int M, int D, int map, Geom g) {
-  const int vec_per_row = D >> 2;
-  const long long total = (long long)M * vec_per_row;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int m = static_cast<int>(i / vec_per_row);
-    const int c = static_cast<int>(i - (long long)m * vec_per_row) * 4;
-    long long r = map_row(map, m, g);
-    float f = rowscale != nullptr ? __ldg(rowscale + m / rs_div) : 1.0f;
-    if (r < 0) {  // cls row of a spatial sequence: d(mean over T) = 1/T
-      r = ((-r - 1) / g.T) * (long long)g.S;
-      f *= 1.0f / g.T;
+                                   const float* __restrict__ rowscale, int rs_div, int M, int D, int map, Geom g,
+                                   float* __restrict__ colsum) {
+  const int c = threadIdx.x * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int m0 = blockIdx.x * 4; m0 < M; m0 += gridDim.x * 4) {
+    float4 v[4];
+    float f[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int m = min(m0 + u, M - 1);
+      long long r = map_row(map, m, g);
+      f[u] = rowscale != nullptr ? __ldg(rowscale + m / rs_div) : 1.0f;
+      if (r < 0) {  // cls row of a spatial sequence: d(mean over T) = 1/T
+        r = ((-r - 1) / g.T) * (long long)g.S;
+        f[u] *= 1.0f / g.T;
+      }
+      v[u] = __ldg(reinterpret_cast<const float4*>(src + r * D + c));
     }
-    const float4 v = __ldg(reinterpret_cast<const float4*>(src + r * D + c));
-    store4<OutT>(out + (long long)m * D + c, v.x * f, v.y * f, v.z * f, v.w * f);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (m0 + u < M) {
+        const float4 o = make_float4(v[u].x * f[u], v[u].y * f[u], v[u].z * f[u], v[u].w * f[u]);
+        store4<OutT>(out + (long long)(m0 + u) * D + c, o.x, o.y, o.z, o.w);
+        acc.x += o.x, acc.y += o.y, acc.z += o.z, acc.w += o.w;
+      }
+  }
+  if (colsum != nullptr) {
+    atomicAdd(colsum + c, acc.x), atomicAdd(colsum + c + 1, acc.y), atomicAdd(colsum + c + 2, acc.z),
+        atomicAdd(colsum + c + 3, acc.w);
   }
 }
 
@@ -395,17 +412,19 @@ extern "C" int pvrl_layernorm_bwd(const void* dy, int32_t dy_dtype, const float*
 }
 
 extern "C" int pvrl_gather_cast(const float* src, void* out, int32_t out_dtype, const float* rowscale, int32_t rs_div,
-                                int32_t M, int32_t D, int32_t map, pvrl_geom_t g, void* stream) {
-  PVRL_CHECK_ARG(src && out && M > 0 && D % 4 == 0, "pvrl_gather_cast: bad arguments");
+                                int32_t M, int32_t D, int32_t map, pvrl_geom_t g, float* colsum, void* stream) {
+  PVRL_CHECK_ARG(src && out && M > 0 && D % 4 == 0 && D <= 4096, "pvrl_gather_cast: bad arguments");
   PVRL_CHECK_ARG(rowscale == nullptr || rs_div > 0, "pvrl_gather_cast: rowscale needs rs_div > 0");
   const Geom gg(g.T > 0 ? g.T : 1, g.HW > 0 ? g.HW : 1);
-  const int grid = grid_for((long long)M * (D / 4), 256);
+  const int block = D / 4;
+  int grid = (M + 3) / 4;
+  if (grid > 148 * 8) grid = 148 * 8;
   if (out_dtype == PVRL_F32)
-    gather_cast_kernel<float>
-        <<<grid, 256, 0, STREAM>>>(src, static_cast<float*>(out), rowscale, rs_div > 0 ? rs_div : 1, M, D, map, gg);
+    gather_cast_kernel<float><<<grid, block, 0, STREAM>>>(src, static_cast<float*>(out), rowscale,
+                                                          rs_div > 0 ? rs_div : 1, M, D, map, gg, colsum);
   else
-    gather_cast_kernel<__nv_bfloat16><<<grid, 256, 0, STREAM>>>(src, static_cast<__nv_bfloat16*>(out), rowscale,
-                                                                 rs_div > 0 ? rs_div : 1, M, D, map, gg);
+    gather_cast_kernel<__nv_bfloat16><<<grid, block, 0, STREAM>>>(src, static_cast<__nv_bfloat16*>(out), rowscale,
+                                                                  rs_div > 0 ? rs_div : 1, M, D, map, gg, colsum);
   return launched("gather_cast_kernel");
 }
 

@@ -45,6 +45,7 @@ struct GemmArgs {
   const float* resid;
   const float* add_pos;
   const float* add_time;
+  float* colsum;
   Geom g;
 };
 
@@ -102,7 +103,7 @@ __device__ __forceinline__ float4 load_side(const GemmArgs& p, int m, const RowC
 }
 
 template <int EPI, typename OutT>
-__device__ __forceinline__ void epilogue_vec4(const GemmArgs& p, int m, const RowCtx& rc, int n, float4 v,
+__device__ __forceinline__ void epilogue_vec4(const GemmArgs& p, int m, const RowCtx& rc, int n, float4& v,
                                               const float4& bias4, const float4& side) {
   if (EPI == PVRL_EPI_ATOMIC) {
     float* dst = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + n;
@@ -306,6 +307,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       constexpr int NCH = HALF_COLS / 32;
       constexpr bool HAS_SIDE = EPI == PVRL_EPI_RESID || EPI == PVRL_EPI_DGELU;
+      constexpr bool HAS_COLSUM = EPI == PVRL_EPI_STORE || EPI == PVRL_EPI_DGELU;
       const int n_first = n_blk * BN + half * HALF_COLS + piece * 4;   // this lane's columns in chunk 0
       float4 side[2][8];
       if (HAS_SIDE && n_first < p.N) {
@@ -335,12 +337,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int n = n0 + piece * 4;
           float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (EPI != PVRL_EPI_ATOMIC && p.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+          float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int row = 4 * i + rsub;
-            const float4 v = *reinterpret_cast<const float4*>(stg + row * 128 + ((piece ^ (row & 7)) << 4));
+            float4 v = *reinterpret_cast<const float4*>(stg + row * 128 + ((piece ^ (row & 7)) << 4));
             const int m = m_base + row;
-            if (m < p.M) epilogue_vec4<EPI, OutT>(p, m, rc[i], n, v, bias4, HAS_SIDE ? side[c & 1][i] : bias4);
+            if (m < p.M) {
+              epilogue_vec4<EPI, OutT>(p, m, rc[i], n, v, bias4, HAS_SIDE ? side[c & 1][i] : bias4);
+              if (HAS_COLSUM) add4(csum, v);
+            }
+          }
+          if (HAS_COLSUM && p.colsum != nullptr) {   // fused bias gradient: column sums of what was just stored
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+              csum.x += __shfl_xor_sync(0xffffffffu, csum.x, o), csum.y += __shfl_xor_sync(0xffffffffu, csum.y, o);
+              csum.z += __shfl_xor_sync(0xffffffffu, csum.z, o), csum.w += __shfl_xor_sync(0xffffffffu, csum.w, o);
+            }
+            if (rsub == 0)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.colsum + n), "f"(csum.x), "f"(csum.y),
+                           "f"(csum.z), "f"(csum.w)
+                           : "memory");
           }
           __syncwarp();
         }
@@ -499,6 +516,9 @@ extern "C" int pvrl_gemm_bf16(const pvrl_gemm_t* d, void* stream_) {
   if (d->epilogue == PVRL_EPI_GELU) PVRL_CHECK_ARG(d->out2 != nullptr, "pvrl_gemm_bf16: GELU needs out2");
   if (d->epilogue == PVRL_EPI_DGELU) PVRL_CHECK_ARG(d->aux != nullptr, "pvrl_gemm_bf16: DGELU needs aux");
   if (d->rowscale) PVRL_CHECK_ARG(d->rs_div > 0, "pvrl_gemm_bf16: rowscale needs rs_div > 0");
+  if (d->colsum)
+    PVRL_CHECK_ARG(d->epilogue == PVRL_EPI_STORE || d->epilogue == PVRL_EPI_DGELU,
+                   "pvrl_gemm_bf16: colsum is fused into the STORE / DGELU epilogues only");
   if (d->map == PVRL_MAP_SPATIAL)
     PVRL_CHECK_ARG(d->epilogue == PVRL_EPI_RESID && d->out2 != nullptr,
                    "pvrl_gemm_bf16: MAP_SPATIAL needs the RESID epilogue and a cls side buffer");
@@ -509,6 +529,7 @@ extern "C" int pvrl_gemm_bf16(const pvrl_gemm_t* d, void* stream_) {
   a.bias = d->bias, a.rowscale = d->rowscale, a.rs_div = d->rs_div > 0 ? d->rs_div : 1;
   a.map = d->map, a.aux = d->aux, a.ld_aux = d->ld_aux, a.resid = d->resid;
   a.add_pos = d->add_pos, a.add_time = d->add_time;
+  a.colsum = d->colsum;
   a.g = Geom(d->g.T > 0 ? d->g.T : 1, d->g.HW > 0 ? d->g.HW : 1);
 
   const int num_kb = (d->K + BK - 1) / BK;

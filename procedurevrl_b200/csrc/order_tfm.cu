@@ -40,7 +40,8 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // x_mode: 0 = x as is, 1 = LayerNorm(x) (block column 0 also writes xhat / rstd for the backward), 2 = QuickGELU(x).
 // These kernels are latency-bound (a few dozen rows): the row tile [mt][K] is fetched with cp.async (every 16-byte
 // piece in flight at once, no register staging) while the warp's whole weight row streams into registers.
-__global__ void __launch_bounds__(OT_THREADS, 1)
+template <int KJ>   // K <= 128 * KJ: KJ = 4 keeps two blocks per SM resident (one wave for N <= 2368 columns)
+__global__ void __launch_bounds__(OT_THREADS, KJ <= 4 ? 2 : 1)
 ot_linear_fwd_kernel(const float* __restrict__ x, int x_mode, const float* __restrict__ ln_w,
                      const float* __restrict__ ln_b, float eps, float* __restrict__ xhat_out,
                      float* __restrict__ rstd_out, const float* __restrict__ W, const float* __restrict__ bias,
@@ -52,9 +53,9 @@ ot_linear_fwd_kernel(const float* __restrict__ x, int x_mode, const float* __res
   const int n = blockIdx.x * 8 + warp;
   const int k4n = K >> 2;
   for (int i = threadIdx.x; i < rows * k4n; i += OT_THREADS) cp_async16(xs + 4 * i, x + (long long)m0 * K + 4 * i);
-  float4 wreg[OT_KMAX / 128];
+  float4 wreg[KJ];
 #pragma unroll
-  for (int j = 0; j < OT_KMAX / 128; ++j)
+  for (int j = 0; j < KJ; ++j)
     if (n < N && j * 128 < K) wreg[j] = __ldg(reinterpret_cast<const float4*>(W + (long long)n * K + j * 128 + lane * 4));
   float acc[OT_MT];
 #pragma unroll
@@ -90,7 +91,7 @@ ot_linear_fwd_kernel(const float* __restrict__ x, int x_mode, const float* __res
   }
   if (n < N) {
 #pragma unroll
-    for (int j = 0; j < OT_KMAX / 128; ++j) {
+    for (int j = 0; j < KJ; ++j) {
       if (j * 128 < K) {
         const float4 w4 = wreg[j];
 #pragma unroll
@@ -413,12 +414,17 @@ extern "C" int pvrl_ot_linear_fwd(const float* x, int32_t x_mode, const float* l
   const int smem = mt * K * 4;
   static bool configured = false;
   if (!configured) {
-    PVRL_CUDA(cudaFuncSetAttribute(ot_linear_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    PVRL_CUDA(cudaFuncSetAttribute(ot_linear_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    PVRL_CUDA(cudaFuncSetAttribute(ot_linear_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
   dim3 grid((N + 7) / 8, (M + mt - 1) / mt);
-  ot_linear_fwd_kernel<<<grid, OT_THREADS, smem, STREAM>>>(x, x_mode, ln_w, ln_b, eps, xhat_out, rstd_out, W, bias, resid,
-                                                           y, M, N, K, mt);
+  if (K <= 512)
+    ot_linear_fwd_kernel<4><<<grid, OT_THREADS, smem, STREAM>>>(x, x_mode, ln_w, ln_b, eps, xhat_out, rstd_out, W, bias,
+                                                                resid, y, M, N, K, mt);
+  else
+    ot_linear_fwd_kernel<16><<<grid, OT_THREADS, smem, STREAM>>>(x, x_mode, ln_w, ln_b, eps, xhat_out, rstd_out, W, bias,
+                                                                 resid, y, M, N, K, mt);
   return launched("ot_linear_fwd_kernel");
 }
 

@@ -115,7 +115,8 @@ class EncoderEngine:
         ops.gemm(A, wt, out, M=M, N=N, K=Keff, **epi)
 
     def linear_dw(self, dy, x, gw, gb, Mc, N_w, K_w):
-        """gw[N_w, K_w] += dy[Mc, N_w]^T x[Mc, K_w];  gb[N_w] += colsum(dy)."""
+        """gw[N_w, K_w] += dy[Mc, N_w]^T x[Mc, K_w];  gb[N_w] += colsum(dy) (gb = None when the kernel that produced
+        dy already accumulated the bias gradient -- `colsum=` of ops.gather_cast / ops.gemm)."""
         if gb is not None:
             ops.colsum(dy, gb, Mc, N_w)
         if not self.x3:
@@ -283,9 +284,8 @@ class EncoderEngine:
         KP = 3 * self.patch * self.patch
         Mp = Bc * T * HW
         dYp = self._act(Mp, D, dev)
-        ops.gather_cast(dx, dYp, Mp, D, ops.MAP_PATCH, **g)
-        self.linear_dw(dYp, st["A"], G[self.pre + "patch_embed.proj.weight"].view(D, KP),
-                       G[self.pre + "patch_embed.proj.bias"], Mp, D, KP)
+        ops.gather_cast(dx, dYp, Mp, D, ops.MAP_PATCH, colsum=G[self.pre + "patch_embed.proj.bias"], **g)
+        self.linear_dw(dYp, st["A"], G[self.pre + "patch_embed.proj.weight"].view(D, KP), None, Mp, D, KP)
         gpos, gte = G[self.pre + "pos_embed"][0], G[self.pre + "time_embed"][0]
         dpos = gpos if st["pos_idx"] is None else torch.zeros(HW + 1, D, device=dev)
         dte = gte if st["te_idx"] is None else torch.zeros(T, D, device=dev)
@@ -308,11 +308,12 @@ class EncoderEngine:
 
         # ---- MLP: x3 = x2 + s_m * (fc2(gelu(fc1(LN(x2)))))
         dY = self._act(Mm, D, dev)
-        ops.gather_cast(dx, dY, Mm, D, ops.MAP_IDENT, rowscale=dp.get("mlp"), rs_div=S)
-        self.linear_dw(dY, sv["hid"], G[b + "mlp.fc2.weight"], G[b + "mlp.fc2.bias"], Mm, D, Hd)
+        ops.gather_cast(dx, dY, Mm, D, ops.MAP_IDENT, rowscale=dp.get("mlp"), rs_div=S, colsum=G[b + "mlp.fc2.bias"])
+        self.linear_dw(dY, sv["hid"], G[b + "mlp.fc2.weight"], None, Mm, D, Hd)
         d_pre = self._act(Mm, Hd, dev)
-        self.linear_dx(dY, b + "mlp.fc2.weight", d_pre, Mm, Hd, D, epilogue=ops.EPI_DGELU, aux=sv["dact"])
-        self.linear_dw(d_pre, sv["ln_m"], G[b + "mlp.fc1.weight"], G[b + "mlp.fc1.bias"], Mm, Hd, D)
+        self.linear_dx(dY, b + "mlp.fc2.weight", d_pre, Mm, Hd, D, epilogue=ops.EPI_DGELU, aux=sv["dact"],
+                       colsum=G[b + "mlp.fc1.bias"])
+        self.linear_dw(d_pre, sv["ln_m"], G[b + "mlp.fc1.weight"], None, Mm, Hd, D)
         d_ln = self._act(Mm, D, dev)
         self.linear_dx(d_pre, b + "mlp.fc1.weight", d_ln, Mm, D, Hd)
         del d_pre
@@ -321,8 +322,9 @@ class EncoderEngine:
 
         # ---- spatial: tokens x2 = x1 + s_s * proj(attn(LN(gather(x0 cls, x1)))), cls = x0 cls + mean_t(...)
         dYs = self._act(Ms, D, dev)
-        ops.gather_cast(dx, dYs, Ms, D, ops.MAP_SPATIAL, rowscale=dp.get("spatial"), rs_div=HW + 1, **g)
-        self.linear_dw(dYs, sv["o_s"], G[b + "attn.proj.weight"], G[b + "attn.proj.bias"], Ms, D, D)
+        ops.gather_cast(dx, dYs, Ms, D, ops.MAP_SPATIAL, rowscale=dp.get("spatial"), rs_div=HW + 1,
+                        colsum=G[b + "attn.proj.bias"], **g)
+        self.linear_dw(dYs, sv["o_s"], G[b + "attn.proj.weight"], None, Ms, D, D)
         d_o = self._act(Ms, D, dev)
         self.linear_dx(dYs, b + "attn.proj.weight", d_o, Ms, D, D)
         dqkv = self._act(Ms, 3 * D, dev)
@@ -335,11 +337,12 @@ class EncoderEngine:
 
         # ---- temporal: x1 = x0[:,1:] + fc(s_t * proj(attn(LN(x0[:,1:]))))
         dYf = self._act(Mt, D, dev)
-        ops.gather_cast(dx, dYf, Mt, D, ops.MAP_SKIPCLS, **g)
-        self.linear_dw(dYf, sv["p_t"], G[b + "temporal_fc.weight"], G[b + "temporal_fc.bias"], Mt, D, D)
+        ops.gather_cast(dx, dYf, Mt, D, ops.MAP_SKIPCLS, colsum=G[b + "temporal_fc.bias"], **g)
+        self.linear_dw(dYf, sv["p_t"], G[b + "temporal_fc.weight"], None, Mt, D, D)
         d_p = self._act(Mt, D, dev)
-        self.linear_dx(dYf, b + "temporal_fc.weight", d_p, Mt, D, D, rowscale=dp.get("temporal"), rs_div=T)
-        self.linear_dw(d_p, sv["o_t"], G[b + "temporal_attn.proj.weight"], G[b + "temporal_attn.proj.bias"], Mt, D, D)
+        self.linear_dx(dYf, b + "temporal_fc.weight", d_p, Mt, D, D, rowscale=dp.get("temporal"), rs_div=T,
+                       colsum=G[b + "temporal_attn.proj.bias"])
+        self.linear_dw(d_p, sv["o_t"], G[b + "temporal_attn.proj.weight"], None, Mt, D, D)
         d_o = self._act(Mt, D, dev)
         self.linear_dx(d_p, b + "temporal_attn.proj.weight", d_o, Mt, D, D)
         dqkv = self._act(Mt, 3 * D, dev)

@@ -30,7 +30,7 @@ class GemmDesc(ctypes.Structure):
         ("bias", _c_void_p), ("rowscale", _c_void_p), ("rs_div", _c_int), ("map", _c_int),
         ("aux", _c_void_p), ("ld_aux", _c_i64),
         ("resid", _c_void_p), ("add_pos", _c_void_p), ("add_time", _c_void_p),
-        ("g", Geom), ("k_splits", _c_int),
+        ("g", Geom), ("k_splits", _c_int), ("colsum", _c_void_p),
     ]
 
 
@@ -42,7 +42,8 @@ _SIGS = {
                            _c_float, _c_int, Geom, _c_void_p],
     "pvrl_layernorm_bwd": [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                            _c_void_p, _c_int, _c_int, _c_int, Geom, _c_void_p],
-    "pvrl_gather_cast": [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int, Geom, _c_void_p],
+    "pvrl_gather_cast": [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int, Geom, _c_void_p,
+                         _c_void_p],
     "pvrl_cls_merge": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],
     "pvrl_colsum": [_c_void_p, _c_int, _c_i64, _c_void_p, _c_int, _c_int, _c_void_p],
     "pvrl_cast_weight": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
@@ -140,7 +141,7 @@ def _geom(T=1, HW=1):
 # ---------------------------------------------------------------------------------------------- GEMM
 def gemm(A, B, out, *, M, N, K, trans=0, epilogue=EPI_STORE, out2=None, bias=None, rowscale=None, rs_div=0,
          map=MAP_IDENT, aux=None, resid=None, add_pos=None, add_time=None, T=1, HW=1, k_splits=0,
-         lda=None, ldb=None, ldo=None):
+         lda=None, ldb=None, ldo=None, colsum=None):
     """out = epilogue(A @ B^T) -- see pvrl_gemm_t in include/pvrl.h.  A, B bf16; contiguous 2-D tensors."""
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
     d = GemmDesc()
@@ -156,6 +157,7 @@ def gemm(A, B, out, *, M, N, K, trans=0, epilogue=EPI_STORE, out2=None, bias=Non
     d.resid, d.add_pos, d.add_time = _p(resid), _p(add_pos), _p(add_time)
     d.g = _geom(T, HW)
     d.k_splits = k_splits
+    d.colsum = _p(colsum)
     _check(lib().pvrl_gemm_bf16(ctypes.byref(d), _stream()), "pvrl_gemm_bf16")
     return out
 
@@ -184,9 +186,9 @@ def layernorm_bwd(dy, x, w, stats, dx, dw, db, M, D, map=MAP_IDENT, x_cls=None, 
                                     map, _geom(T, HW), _stream()), "pvrl_layernorm_bwd")
 
 
-def gather_cast(src, out, M, D, map=MAP_IDENT, rowscale=None, rs_div=0, T=1, HW=1):
-    _check(lib().pvrl_gather_cast(_p(src), _p(out), _dt(out), _p(rowscale), rs_div, M, D, map, _geom(T, HW), _stream()),
-           "pvrl_gather_cast")
+def gather_cast(src, out, M, D, map=MAP_IDENT, rowscale=None, rs_div=0, T=1, HW=1, colsum=None):
+    _check(lib().pvrl_gather_cast(_p(src), _p(out), _dt(out), _p(rowscale), rs_div, M, D, map, _geom(T, HW), _p(colsum),
+                                  _stream()), "pvrl_gather_cast")
     return out
 
 

@@ -3,9 +3,10 @@ kernels (include/pvrl.h) -- the B200-native replacement for the ~1500 eager kern
 DiffusionTransformer.diffusion_signal_training (reference lib/models/tfm_model.py:165-204) and its autograd.
 
 Per denoising level: one level-input kernel, then per ResidualAttentionBlock (tfm_model.py:32-53) five launches
-(LN+in_proj, attention, out_proj+residual, LN+c_fc, QuickGELU+c_proj+residual); the backward is eleven launches per
-block.  Levels are independent in the backward because each level's noisy input is built from the *detached*
-output of the previous level (tfm_model.py:183-186).  torch supplies memory and the autograd hook-up only."""
+(LN+in_proj, attention, out_proj+residual, LN+c_fc, QuickGELU+c_proj+residual).  Levels are independent in the
+backward because each level's noisy input is built from the *detached* output of the previous level
+(tfm_model.py:183-186) and they share the block weights, so the backward stacks the levels along the row axis and runs
+once: eleven launches per block over L*B*S rows.  torch supplies memory and the autograd hook-up only."""
 import torch
 
 from . import ops
@@ -32,32 +33,35 @@ class OrderLevels(torch.autograd.Function):
         tvecs, type_w, pos_w, pad_w = (t.detach().contiguous() for t in (tvecs, type_w, pos_w, pad_w))
         P = [p.detach() for p in params]
         mask_rows = torch.arange(B, device=dev) * S + mask_inds
-        saved, outs = [], []
+        # activations saved for the backward live in [L*M, ...] buffers, level lvl in rows [lvl*M, (lvl+1)*M): the levels
+        # are independent in the backward (detached inputs) and share the block weights, so the backward runs ONCE over
+        # all L*M rows -- a quarter of the launches, and the weight gradients sum over the levels inside the dW kernels
+        Hd = P[8].shape[0]
+        saved = [dict(xhat1=torch.empty(L * M, C, **f32), rstd1=torch.empty(L * M, **f32),
+                      qkv=torch.empty(L * M, 3 * C, **f32), probs=torch.empty(L * B, H, S, S, **f32),
+                      o=torch.empty(L * M, C, **f32), xhat2=torch.empty(L * M, C, **f32),
+                      rstd2=torch.empty(L * M, **f32), u=torch.empty(L * M, Hd, **f32)) for _ in range(nblk)]
+        outs = []
         src = x0.contiguous()
         for lvl in range(L):
             ca, cb = coef[lvl]
+            r0, r1 = lvl * M, (lvl + 1) * M
             h = torch.empty(M, C, **f32)
             ops.ot_embed_fwd(video, src, noise[lvl].contiguous(), ca, cb, mask_inds, pad_start, type_w, pos_w, pad_w,
                              tvecs[lvl], h, B, S)
-            blocks = []
             for i in range(nblk):
                 (ln1w, ln1b, win, bin_, wout, bout, ln2w, ln2b, wfc, bfc, wproj, bproj) = P[12 * i:12 * i + 12]
-                xhat1, rstd1 = torch.empty(M, C, **f32), torch.empty(M, **f32)
-                qkv = torch.empty(M, 3 * C, **f32)
-                ops.ot_linear_fwd(h, win, bin_, qkv, ops.OT_X_LN, ln1w, ln1b, eps, xhat1, rstd1)
-                probs, o = torch.empty(B, H, S, S, **f32), torch.empty(M, C, **f32)
-                ops.ot_attn_fwd(qkv, pad_start, probs, o, B, S, H)
+                sv = saved[i]
+                qkv, o, u = sv["qkv"][r0:r1], sv["o"][r0:r1], sv["u"][r0:r1]
+                ops.ot_linear_fwd(h, win, bin_, qkv, ops.OT_X_LN, ln1w, ln1b, eps, sv["xhat1"][r0:r1], sv["rstd1"][r0:r1])
+                ops.ot_attn_fwd(qkv, pad_start, sv["probs"][lvl * B:(lvl + 1) * B], o, B, S, H)
                 h_mid = torch.empty(M, C, **f32)
                 ops.ot_linear_fwd(o, wout, bout, h_mid, resid=h)
-                xhat2, rstd2 = torch.empty(M, C, **f32), torch.empty(M, **f32)
-                u = torch.empty(M, wfc.shape[0], **f32)
-                ops.ot_linear_fwd(h_mid, wfc, bfc, u, ops.OT_X_LN, ln2w, ln2b, eps, xhat2, rstd2)
+                ops.ot_linear_fwd(h_mid, wfc, bfc, u, ops.OT_X_LN, ln2w, ln2b, eps, sv["xhat2"][r0:r1], sv["rstd2"][r0:r1])
                 h = torch.empty(M, C, **f32)
                 ops.ot_linear_fwd(u, wproj, bproj, h, ops.OT_X_QGELU, resid=h_mid)
-                blocks.append((xhat1, rstd1, qkv, probs, o, xhat2, rstd2, u))
             den = h.index_select(0, mask_rows)          # tokens at the mask positions (tfm_model.py:194)
             outs.append(den)
-            saved.append(blocks)
             src = den
         ctx.cfg, ctx.saved, ctx.P = cfg, saved, P
         ctx.consts = (mask_inds, pad_start, mask_rows)
@@ -70,47 +74,50 @@ class OrderLevels(torch.autograd.Function):
         B, S, H = cfg["B"], cfg["S"], cfg["heads"]
         mask_inds, pad_start, mask_rows = ctx.consts
         M, C, L, nblk, pshapes = ctx.shapes
+        LM = L * M
         dev = d_inter.device
         f32 = dict(device=dev, dtype=torch.float32)
         d_inter = d_inter.contiguous().float()
         # one zero-filled buffer for everything the kernels accumulate into
-        sizes = [M * C, 2 * C, S * C, C] + [int(torch.Size(s).numel()) for s in pshapes]
+        sizes = [M * C, 2 * C, S * C, C, LM * C] + [int(torch.Size(s).numel()) for s in pshapes]
         flat = torch.zeros(sum(sizes), **f32)
         views, off = [], 0
         for sz in sizes:
             views.append(flat[off:off + sz])
             off += sz
         dvideo, dtype, dpos, dpad = views[0].view(M, C), views[1].view(2, C), views[2].view(S, C), views[3].view(1, C)
-        G = [v.view(s) for v, s in zip(views[4:], pshapes)]
+        dh = views[4].view(LM, C)                        # gradient w.r.t. the block outputs of all levels, rows as saved
+        G = [v.view(s) for v, s in zip(views[5:], pshapes)]
+        rows_all = (mask_rows.unsqueeze(0) + torch.arange(L, device=dev).unsqueeze(1) * M).reshape(-1)
+        dh.index_copy_(0, rows_all, d_inter)
+        for i in reversed(range(nblk)):
+            (ln1w, ln1b, win, bin_, wout, bout, ln2w, ln2b, wfc, bfc, wproj, bproj) = P[12 * i:12 * i + 12]
+            (g_ln1w, g_ln1b, g_win, g_bin, g_wout, g_bout, g_ln2w, g_ln2b, g_wfc, g_bfc, g_wproj, g_bproj) = \
+                G[12 * i:12 * i + 12]
+            sv = saved[i]
+            u = sv["u"]
+            # h_out = h_mid + c_proj(QuickGELU(u)),  u = c_fc(LN2(h_mid))
+            ops.ot_linear_dw(dh, u, g_wproj, g_bproj, ops.OT_X_QGELU)
+            dU = torch.empty_like(u)
+            ops.ot_linear_dx(dh, wproj, dU, pre=u)
+            ops.ot_linear_dw(dU, sv["xhat2"], g_wfc, g_bfc, ops.OT_X_LN, ln2w, ln2b)
+            dA = torch.empty(LM, C, **f32)
+            ops.ot_linear_dx(dU, wfc, dA)
+            ops.ot_ln_bwd(dA, sv["xhat2"], sv["rstd2"], ln2w, dh, g_ln2w, g_ln2b)
+            # h_mid = h_in + out_proj(attn(in_proj(LN1(h_in))))
+            ops.ot_linear_dw(dh, sv["o"], g_wout, g_bout)
+            dO = torch.empty(LM, C, **f32)
+            ops.ot_linear_dx(dh, wout, dO)
+            dqkv = torch.empty(LM, 3 * C, **f32)
+            ops.ot_attn_bwd(sv["qkv"], sv["probs"], dO, dqkv, L * B, S, H)
+            ops.ot_linear_dw(dqkv, sv["xhat1"], g_win, g_bin, ops.OT_X_LN, ln1w, ln1b)
+            dA = torch.empty(LM, C, **f32)
+            ops.ot_linear_dx(dqkv, win, dA)
+            ops.ot_ln_bwd(dA, sv["xhat1"], sv["rstd1"], ln1w, dh, g_ln1w, g_ln1b)
+            saved[i] = None
         dtvecs = torch.empty(L, C, **f32)
         for lvl in range(L):
-            dh = torch.zeros(M, C, **f32)
-            dh.index_copy_(0, mask_rows, d_inter[lvl * B:(lvl + 1) * B])
-            for i in reversed(range(nblk)):
-                (ln1w, ln1b, win, bin_, wout, bout, ln2w, ln2b, wfc, bfc, wproj, bproj) = P[12 * i:12 * i + 12]
-                (g_ln1w, g_ln1b, g_win, g_bin, g_wout, g_bout, g_ln2w, g_ln2b, g_wfc, g_bfc, g_wproj, g_bproj) = \
-                    G[12 * i:12 * i + 12]
-                xhat1, rstd1, qkv, probs, o, xhat2, rstd2, u = saved[lvl][i]
-                # h_out = h_mid + c_proj(QuickGELU(u)),  u = c_fc(LN2(h_mid))
-                ops.ot_linear_dw(dh, u, g_wproj, g_bproj, ops.OT_X_QGELU)
-                dU = torch.empty_like(u)
-                ops.ot_linear_dx(dh, wproj, dU, pre=u)
-                ops.ot_linear_dw(dU, xhat2, g_wfc, g_bfc, ops.OT_X_LN, ln2w, ln2b)
-                dA = torch.empty(M, C, **f32)
-                ops.ot_linear_dx(dU, wfc, dA)
-                ops.ot_ln_bwd(dA, xhat2, rstd2, ln2w, dh, g_ln2w, g_ln2b)
-                # h_mid = h_in + out_proj(attn(in_proj(LN1(h_in))))
-                ops.ot_linear_dw(dh, o, g_wout, g_bout)
-                dO = torch.empty(M, C, **f32)
-                ops.ot_linear_dx(dh, wout, dO)
-                dqkv = torch.empty(M, 3 * C, **f32)
-                ops.ot_attn_bwd(qkv, probs, dO, dqkv, B, S, H)
-                ops.ot_linear_dw(dqkv, xhat1, g_win, g_bin, ops.OT_X_LN, ln1w, ln1b)
-                dA = torch.empty(M, C, **f32)
-                ops.ot_linear_dx(dqkv, win, dA)
-                ops.ot_ln_bwd(dA, xhat1, rstd1, ln1w, dh, g_ln1w, g_ln1b)
-            saved[lvl] = None
-            ops.ot_embed_bwd(dh, mask_inds, pad_start, dvideo, dtype, dpos, dpad, dtvecs[lvl], B, S)
+            ops.ot_embed_bwd(dh[lvl * M:(lvl + 1) * M], mask_inds, pad_start, dvideo, dtype, dpos, dpad, dtvecs[lvl], B, S)
         ctx.saved = None
         return (None, dvideo, dtvecs, dtype, dpos, dpad, None, None, None, None) + tuple(G)
 

@@ -45,7 +45,7 @@ def _rows(map, M, T, HW, dev):
 
 def gemm(A, B, out, *, M, N, K, trans=0, epilogue=EPI_STORE, out2=None, bias=None, rowscale=None, rs_div=0,
          map=MAP_IDENT, aux=None, resid=None, add_pos=None, add_time=None, T=1, HW=1, k_splits=0,
-         lda=None, ldb=None, ldo=None):
+         lda=None, ldb=None, ldo=None, colsum=None):
     _launches[0] += 1
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
     if trans == 0:
@@ -82,6 +82,8 @@ def gemm(A, B, out, *, M, N, K, trans=0, epilogue=EPI_STORE, out2=None, bias=Non
             val = val + add_pos[1 + n] + add_time[bt % T]
         o2[rows[tok]] = val
         return out
+    if colsum is not None:
+        colsum += acc.sum(0)
     o2[rows] = acc.to(out.dtype)
     return out
 
@@ -146,7 +148,7 @@ def layernorm_bwd(dy, x, w, stats, dx, dw, db, M, D, map=MAP_IDENT, x_cls=None, 
         dxf.index_add_(0, rows, dxr)
 
 
-def gather_cast(src, out, M, D, map=MAP_IDENT, rowscale=None, rs_div=0, T=1, HW=1):
+def gather_cast(src, out, M, D, map=MAP_IDENT, rowscale=None, rs_div=0, T=1, HW=1, colsum=None):
     _launches[0] += 1
     rows = _rows(map, M, T, HW, src.device)
     sf = src.reshape(-1, D)
@@ -158,7 +160,10 @@ def gather_cast(src, out, M, D, map=MAP_IDENT, rowscale=None, rs_div=0, T=1, HW=
         cls = rows < 0
         f = torch.where(cls, f / T, f)
         rows = torch.where(cls, ((-rows - 1) // T) * S, rows)
-    out[:M] = (sf[rows] * f.unsqueeze(1)).to(out.dtype)
+    val = sf[rows] * f.unsqueeze(1)
+    out[:M] = val.to(out.dtype)
+    if colsum is not None:
+        colsum += val.sum(0)
     return out
 
 

@@ -49,6 +49,13 @@ def test_gemm_nt_store(ops, M, N, K):
             print("got", out[:2, :8].float().tolist(), "ref", ref[:2, :8].tolist())
         tol = 2e-3 if dt == torch.float32 else 1e-2
         assert rel < tol
+        # fused bias gradient: colsum += column sums of the stored (row-scaled) output
+        rs = torch.rand((M + 6) // 7, device="cuda") + 0.5
+        cs = torch.full((N,), 0.25, device="cuda")
+        ops.gemm(A, B, out, M=M, N=N, K=K, bias=bias, rowscale=rs, rs_div=7, colsum=cs)
+        ref2 = ref * rs[torch.arange(M, device="cuda") // 7].unsqueeze(1)
+        assert _report("gemm colsum", cs, 0.25 + ref2.double().sum(0).float())[1] < 2e-3
+        assert _report("gemm rowscale out", out, ref2)[1] < tol
 
 
 @pytest.mark.parametrize("Mc,M,N", [(64, 128, 256), (512, 256, 256), (1000, 768, 768), (4100, 2304, 768), (999, 768, 3072)])
@@ -219,11 +226,13 @@ def test_gather_cast_clsmerge_colsum_castweight_embedbwd(ops):
     dx = _rand(Bc, S, D, seed=1)
     scale = torch.rand(Bc * T, device="cuda") + 0.5
     out = torch.empty(Bc * T * (HW + 1), D, device="cuda")
-    ops.gather_cast(dx, out, Bc * T * (HW + 1), D, ops.MAP_SPATIAL, rowscale=scale, rs_div=HW + 1, T=T, HW=HW)
+    cs = torch.full((D,), 0.5, device="cuda")
+    ops.gather_cast(dx, out, Bc * T * (HW + 1), D, ops.MAP_SPATIAL, rowscale=scale, rs_div=HW + 1, T=T, HW=HW, colsum=cs)
     tok = dx[:, 1:].reshape(Bc, HW, T, D).permute(0, 2, 1, 3)
     cls = (dx[:, 0] / T).view(Bc, 1, 1, D).expand(Bc, T, 1, D)
     ref = torch.cat((cls, tok), 2).reshape(Bc * T, HW + 1, D) * scale.view(-1, 1, 1)
     assert _report("gather.spatial", out, ref.reshape(-1, D))[0].max() < 1e-6
+    assert _report("gather.colsum", cs, 0.5 + ref.reshape(-1, D).double().sum(0).float())[1] < 1e-5   # fused bias gradient
     outb = torch.empty(Bc * L, D, device="cuda", dtype=torch.bfloat16)
     ops.gather_cast(dx, outb, Bc * L, D, ops.MAP_SKIPCLS, T=T, HW=HW)
     assert torch.equal(outb, dx[:, 1:].reshape(-1, D).bfloat16())
