@@ -10,18 +10,12 @@
 #include <mutex>
 #include <unordered_map>
 
-#include "pvrl_host.h"
-#include "pvrl_ptx.cuh"
+#include "gemm_common.cuh"
 
 namespace pvrl {
 namespace {
 
-constexpr int BM = 128, BK = 64, STAGES = 4;
-constexpr int A_BYTES = BM * BK * 2;          // 16 KB
-constexpr int CHUNK_BYTES = 64 * BK * 2;      // one 64-wide MN chunk of a TN tile (8 KB)
-constexpr int NUM_THREADS = 384;
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int EPI_STAGE_BYTES = 32 * 128;     // per epilogue warp: 32 rows x 32 fp32 columns, 16 B pieces xor-swizzled
+constexpr int STAGES = 4;
 template <int BN>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;                // 32 KB (BN 256) / 24 KB (BN 192)
@@ -30,135 +24,6 @@ struct Cfg {
   static constexpr int SMEM_BYTES = PIPE_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align*/ + 128 /*barriers*/;
 };
 
-struct GemmArgs {
-  int M, N, K;
-  int k_splits, kb_per_split;
-  void* out;
-  long long ldo;
-  void* out2;
-  const float* bias;
-  const float* rowscale;
-  int rs_div;
-  int map;
-  const void* aux;
-  long long ld_aux;
-  const float* resid;
-  const float* add_pos;
-  const float* add_time;
-  float* colsum;
-  Geom g;
-};
-
-// ---- epilogue helpers --------------------------------------------------------------------------------
-// The accumulator leaves TMEM one row per thread (tcgen05.ld 32x32b); a row-per-thread global access would touch 32
-// different 128-byte lines per instruction, so every 32x32 fp32 block is transposed through a 4 KB per-warp staging
-// buffer first: afterwards a lane owns 4 consecutive columns of one row, 8 lanes cover a full 128-byte line and every
-// global load / store / red of the epilogue (output, residual, DGELU pre-activations) is coalesced.
-template <typename T>
-__device__ __forceinline__ void st_vec4(T* dst, const float4& v);
-template <>
-__device__ __forceinline__ void st_vec4<float>(float* dst, const float4& v) {
-  *reinterpret_cast<float4*>(dst) = v;
-}
-template <>
-__device__ __forceinline__ void st_vec4<__nv_bfloat16>(__nv_bfloat16* dst, const float4& v) {
-  uint2 u;
-  u.x = pack_bf16x2(v.x, v.y);
-  u.y = pack_bf16x2(v.z, v.w);
-  *reinterpret_cast<uint2*>(dst) = u;
-}
-template <typename T>
-__device__ __forceinline__ float4 ld_vec4(const T* src);
-template <>
-__device__ __forceinline__ float4 ld_vec4<float>(const float* src) {
-  return __ldg(reinterpret_cast<const float4*>(src));
-}
-template <>
-__device__ __forceinline__ float4 ld_vec4<__nv_bfloat16>(const __nv_bfloat16* src) {
-  const uint2 u = __ldg(reinterpret_cast<const uint2*>(src));
-  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-  return make_float4(a.x, a.y, b.x, b.y);
-}
-__device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w; }
-__device__ __forceinline__ void mul4(float4& a, float s) { a.x *= s, a.y *= s, a.z *= s, a.w *= s; }
-
-// what the transposed epilogue needs to know about one output row (computed once per tile by the lane that owns the
-// row in TMEM order, then handed to the lanes that own it in the transposed order by warp shuffles)
-struct RowCtx {
-  int orow;         // residual-stream / output row (map_row); < 0 = cls row of a spatial sequence
-  float rs;         // DropPath factor of the row (1 when none)
-};
-
-// "side" operand of one 4-column piece: the fp32 residual (RESID) or the saved GELU derivative (DGELU).  It does not
-// depend on the accumulator, so the epilogue fetches it one 32-column chunk ahead (see the kernel) and the HBM latency
-// of these loads overlaps the MMAs / the previous chunk instead of sitting between the TMEM read and the store.
-template <int EPI, typename OutT>
-__device__ __forceinline__ float4 load_side(const GemmArgs& p, int m, const RowCtx& rc, int n) {
-  if (EPI == PVRL_EPI_RESID) {
-    if (p.resid != nullptr && m < p.M && rc.orow >= 0) return ld_vec4<float>(p.resid + (long long)rc.orow * p.ldo + n);
-  } else if (EPI == PVRL_EPI_DGELU) {
-    if (m < p.M) return ld_vec4<OutT>(reinterpret_cast<const OutT*>(p.aux) + (long long)m * p.ld_aux + n);
-  }
-  return make_float4(0.f, 0.f, 0.f, 0.f);
-}
-
-template <int EPI, typename OutT>
-__device__ __forceinline__ void epilogue_vec4(const GemmArgs& p, int m, const RowCtx& rc, int n, float4& v,
-                                              const float4& bias4, const float4& side) {
-  if (EPI == PVRL_EPI_ATOMIC) {
-    float* dst = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + n;
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                 : "memory");
-    return;
-  }
-  add4(v, bias4);
-  if (EPI == PVRL_EPI_GELU) {   // out2 = gelu(z), out = gelu'(z): the backward GEMM then only multiplies (EPI_DGELU)
-    float4 a, d;
-    gelu_both<OutT>(v.x, a.x, d.x), gelu_both<OutT>(v.y, a.y, d.y), gelu_both<OutT>(v.z, a.z, d.z),
-        gelu_both<OutT>(v.w, a.w, d.w);
-    st_vec4<OutT>(reinterpret_cast<OutT*>(p.out) + (long long)m * p.ldo + n, d);
-    st_vec4<OutT>(reinterpret_cast<OutT*>(p.out2) + (long long)m * p.ldo + n, a);
-    return;
-  }
-  if (EPI == PVRL_EPI_DGELU) v.x *= side.x, v.y *= side.y, v.z *= side.z, v.w *= side.w;
-  mul4(v, rc.rs);
-  if (EPI == PVRL_EPI_RESID) {
-    float* out = reinterpret_cast<float*>(p.out);
-    if (rc.orow < 0) {  // cls row of a spatial sequence: park it for the mean over frames (vit.py:147-149)
-      st_vec4<float>(reinterpret_cast<float*>(p.out2) + (long long)(-rc.orow - 1) * p.ldo + n, v);
-      return;
-    }
-    add4(v, side);
-    if (p.add_pos != nullptr) {  // MAP_PATCH (patch embedding only): + pos_embed[1+n] + time_embed[t]  (vit.py:373-404)
-      const int bt = m / p.g.HW;
-      add4(v, ld_vec4<float>(p.add_pos + (long long)(1 + m - bt * p.g.HW) * p.N + n));
-      add4(v, ld_vec4<float>(p.add_time + (long long)(bt % p.g.T) * p.N + n));
-    }
-    st_vec4<float>(out + (long long)rc.orow * p.ldo + n, v);
-    return;
-  }
-  // STORE / DGELU
-  st_vec4<OutT>(reinterpret_cast<OutT*>(p.out) + (long long)rc.orow * p.ldo + n, v);
-}
-
-// tile index -> (m block, n block, k split).  NT: n fastest, so the CTAs of a wave share A tiles through L2 and the
-// (small) weight matrix stays resident.  TN (dW, split-K): the k split is the SLOWEST index, so at any time the
-// resident CTAs cover all output tiles of one or two contraction slices and every slice of dY / X is fetched from
-// HBM once instead of once per output tile.
-template <bool TN>
-__device__ __forceinline__ void decode_tile(int tile, int m_tiles, int n_tiles, int k_splits, int& m_blk, int& n_blk,
-                                            int& ks) {
-  if (TN) {
-    const int per = m_tiles * n_tiles;
-    ks = tile / per;
-    const int rest = tile - ks * per;
-    n_blk = rest % n_tiles, m_blk = rest / n_tiles;
-  } else {
-    ks = tile % k_splits;
-    const int rest = tile / k_splits;
-    n_blk = rest % n_tiles, m_blk = rest / n_tiles;
-  }
-}
 
 template <int EPI, typename OutT, bool TN, int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -282,86 +147,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int half = (warp - 4) >> 2;      // column half of the BN-wide accumulator
     constexpr int HALF_COLS = BN / 2;
     uint8_t* stg = smem + C::PIPE_BYTES + (warp - 4) * EPI_STAGE_BYTES;
-    const int rsub = lane >> 3, piece = lane & 7;   // transposed ownership: row 4*i + rsub, columns [4*piece, +4)
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int m_blk, n_blk, ks;
       decode_tile<TN>(tile, m_tiles, n_tiles, p.k_splits, m_blk, n_blk, ks);
       const int m_base = m_blk * BM + quarter * 32;
-      // per-row context, computed by the lane that owns the row in TMEM order ...
-      RowCtx own;
-      {
-        const int m = min(m_base + lane, p.M - 1);
-        own.orow = (EPI == PVRL_EPI_ATOMIC || EPI == PVRL_EPI_GELU) ? m : static_cast<int>(map_row(p.map, m, p.g));
-        own.rs = (EPI != PVRL_EPI_ATOMIC && EPI != PVRL_EPI_GELU && p.rowscale != nullptr)
-                     ? __ldg(p.rowscale + m / p.rs_div) : 1.0f;
-      }
-      // ... and handed to the transposed owners
-      RowCtx rc[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int src = 4 * i + rsub;
-        rc[i].orow = __shfl_sync(0xffffffffu, own.orow, src);
-        rc[i].rs = (EPI != PVRL_EPI_ATOMIC && EPI != PVRL_EPI_GELU) ? __shfl_sync(0xffffffffu, own.rs, src) : 1.0f;
-      }
-      constexpr int NCH = HALF_COLS / 32;
-      constexpr bool HAS_SIDE = EPI == PVRL_EPI_RESID || EPI == PVRL_EPI_DGELU;
-      constexpr bool HAS_COLSUM = EPI == PVRL_EPI_STORE || EPI == PVRL_EPI_DGELU;
-      const int n_first = n_blk * BN + half * HALF_COLS + piece * 4;   // this lane's columns in chunk 0
-      float4 side[2][8];
-      if (HAS_SIDE && n_first < p.N) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) side[0][i] = load_side<EPI, OutT>(p, m_base + 4 * i + rsub, rc[i], n_first);
-      }
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int col0 = half * HALF_COLS + c * 32;
-        const int n0 = n_blk * BN + col0;
-        if (n0 < p.N) {  // warp-uniform
-          if (HAS_SIDE && c + 1 < NCH && n0 + 32 < p.N) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              side[(c + 1) & 1][i] = load_side<EPI, OutT>(p, m_base + 4 * i + rsub, rc[i], n0 + 32 + piece * 4);
-          }
-          uint32_t raw[32];
-          tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col0, raw);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
-          __syncwarp();
-          const int n = n0 + piece * 4;
-          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (EPI != PVRL_EPI_ATOMIC && p.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-          float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = 4 * i + rsub;
-            float4 v = *reinterpret_cast<const float4*>(stg + row * 128 + ((piece ^ (row & 7)) << 4));
-            const int m = m_base + row;
-            if (m < p.M) {
-              epilogue_vec4<EPI, OutT>(p, m, rc[i], n, v, bias4, HAS_SIDE ? side[c & 1][i] : bias4);
-              if (HAS_COLSUM) add4(csum, v);
-            }
-          }
-          if (HAS_COLSUM && p.colsum != nullptr) {   // fused bias gradient: column sums of what was just stored
-#pragma unroll
-            for (int o = 8; o <= 16; o <<= 1) {
-              csum.x += __shfl_xor_sync(0xffffffffu, csum.x, o), csum.y += __shfl_xor_sync(0xffffffffu, csum.y, o);
-              csum.z += __shfl_xor_sync(0xffffffffu, csum.z, o), csum.w += __shfl_xor_sync(0xffffffffu, csum.w, o);
-            }
-            if (rsub == 0)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.colsum + n), "f"(csum.x), "f"(csum.y),
-                           "f"(csum.z), "f"(csum.w)
-                           : "memory");
-          }
-          __syncwarp();
-        }
-      }
+      epilogue_tile<EPI, OutT, HALF_COLS>(p, stg, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN +
+                                                       half * HALF_COLS,
+                                          m_base, n_blk * BN + half * HALF_COLS, tfull_bar(acc), acc_phase, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -503,6 +297,10 @@ void pick_tiling(int M, int N, int num_kb, bool splitk, int forced_splits, int f
 }  // namespace
 }  // namespace pvrl
 
+namespace pvrl {
+int gemm2_dispatch(const pvrl_gemm_t* d, cudaStream_t stream);   // gemm2_sm100.cu: 256 x 256 tiles on CTA pairs
+}
+
 extern "C" int pvrl_gemm_bf16(const pvrl_gemm_t* d, void* stream_) {
   using namespace pvrl;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -523,14 +321,15 @@ extern "C" int pvrl_gemm_bf16(const pvrl_gemm_t* d, void* stream_) {
     PVRL_CHECK_ARG(d->epilogue == PVRL_EPI_RESID && d->out2 != nullptr,
                    "pvrl_gemm_bf16: MAP_SPATIAL needs the RESID epilogue and a cls side buffer");
 
-  GemmArgs a;
-  a.M = d->M, a.N = d->N, a.K = d->K;
-  a.out = d->out, a.ldo = d->ldo, a.out2 = d->out2;
-  a.bias = d->bias, a.rowscale = d->rowscale, a.rs_div = d->rs_div > 0 ? d->rs_div : 1;
-  a.map = d->map, a.aux = d->aux, a.ld_aux = d->ld_aux, a.resid = d->resid;
-  a.add_pos = d->add_pos, a.add_time = d->add_time;
-  a.colsum = d->colsum;
-  a.g = Geom(d->g.T > 0 ? d->g.T : 1, d->g.HW > 0 ? d->g.HW : 1);
+  // CTA-pair tiles (gemm2_sm100.cu) for the long contractions (dW, K >= 1536), single-CTA 128 x 256 / 128 x 192 tiles
+  // for the K = 768 layers whose time is mostly epilogue and which gain from the finer wave granularity (measured,
+  // profiles/): PVRL_GEMM_2CTA = 0 / 1 pins one of the two.
+  static const int mode_2cta = [] {
+    const char* e = getenv("PVRL_GEMM_2CTA");
+    return e ? atoi(e) : 2;
+  }();
+  if (mode_2cta == 1 || (mode_2cta == 2 && (d->trans == 1 || d->K >= 1536))) return gemm2_dispatch(d, stream);
+  GemmArgs a = make_gemm_args(d);
 
   const int num_kb = (d->K + BK - 1) / BK;
   int splits = 1, bn = 256;

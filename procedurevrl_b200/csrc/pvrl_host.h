@@ -47,6 +47,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn get_encode_fn();   // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda)
 int num_sms();
+// cached 2-D bf16 tensor map over a row-major [outer, inner] matrix (gemm_sm100.cu)
+int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                      uint32_t box_outer);
 
 struct Geom {
   int T, HW, L, S;
