@@ -280,15 +280,24 @@ def run_b200(args):
                          "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "TFLOP/s",
                          "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic,
                          "peak_source": f"bf16_tflops_sustained, {peak_src}",
-                         "launches": n_gemm, "gemm_share_of_step": round(gemm_ms / (eager_ms if graphed else ms), 4),
-                         "timed_in": "one eager step after the graph-replayed timed region" if graphed else "timed region",
+                         "launches": n_gemm, "gemm_share_of_step": round(gemm_ms / ms_step, 4),
+                         "timed_in": ("CUDA events around every GEMM launch of one eager step run after the graph-replayed timed "
+                                      "region (events cannot time nodes inside a graph); share = that GEMM time / ms_per_step")
+                         if graphed else "timed region",
                          "step_mfu": round(step_flops / (ms_step / 1e3) / 1e12 / peak, 4)},
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(T, args.depth, budget_s=25.0)
         print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing NCCL down: the step's CUDA graph holds the communicator's all-reduce, and
+        # ncclCommDestroy behind destroy_process_group() hung the 2-GPU run after the result line was printed.
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle)

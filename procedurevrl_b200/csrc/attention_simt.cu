@@ -254,6 +254,116 @@ attn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ out, const T* _
   }
 }
 
+
+// ---- long sequences (joint space-time attention: 1 + HW*T = 1569 tokens, vit.py:124-127) --------------------------------
+// Flash-style backward on CUDA cores: nothing of size seq x seq is materialised.  K_dq: thread = query (q, dO, dq in
+// registers), keys / values stream through shared memory in blocks of 64.  K_dkv: thread = key (k, then k + v, in
+// registers), queries / dO / lse / delta stream through shared memory; two passes over the queries (dv, then dk) keep
+// the live registers below 200.  fp32 arithmetic, deterministic, no atomics.  This path exists for coverage of
+// TIMESFORMER.ATTENTION_TYPE joint_space_time (no shipped config uses it); it is not tuned.
+constexpr int LONG_BLK = 64;      // streamed rows per shared-memory block
+constexpr int LONG_THREADS = 128;
+
+template <typename T>
+__global__ void __launch_bounds__(LONG_THREADS)
+attn_bwd_dq_long_kernel(const T* __restrict__ qkv, const T* __restrict__ out, const T* __restrict__ dout,
+                        const float* __restrict__ lse, T* __restrict__ dqkv, int seq, int H, float scale) {
+  __shared__ __align__(16) float sK[LONG_BLK * ROW], sV[LONG_BLK * ROW];
+  const long long pair = blockIdx.x;
+  const int s_idx = static_cast<int>(pair / H), h = static_cast<int>(pair % H);
+  const int C = H * HD;
+  const long long pitch = 3LL * C;
+  const int i = blockIdx.y * LONG_THREADS + threadIdx.x;
+  const bool active = i < seq;
+  float q[HD], go[HD], acc[HD];
+  float li = 0.f, di = 0.f;
+#pragma unroll
+  for (int d = 0; d < HD; ++d) q[d] = 0.f, go[d] = 0.f, acc[d] = 0.f;
+  if (active) {
+    load_row64<T>(qkv + ((long long)s_idx * seq + i) * pitch + h * HD, q);
+    load_row64<T>(dout + ((long long)s_idx * seq + i) * C + h * HD, go);
+    load_row64<T>(out + ((long long)s_idx * seq + i) * C + h * HD, acc);   // acc temporarily holds O_i
+#pragma unroll
+    for (int d = 0; d < HD; ++d) di = fmaf(acc[d], go[d], di), acc[d] = 0.f, q[d] *= scale;
+    li = lse[pair * seq + i];
+  }
+  const T* base = qkv + (long long)s_idx * seq * pitch + h * HD;
+  for (int k0 = 0; k0 < seq; k0 += LONG_BLK) {
+    const int nk = min(LONG_BLK, seq - k0);
+    __syncthreads();
+    stage_rows<T>(base + (long long)k0 * pitch + C, pitch, nk, sK);
+    stage_rows<T>(base + (long long)k0 * pitch + 2 * C, pitch, nk, sV);
+    __syncthreads();
+    if (active)
+      for (int j = 0; j < nk; ++j) {
+        const float p = __expf(dot64(q, sK + j * ROW) - li);
+        const float dp = dot64(go, sV + j * ROW);
+        axpy64(acc, p * (dp - di) * scale, sK + j * ROW);
+      }
+  }
+  if (active) store_row64<T>(dqkv + ((long long)s_idx * seq + i) * pitch + h * HD, acc);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(LONG_THREADS)
+attn_bwd_dkv_long_kernel(const T* __restrict__ qkv, const T* __restrict__ out, const T* __restrict__ dout,
+                         const float* __restrict__ lse, T* __restrict__ dqkv, int seq, int H, float scale) {
+  __shared__ __align__(16) float sQ[LONG_BLK * ROW], sdO[LONG_BLK * ROW];
+  __shared__ float sL[LONG_BLK], sD[LONG_BLK];
+  const long long pair = blockIdx.x;
+  const int s_idx = static_cast<int>(pair / H), h = static_cast<int>(pair % H);
+  const int C = H * HD;
+  const long long pitch = 3LL * C;
+  const int j = blockIdx.y * LONG_THREADS + threadIdx.x;
+  const bool active = j < seq;
+  const T* qbase = qkv + (long long)s_idx * seq * pitch + h * HD;
+  const T* obase = out + (long long)s_idx * seq * C + h * HD;
+  const T* gbase = dout + (long long)s_idx * seq * C + h * HD;
+  float k[HD], v[HD], acc[HD];
+#pragma unroll
+  for (int d = 0; d < HD; ++d) k[d] = 0.f, v[d] = 0.f;
+  if (active) {
+    load_row64<T>(qbase + (long long)j * pitch + C, k);
+#pragma unroll
+    for (int d = 0; d < HD; ++d) k[d] *= scale;      // s_ij = q_i . (scale k_j)
+  }
+  for (int pass = 0; pass < 2; ++pass) {             // pass 0: dv_j = sum_i p_ij dO_i ; pass 1: dk_j = scale sum_i ds_ij q_i
+    if (pass == 1 && active) load_row64<T>(qbase + (long long)j * pitch + 2 * C, v);
+#pragma unroll
+    for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+    for (int q0 = 0; q0 < seq; q0 += LONG_BLK) {
+      const int nq = min(LONG_BLK, seq - q0);
+      __syncthreads();
+      stage_rows<T>(qbase + (long long)q0 * pitch, pitch, nq, sQ);
+      stage_rows<T>(gbase + (long long)q0 * C, C, nq, sdO);
+      if (threadIdx.x < nq) {
+        sL[threadIdx.x] = lse[pair * seq + q0 + threadIdx.x];
+        if (pass == 1) {                             // delta_i = dO_i . O_i, recomputed per block (O is read from global)
+          float orow[HD], grow[HD];
+          load_row64<T>(obase + (long long)(q0 + threadIdx.x) * C, orow);
+          load_row64<T>(gbase + (long long)(q0 + threadIdx.x) * C, grow);
+          float dsum = 0.f;
+#pragma unroll
+          for (int d = 0; d < HD; ++d) dsum = fmaf(orow[d], grow[d], dsum);
+          sD[threadIdx.x] = dsum;
+        }
+      }
+      __syncthreads();
+      if (active)
+        for (int i = 0; i < nq; ++i) {
+          const float p = __expf(dot64(k, sQ + i * ROW) - sL[i]);
+          if (pass == 0) {
+            axpy64(acc, p, sdO + i * ROW);
+          } else {
+            const float dp = dot64(v, sdO + i * ROW);
+            axpy64(acc, p * (dp - sD[i]) * scale, sQ + i * ROW);
+          }
+        }
+    }
+    if (active) store_row64<T>(dqkv + ((long long)s_idx * seq + j) * pitch + (pass == 0 ? 2 * C : C) + h * HD, acc);
+  }
+}
+
 }  // namespace
 }  // namespace pvrl
 
@@ -327,11 +437,28 @@ extern "C" int pvrl_attn_fwd(const void* qkv, void* out, float* lse, int32_t dty
                            : attn_fwd_launch<__nv_bfloat16>(qkv, out, lse, n_seq, seq, H, scale, st);
 }
 
+template <typename T>
+static int attn_bwd_long_launch(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                                int n_seq, int seq, int H, float scale, cudaStream_t stream) {
+  dim3 grid(static_cast<unsigned>(n_seq) * H, (seq + LONG_THREADS - 1) / LONG_THREADS);
+  attn_bwd_dq_long_kernel<T><<<grid, LONG_THREADS, 0, stream>>>(static_cast<const T*>(qkv), static_cast<const T*>(out),
+                                                               static_cast<const T*>(dout), lse, static_cast<T*>(dqkv),
+                                                               seq, H, scale);
+  int rc = launched("attn_bwd_dq_long_kernel");
+  if (rc) return rc;
+  attn_bwd_dkv_long_kernel<T><<<grid, LONG_THREADS, 0, stream>>>(static_cast<const T*>(qkv), static_cast<const T*>(out),
+                                                                static_cast<const T*>(dout), lse, static_cast<T*>(dqkv),
+                                                                seq, H, scale);
+  return launched("attn_bwd_dkv_long_kernel");
+}
+
 extern "C" int pvrl_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                              int32_t dtype, int32_t n_seq, int32_t seq, int32_t H, float scale, void* stream) {
   PVRL_CHECK_ARG(qkv && out && dout && lse && dqkv && n_seq > 0 && seq > 0 && H > 0, "pvrl_attn_bwd: bad arguments");
-  PVRL_CHECK_ARG(seq <= 208, "pvrl_attn_bwd: seq=%d > 208 is not supported by the CUDA-core backward", seq);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (seq > 208)
+    return dtype == PVRL_F32 ? attn_bwd_long_launch<float>(qkv, out, dout, lse, dqkv, n_seq, seq, H, scale, st)
+                             : attn_bwd_long_launch<__nv_bfloat16>(qkv, out, dout, lse, dqkv, n_seq, seq, H, scale, st);
   if (seq <= 8 && dtype == PVRL_BF16) return attn_t8_bwd_launch(qkv, out, dout, lse, dqkv, n_seq, seq, H, scale, st);
   if (seq <= 32)
     return dtype == PVRL_F32

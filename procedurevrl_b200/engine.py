@@ -32,7 +32,9 @@ class EncoderEngine:
                  attention_type="divided_space_time", precision="bf16", prefix="model."):
         """params: dict name -> fp32 CUDA tensor/Parameter with the reference state_dict names."""
         assert precision in ("bf16", "bf16x3")
-        assert attention_type == "divided_space_time", "engine implements the divided space-time schedule"
+        assert attention_type in ("divided_space_time", "space_only", "joint_space_time"), attention_type
+        self.attention_type = attention_type
+        self.divided = attention_type == "divided_space_time"
         self.p = params
         self.pre = prefix
         self.depth, self.T0, self.D, self.H = depth, num_frames, embed_dim, num_heads
@@ -55,10 +57,11 @@ class EncoderEngine:
                                     "patch_embed.proj.bias")]
         for i in range(self.depth):
             b = f"{self.pre}blocks.{i}."
-            for ln in ("norm1", "temporal_norm1", "norm2"):
+            for ln in (("norm1", "temporal_norm1", "norm2") if self.divided else ("norm1", "norm2")):
                 n += [b + ln + ".weight", b + ln + ".bias"]
             for l in LINEARS:
-                n += [b + l + ".weight", b + l + ".bias"]
+                if self.divided or not l.startswith("temporal"):
+                    n += [b + l + ".weight", b + l + ".bias"]
         n += [self.pre + "norm.weight", self.pre + "norm.bias"]
         return n
 
@@ -156,6 +159,8 @@ class EncoderEngine:
         of DropPath factors mask/keep (vit_utils.py:140-155); None entries = identity."""
         assert frames.dtype == torch.float32          # ops._p rejects non-CUDA tensors: there is no CPU path
         frames = frames.contiguous()
+        if not self.divided:
+            return self._forward_plain(frames, drop_scales, save)
         Bc, C, T, Hh, Ww = frames.shape
         D, P = self.D, self.patch
         HW = (Hh // P) * (Ww // P)
@@ -257,6 +262,8 @@ class EncoderEngine:
     # ------------------------------------------------------------------------------------------ backward
     def backward(self, st, dfeat):
         """dfeat fp32 [Bc, D] -> dict name -> fp32 gradient (views of one flat zero-initialised buffer)."""
+        if not self.divided:
+            return self._backward_plain(st, dfeat)
         Bc, T, HW = st["Bc"], st["T"], st["HW"]
         D = self.D
         L, S = HW * T, 1 + HW * T
@@ -352,6 +359,158 @@ class EncoderEngine:
         self.linear_dx(dqkv, b + "temporal_attn.qkv.weight", d_ln, Mt, D, 3 * D)
         ops.layernorm_bwd(d_ln, sv["x0"], P[b + "temporal_norm1.weight"], sv["st_t"], dx,
                           G[b + "temporal_norm1.weight"], G[b + "temporal_norm1.bias"], Mt, D, ops.MAP_SKIPCLS, **g)
+
+
+# ---------------------------------------------------------------------------------------------- plain ViT schedules
+def _grad_buffers(eng, dev):
+    P = eng.p
+    if eng.grad_sink is not None:
+        return eng.grad_sink
+    sizes = [P[n].numel() for n in eng.grad_names]
+    flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+    G, off = {}, 0
+    for n, sz in zip(eng.grad_names, sizes):
+        G[n] = flat[off:off + sz].view(P[n].shape)
+        off += sz
+    return G
+
+
+def _forward_plain(self, frames, drop_scales, save):
+    """TIMESFORMER.ATTENTION_TYPE space_only / joint_space_time (vit.py:124-127, :393, :414-416): every block is
+    x += attn(norm1(x)); x += mlp(norm2(x)) over sequences of Sx tokens --
+      space_only        Bx = Bc*T sequences of 1 + HW tokens (one per frame, no time embedding), frames averaged at the end;
+      joint_space_time  Bx = Bc sequences of 1 + HW*T tokens (same embedding as the divided model)."""
+    Bc, C, T, Hh, Ww = frames.shape
+    D, P, Hd = self.D, self.patch, self.hidden
+    HW = (Hh // P) * (Ww // P)
+    so = self.attention_type == "space_only"
+    Bx, Tx = (Bc * T, 1) if so else (Bc, T)               # geometry of the residual stream as the kernels see it
+    Sx = 1 + HW * Tx
+    Mx = Bx * Sx
+    dev = frames.device
+    g = dict(T=Tx, HW=HW)
+    f32 = dict(device=dev, dtype=torch.float32)
+    pos, te, pos_idx, te_idx = self._pos_time(HW, T)
+    if so:
+        te = torch.zeros(1, D, **f32)                     # space_only adds no time embedding (vit.py:393)
+    KP = 3 * P * P
+    A = self._act(Bc * T * HW, KP, dev)
+    ops.patchify(frames, A, P)
+    x = torch.empty(Bx, Sx, D, **f32)
+    self.linear(A, self.pre + "patch_embed.proj.weight", x, Bc * T * HW, D, KP, epilogue=ops.EPI_RESID,
+                bias=self.p[self.pre + "patch_embed.proj.bias"], map=ops.MAP_PATCH, add_pos=pos, add_time=te, ldo=D, **g)
+    ops.cls_init(x, self.p[self.pre + "cls_token"], pos)
+    Pm = self.p
+    blocks = []
+    for i in range(self.depth):
+        dp = (drop_scales[i] if drop_scales is not None else None) or {}
+        b = f"{self.pre}blocks.{i}."
+        x0 = x
+        ln_a, st_a = self._act(Mx, D, dev), torch.empty(Mx, 2, **f32)
+        ops.layernorm_fwd(x0, Pm[b + "norm1.weight"], Pm[b + "norm1.bias"], ln_a, st_a, Mx, D, self.eps, ops.MAP_IDENT)
+        qkv = self._act(Mx, 3 * D, dev)
+        self.linear(ln_a, b + "attn.qkv.weight", qkv, Mx, 3 * D, D, bias=Pm[b + "attn.qkv.bias"])
+        o, lse = self._act(Mx, D, dev), torch.empty(Bx, self.H, Sx, **f32)
+        self.spatial_attn_fwd(qkv, o, lse, Bx, Sx)
+        x1 = torch.empty(Bx, Sx, D, **f32)
+        self.linear(o, b + "attn.proj.weight", x1, Mx, D, D, epilogue=ops.EPI_RESID, bias=Pm[b + "attn.proj.bias"],
+                    rowscale=dp.get("attn"), rs_div=Sx, map=ops.MAP_IDENT, resid=x0, ldo=D)
+        ln_m, st_m = self._act(Mx, D, dev), torch.empty(Mx, 2, **f32)
+        ops.layernorm_fwd(x1, Pm[b + "norm2.weight"], Pm[b + "norm2.bias"], ln_m, st_m, Mx, D, self.eps, ops.MAP_IDENT)
+        dact, hid = self._act(Mx, Hd, dev), self._act(Mx, Hd, dev)
+        self.linear(ln_m, b + "mlp.fc1.weight", dact, Mx, Hd, D, epilogue=ops.EPI_GELU, bias=Pm[b + "mlp.fc1.bias"],
+                    out2=hid)
+        x = torch.empty(Bx, Sx, D, **f32)
+        self.linear(hid, b + "mlp.fc2.weight", x, Mx, D, Hd, epilogue=ops.EPI_RESID, bias=Pm[b + "mlp.fc2.bias"],
+                    rowscale=dp.get("mlp"), rs_div=Sx, map=ops.MAP_IDENT, resid=x1, ldo=D)
+        blocks.append(dict(x0=x0, x1=x1, ln_a=ln_a, st_a=st_a, qkv=qkv, o=o, lse=lse, ln_m=ln_m, st_m=st_m, dact=dact,
+                           hid=hid, dp=dp) if save else None)
+    # final norm on the cls rows; space_only first averages the frames of a clip (vit.py:414-418)
+    feat = torch.empty(Bc, D, **f32)
+    st_f = torch.empty(Bc, 2, **f32)
+    if so:
+        xm = x.view(Bc, T, Sx, D)[:, :, 0].mean(1).contiguous()
+        ops.layernorm_fwd(xm, Pm[self.pre + "norm.weight"], Pm[self.pre + "norm.bias"], feat, st_f, Bc, D, self.eps,
+                          ops.MAP_IDENT)
+    else:
+        xm = x
+        ops.layernorm_fwd(x, Pm[self.pre + "norm.weight"], Pm[self.pre + "norm.bias"], feat, st_f, Bc, D, self.eps,
+                          ops.MAP_CLS, **g)
+    if not save:
+        return feat, None
+    return feat, dict(Bc=Bc, T=T, HW=HW, A=A, xm=xm, st_f=st_f, blocks=blocks, pos_idx=pos_idx, te_idx=te_idx)
+
+
+def _backward_plain(self, st, dfeat):
+    Bc, T, HW = st["Bc"], st["T"], st["HW"]
+    D, Hd = self.D, self.hidden
+    so = self.attention_type == "space_only"
+    Bx, Tx = (Bc * T, 1) if so else (Bc, T)
+    Sx = 1 + HW * Tx
+    Mx = Bx * Sx
+    dev = dfeat.device
+    g = dict(T=Tx, HW=HW)
+    P = self.p
+    G = _grad_buffers(self, dev)
+    dx = torch.zeros(Bx, Sx, D, device=dev, dtype=torch.float32)
+    if so:
+        dxm = torch.zeros(Bc, D, device=dev, dtype=torch.float32)
+        ops.layernorm_bwd(dfeat.contiguous(), st["xm"], P[self.pre + "norm.weight"], st["st_f"], dxm,
+                          G[self.pre + "norm.weight"], G[self.pre + "norm.bias"], Bc, D, ops.MAP_IDENT)
+        dx.view(Bc, T, Sx, D)[:, :, 0] = (dxm / T).unsqueeze(1)          # backward of the mean over frames
+    else:
+        ops.layernorm_bwd(dfeat.contiguous(), st["xm"], P[self.pre + "norm.weight"], st["st_f"], dx,
+                          G[self.pre + "norm.weight"], G[self.pre + "norm.bias"], Bc, D, ops.MAP_CLS, **g)
+    for i in reversed(range(self.depth)):
+        sv = st["blocks"][i]
+        b = f"{self.pre}blocks.{i}."
+        dp = sv["dp"]
+        # ---- MLP
+        dY = self._act(Mx, D, dev)
+        ops.gather_cast(dx, dY, Mx, D, ops.MAP_IDENT, rowscale=dp.get("mlp"), rs_div=Sx, colsum=G[b + "mlp.fc2.bias"])
+        self.linear_dw(dY, sv["hid"], G[b + "mlp.fc2.weight"], None, Mx, D, Hd)
+        d_pre = self._act(Mx, Hd, dev)
+        self.linear_dx(dY, b + "mlp.fc2.weight", d_pre, Mx, Hd, D, epilogue=ops.EPI_DGELU, aux=sv["dact"],
+                       colsum=G[b + "mlp.fc1.bias"])
+        self.linear_dw(d_pre, sv["ln_m"], G[b + "mlp.fc1.weight"], None, Mx, Hd, D)
+        d_ln = self._act(Mx, D, dev)
+        self.linear_dx(d_pre, b + "mlp.fc1.weight", d_ln, Mx, D, Hd)
+        del d_pre
+        ops.layernorm_bwd(d_ln, sv["x1"], P[b + "norm2.weight"], sv["st_m"], dx, G[b + "norm2.weight"],
+                          G[b + "norm2.bias"], Mx, D, ops.MAP_IDENT)
+        # ---- attention
+        dYa = self._act(Mx, D, dev)
+        ops.gather_cast(dx, dYa, Mx, D, ops.MAP_IDENT, rowscale=dp.get("attn"), rs_div=Sx, colsum=G[b + "attn.proj.bias"])
+        self.linear_dw(dYa, sv["o"], G[b + "attn.proj.weight"], None, Mx, D, D)
+        d_o = self._act(Mx, D, dev)
+        self.linear_dx(dYa, b + "attn.proj.weight", d_o, Mx, D, D)
+        dqkv = self._act(Mx, 3 * D, dev)
+        self.spatial_attn_bwd(sv["qkv"], sv["o"], d_o, sv["lse"], dqkv, Bx, Sx)
+        self.linear_dw(dqkv, sv["ln_a"], G[b + "attn.qkv.weight"], G[b + "attn.qkv.bias"], Mx, 3 * D, D)
+        d_ln = self._act(Mx, D, dev)
+        self.linear_dx(dqkv, b + "attn.qkv.weight", d_ln, Mx, D, 3 * D)
+        ops.layernorm_bwd(d_ln, sv["x0"], P[b + "norm1.weight"], sv["st_a"], dx, G[b + "norm1.weight"],
+                          G[b + "norm1.bias"], Mx, D, ops.MAP_IDENT)
+        st["blocks"][i] = None
+    # embeddings
+    KP = 3 * self.patch * self.patch
+    Mp = Bc * T * HW
+    dYp = self._act(Mp, D, dev)
+    ops.gather_cast(dx, dYp, Mp, D, ops.MAP_PATCH, colsum=G[self.pre + "patch_embed.proj.bias"], **g)
+    self.linear_dw(dYp, st["A"], G[self.pre + "patch_embed.proj.weight"].view(D, KP), None, Mp, D, KP)
+    gpos, gte = G[self.pre + "pos_embed"][0], G[self.pre + "time_embed"][0]
+    dpos = gpos if st["pos_idx"] is None else torch.zeros(HW + 1, D, device=dev)
+    dte = None if so else (gte if st["te_idx"] is None else torch.zeros(T, D, device=dev))
+    ops.embed_bwd(dx, G[self.pre + "cls_token"].view(D), dpos, dte, Bx, D, Tx, HW)
+    if st["pos_idx"] is not None:
+        gpos.index_add_(0, st["pos_idx"], dpos)
+    if dte is not None and st["te_idx"] is not None:
+        gte.index_add_(0, st["te_idx"], dte)
+    return G
+
+
+EncoderEngine._forward_plain = _forward_plain
+EncoderEngine._backward_plain = _backward_plain
 
 
 class EncoderFunction(torch.autograd.Function):

@@ -97,9 +97,8 @@ class VisionTransformer(nn.Module):
                  norm_layer=nn.LayerNorm, num_frames=8, attention_type="divided_space_time", label_emb="", mlp=0,
                  text_model="", lp=False, num_seg=0, extra_tr="order", drope=0.0, cfg=None):
         super().__init__()
-        if attention_type != "divided_space_time":
-            raise NotImplementedError(
-                f"TIMESFORMER.ATTENTION_TYPE={attention_type}: only divided_space_time runs on the sm_100a engine so far")
+        if attention_type not in ("divided_space_time", "space_only", "joint_space_time"):
+            raise ValueError(f"TIMESFORMER.ATTENTION_TYPE={attention_type}")
         self.cfg = cfg
         self.num_classes = num_classes
         self.num_features = self.embed_dim = embed_dim
@@ -169,9 +168,10 @@ class VisionTransformer(nn.Module):
         trunc_normal_(self.pos_embed, std=0.02)
         trunc_normal_(self.cls_token, std=0.02)
         # vit.py:273-281 zero-initialises temporal_fc in *every* block (the `i > 0` guard sees the ModuleList first)
-        for blk in self.blocks:
-            nn.init.constant_(blk.temporal_fc.weight, 0)
-            nn.init.constant_(blk.temporal_fc.bias, 0)
+        if attention_type == "divided_space_time":
+            for blk in self.blocks:
+                nn.init.constant_(blk.temporal_fc.weight, 0)
+                nn.init.constant_(blk.temporal_fc.bias, 0)
 
         self._engine = None
         self._label_dev = None
@@ -224,6 +224,11 @@ class VisionTransformer(nn.Module):
                 out.append(None)
                 continue
             keep = 1.0 - r
+            if self.attention_type != "divided_space_time":      # plain blocks: one row per sequence of the view (vit.py:125-126)
+                n = Bc * T if self.attention_type == "space_only" else Bc
+                s = torch.floor(keep + torch.rand(2 * n, device=dev)) / keep
+                out.append({"attn": s[:n].contiguous(), "mlp": s[n:].contiguous()})
+                continue
             u = torch.rand(Bc * HW + Bc * T + Bc, device=dev)
             s = torch.floor(keep + u) / keep
             out.append({"temporal": s[:Bc * HW].contiguous(), "spatial": s[Bc * HW:Bc * HW + Bc * T].contiguous(),

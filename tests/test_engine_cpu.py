@@ -158,3 +158,36 @@ def test_forecast(shadow, gold_dir):
     with torch.no_grad():
         probs = m(x)
     torch.testing.assert_close(probs, g["probs"], rtol=5e-3, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["coin_d2_spaceonly.pt", "coin_d2_joint.pt"])
+def test_attention_type_variants(shadow, gold_dir, name):
+    """TIMESFORMER.ATTENTION_TYPE space_only / joint_space_time (vit.py:124-127, :414-416) through the
+    plain-ViT schedule of the engine: logits vs the reference golden, gradients vs the oracle's autograd."""
+    g = torch.load(os.path.join(gold_dir, name))
+    c = g["cfg"]
+    cfg = coin_cfg(gold_dir, c["depth"], c["T"], "bf16x3")
+    cfg.merge_from_list(["TIMESFORMER.ATTENTION_TYPE", c["attention_type"]])
+    m = MODEL_REGISTRY.get("vit_base_patch16_224_develop")(cfg)
+    st = O.seeded_state(depth=c["depth"], frames=c["T"], seed=c["state_seed"])
+    own = m.state_dict()
+    assert not any("temporal" in k for k in own)                   # the reference builds no temporal modules here
+    m.load_state_dict({k: v for k, v in st.items() if k in own}, strict=True)
+    for p in m.parameters():
+        p.requires_grad_(True)
+    x = O.synthetic_clips(c["B"], 3, c["T"], 224, 224, seed=c["clip_seed"])
+    m.train()
+    logits = m(x)
+    torch.testing.assert_close(logits, g["logits"], rtol=1e-3, atol=2e-3)
+    labels = torch.tensor([5, 300])[:c["B"]]
+    torch.nn.functional.cross_entropy(logits, labels).backward()
+    p = {k: v.clone().requires_grad_(True) for k, v in st.items()}
+    e = torch.load(os.path.join(gold_dir, "clip_step_emb_coin.pt"))
+    ref = O.match_lang_forward(p, x, e / e.norm(dim=1, keepdim=True), depth=c["depth"], attention_type=c["attention_type"])
+    torch.nn.functional.cross_entropy(ref, labels).backward()
+    for k, prm in m.named_parameters():
+        if prm.grad is None or p[k].grad is None:
+            continue
+        rn = p[k].grad.norm().item()
+        assert abs(prm.grad.norm().item() - rn) <= 5e-3 * rn + 1e-7, k
+        torch.testing.assert_close(prm.grad, p[k].grad, rtol=5e-3, atol=5e-3 * rn / prm.numel() ** 0.5 + 1e-7, msg=k)
