@@ -120,6 +120,18 @@ int pvrl_colsum(const void* a, int32_t a_dtype, int64_t lda, float* out, int32_t
 int pvrl_cast_weight(const float* w, void* w_out, void* wT_out, int32_t out_dtype, int32_t rows, int32_t cols,
                      void* stream);
 
+/* The same for many matrices in one launch.  descs_dev: DEVICE array of n descriptors sorted by tile0, where matrix i
+ * owns the 32x32 tiles [tile0, tile0 + tiles_x * ceil(rows/32)), tiles_x = ceil(cols/32); out / outT may be NULL. */
+typedef struct pvrl_cast_desc {
+  const float* w;
+  void* out;
+  void* outT;
+  int32_t rows, cols;
+  int32_t tile0, tiles_x;
+} pvrl_cast_desc_t;
+int pvrl_cast_weight_multi(const pvrl_cast_desc_t* descs_dev, int32_t n, int32_t total_tiles, int32_t out_dtype,
+                           void* stream);
+
 /* Error-compensated operand split for the "bf16x3" parity mode: a = hi + lo with hi = bf16(a), lo = bf16(a - hi).
  * pattern 0: out = [hi | hi | lo], pattern 1: out = [hi | lo | hi]; along = 1 concatenates along columns
  * ([M, 3*K]), along = 0 along rows ([3*M, K]).  A GEMM over the 3x longer contraction then yields

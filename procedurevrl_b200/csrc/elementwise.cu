@@ -212,27 +212,37 @@ int layernorm_bwd_launch(const void* dy, const float* x, const float* x_cls, con
 // access is one contiguous D*4-byte burst, and because a thread keeps its columns the bias gradient colsum(out) comes
 // for free (registers -> one fp32 atomic per column and block) -- the separate pvrl_colsum pass over dY disappears.
 template <typename OutT>
-__global__ void gather_cast_kernel(const float* __restrict__ src, OutT* __restrict__ out,
-                                   const float* __restrict__ rowscale, int rs_div, int M, int D, int map, Geom g,
-                                   float* __restrict__ colsum) {
+__global__ void __launch_bounds__(256)
+gather_cast_kernel(const float* __restrict__ src, OutT* __restrict__ out, const float* __restrict__ rowscale, int rs_div,
+                   int M, int D, int map, Geom g, float* __restrict__ colsum) {
+  constexpr int R = 8;                      // rows in flight per thread
   const int c = threadIdx.x * 4;
+  const int lane = threadIdx.x & 31;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int m0 = blockIdx.x * 4; m0 < M; m0 += gridDim.x * 4) {
-    float4 v[4];
-    float f[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int m = min(m0 + u, M - 1);
-      long long r = map_row(map, m, g);
-      f[u] = rowscale != nullptr ? __ldg(rowscale + m / rs_div) : 1.0f;
-      if (r < 0) {  // cls row of a spatial sequence: d(mean over T) = 1/T
-        r = ((-r - 1) / g.T) * (long long)g.S;
-        f[u] *= 1.0f / g.T;
+  for (int m0 = blockIdx.x * R; m0 < M; m0 += gridDim.x * R) {
+    // the row map (integer divisions) and the DropPath factor are the same for every thread of the block: lanes 0..R-1
+    // of each warp evaluate them once, the others pick them up by shuffle
+    long long r_l = 0;
+    float f_l = 0.f;
+    if (lane < R) {
+      const int m = min(m0 + lane, M - 1);
+      r_l = map_row(map, m, g);
+      f_l = rowscale != nullptr ? __ldg(rowscale + m / rs_div) : 1.0f;
+      if (r_l < 0) {  // cls row of a spatial sequence: d(mean over T) = 1/T
+        r_l = ((-r_l - 1) / g.T) * (long long)g.S;
+        f_l *= 1.0f / g.T;
       }
+    }
+    float4 v[R];
+    float f[R];
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const long long r = __shfl_sync(0xffffffffu, r_l, u);
+      f[u] = __shfl_sync(0xffffffffu, f_l, u);
       v[u] = __ldg(reinterpret_cast<const float4*>(src + r * D + c));
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < R; ++u)
       if (m0 + u < M) {
         const float4 o = make_float4(v[u].x * f[u], v[u].y * f[u], v[u].z * f[u], v[u].w * f[u]);
         store4<OutT>(out + (long long)(m0 + u) * D + c, o.x, o.y, o.z, o.w);
@@ -301,6 +311,44 @@ __global__ void cast_weight_kernel(const float* __restrict__ w, OutT* __restrict
     const int r = blockIdx.y * 32 + threadIdx.x;  // original row -> fast index of the transposed output
     for (int j = threadIdx.y; j < 32; j += 8) {
       const int cc = blockIdx.x * 32 + j;
+      if (r < rows && cc < cols) oT[(long long)cc * rows + r] = static_cast<OutT>(tile[threadIdx.x][j]);
+    }
+  }
+}
+
+// All weights of the model in ONE launch (85 cast_weight launches per optimizer step otherwise): the descriptor table
+// lives in device memory, a block finds its matrix by binary search over the tile offsets.
+template <typename OutT>
+__global__ void cast_weight_multi_kernel(const pvrl_cast_desc_t* __restrict__ descs, int n) {
+  __shared__ float tile[32][33];
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {   // last descriptor with tile0 <= blockIdx.x
+    const int mid = (lo + hi + 1) >> 1;
+    if (descs[mid].tile0 <= static_cast<int>(blockIdx.x)) lo = mid;
+    else hi = mid - 1;
+  }
+  const pvrl_cast_desc_t d = descs[lo];
+  const int t = blockIdx.x - d.tile0;
+  const int bx = t % d.tiles_x, by = t / d.tiles_x;
+  const float* w = d.w;
+  OutT* o = static_cast<OutT*>(d.out);
+  OutT* oT = static_cast<OutT*>(d.outT);
+  const int rows = d.rows, cols = d.cols;
+  const int c = bx * 32 + threadIdx.x;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int r = by * 32 + j;
+    float v = 0.f;
+    if (r < rows && c < cols) {
+      v = w[(long long)r * cols + c];
+      if (o != nullptr) o[(long long)r * cols + c] = static_cast<OutT>(v);
+    }
+    tile[j][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (oT != nullptr) {
+    const int r = by * 32 + threadIdx.x;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+      const int cc = bx * 32 + j;
       if (r < rows && cc < cols) oT[(long long)cc * rows + r] = static_cast<OutT>(tile[threadIdx.x][j]);
     }
   }
@@ -416,9 +464,10 @@ extern "C" int pvrl_gather_cast(const float* src, void* out, int32_t out_dtype, 
   PVRL_CHECK_ARG(src && out && M > 0 && D % 4 == 0 && D <= 4096, "pvrl_gather_cast: bad arguments");
   PVRL_CHECK_ARG(rowscale == nullptr || rs_div > 0, "pvrl_gather_cast: rowscale needs rs_div > 0");
   const Geom gg(g.T > 0 ? g.T : 1, g.HW > 0 ? g.HW : 1);
-  const int block = D / 4;
-  int grid = (M + 3) / 4;
-  if (grid > 148 * 8) grid = 148 * 8;
+  PVRL_CHECK_ARG(D % 128 == 0 && D <= 1024, "pvrl_gather_cast: D=%d must be a multiple of 128, <= 1024", D);
+  const int block = D / 4;                  // whole warps: the row map is shared through warp shuffles
+  int grid = (M + 7) / 8;
+  if (grid > 148 * 5) grid = 148 * 5;
   if (out_dtype == PVRL_F32)
     gather_cast_kernel<float><<<grid, block, 0, STREAM>>>(src, static_cast<float*>(out), rowscale,
                                                           rs_div > 0 ? rs_div : 1, M, D, map, gg, colsum);
@@ -459,6 +508,17 @@ extern "C" int pvrl_cast_weight(const float* w, void* w_out, void* wT_out, int32
     cast_weight_kernel<__nv_bfloat16><<<grid, block, 0, STREAM>>>(w, static_cast<__nv_bfloat16*>(w_out),
                                                                    static_cast<__nv_bfloat16*>(wT_out), rows, cols);
   return launched("cast_weight_kernel");
+}
+
+extern "C" int pvrl_cast_weight_multi(const pvrl_cast_desc_t* descs_dev, int32_t n, int32_t total_tiles,
+                                      int32_t out_dtype, void* stream) {
+  PVRL_CHECK_ARG(descs_dev && n > 0 && total_tiles > 0, "pvrl_cast_weight_multi: bad arguments");
+  dim3 block(32, 8);
+  if (out_dtype == PVRL_F32)
+    cast_weight_multi_kernel<float><<<total_tiles, block, 0, STREAM>>>(descs_dev, n);
+  else
+    cast_weight_multi_kernel<__nv_bfloat16><<<total_tiles, block, 0, STREAM>>>(descs_dev, n);
+  return launched("cast_weight_multi_kernel");
 }
 
 extern "C" int pvrl_split3(const float* a, void* out, int32_t M, int32_t K, int32_t pattern, int32_t along,

@@ -184,9 +184,27 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stg, u
   constexpr int NCH = HALF_COLS / 32;
   constexpr bool HAS_SIDE = EPI == PVRL_EPI_RESID || EPI == PVRL_EPI_DGELU;
   constexpr bool HAS_COLSUM = EPI == PVRL_EPI_STORE || EPI == PVRL_EPI_DGELU;
+  // bf16 gelu' (DGELU): the side operand of the WHOLE tile is fetched packed (2 registers per piece) before the
+  // accumulator is waited for -- one chunk of lookahead (~0.4 us of work) does not cover an HBM round trip.
+  // fp32 residuals (RESID) / fp32 gelu' keep the two-deep chunk pipeline (a whole tile would need 128 registers).
+  constexpr bool SIDE_PACKED = EPI == PVRL_EPI_DGELU && sizeof(OutT) == 2;
   const int n_first = n_base + piece * 4;   // this lane's columns in chunk 0
-  float4 side[2][8];
-  if (HAS_SIDE && n_first < p.N) {
+  float4 side[SIDE_PACKED ? 1 : 2][8];
+  uint2 sidep[SIDE_PACKED ? NCH : 1][8];
+  if (SIDE_PACKED) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int n = n_first + c * 32;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m_base + 4 * i + rsub;
+        sidep[c][i] = (m < p.M && n < p.N)
+                          ? __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) +
+                                                                 (long long)m * p.ld_aux + n))
+                          : make_uint2(0u, 0u);
+      }
+    }
+  } else if (HAS_SIDE && n_first < p.N) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) side[0][i] = load_side<EPI, OutT>(p, m_base + 4 * i + rsub, rc[i], n_first);
   }
@@ -196,7 +214,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stg, u
   for (int c = 0; c < NCH; ++c) {
     const int n0 = n_base + c * 32;
     if (n0 < p.N) {  // warp-uniform
-      if (HAS_SIDE && c + 1 < NCH && n0 + 32 < p.N) {
+      if (HAS_SIDE && !SIDE_PACKED && c + 1 < NCH && n0 + 32 < p.N) {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           side[(c + 1) & 1][i] = load_side<EPI, OutT>(p, m_base + 4 * i + rsub, rc[i], n0 + 32 + piece * 4);
@@ -219,7 +237,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stg, u
         float4 v = *reinterpret_cast<const float4*>(stg + row * 128 + ((piece ^ (row & 7)) << 4));
         const int m = m_base + row;
         if (m < p.M) {
-          epilogue_vec4<EPI, OutT>(p, m, rc[i], n, v, bias4, HAS_SIDE ? side[c & 1][i] : bias4);
+          float4 sd = bias4;
+          if (SIDE_PACKED) {
+            const float2 lo = unpack_bf16x2(sidep[c][i].x), hi = unpack_bf16x2(sidep[c][i].y);
+            sd = make_float4(lo.x, lo.y, hi.x, hi.y);
+          } else if (HAS_SIDE) {
+            sd = side[c & 1][i];
+          }
+          epilogue_vec4<EPI, OutT>(p, m, rc[i], n, v, bias4, sd);
           if (HAS_COLSUM) add4(csum, v);
         }
       }

@@ -91,6 +91,36 @@ class EncoderEngine:
         self._wcache[name] = (ver, wb, wt)
         return wb, wt
 
+    def refresh_weights(self):
+        """Re-cast every Linear weight whose master changed, in ONE launch (bf16 mode; called at the top of forward)."""
+        if self.x3:
+            return
+        names = [self.pre + "patch_embed.proj.weight"]
+        for i in range(self.depth):
+            b = f"{self.pre}blocks.{i}."
+            names += [b + l + ".weight" for l in LINEARS if self.divided or not l.startswith("temporal")]
+        key = tuple((self.p[n]._version, self.p[n].data_ptr()) for n in names) + (self._wepoch,)
+        if getattr(self, "_wkey", None) == key:
+            return
+        triples = []
+        for n in names:
+            w = self.p[n]
+            w2 = w.detach().reshape(w.shape[0], -1)
+            hit = self._wcache.get(n)
+            if hit is not None and hit[1].device == w2.device:
+                wb, wt = hit[1], hit[2]
+            else:
+                N, K = w2.shape
+                wb = torch.empty(N, K, device=w2.device, dtype=torch.bfloat16)
+                wt = torch.empty(K, N, device=w2.device, dtype=torch.bfloat16)
+            self._wcache[n] = ((w._version, w.data_ptr(), self._wepoch), wb, wt)
+            triples.append((w2, wb, wt))
+        sig = tuple((t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr()) for t in triples)
+        if getattr(self, "_wtable_sig", None) != sig:          # operand addresses are stable -> the table is built once
+            self._wtable, self._wtable_sig = ops.cast_weight_table(triples), sig
+        ops.cast_weight_multi(self._wtable)
+        self._wkey = key
+
     def invalidate_weights(self):
         """Force the bf16 operand copies to be re-cast on next use (call once per optimizer step when the step is
         captured in a CUDA graph: the cast kernels must be part of every replay)."""
@@ -159,6 +189,7 @@ class EncoderEngine:
         of DropPath factors mask/keep (vit_utils.py:140-155); None entries = identity."""
         assert frames.dtype == torch.float32          # ops._p rejects non-CUDA tensors: there is no CPU path
         frames = frames.contiguous()
+        self.refresh_weights()
         if not self.divided:
             return self._forward_plain(frames, drop_scales, save)
         Bc, C, T, Hh, Ww = frames.shape

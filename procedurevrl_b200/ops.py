@@ -47,6 +47,7 @@ _SIGS = {
     "pvrl_cls_merge": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],
     "pvrl_colsum": [_c_void_p, _c_int, _c_i64, _c_void_p, _c_int, _c_int, _c_void_p],
     "pvrl_cast_weight": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
+    "pvrl_cast_weight_multi": [_c_void_p, _c_int, _c_int, _c_int, _c_void_p],
     "pvrl_split3": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],
     "pvrl_embed_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, Geom, _c_void_p],
     "pvrl_attn_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p],
@@ -204,6 +205,29 @@ def cast_weight(w, w_out, wT_out):
     rows, cols = w.shape
     ref = w_out if w_out is not None else wT_out
     _check(lib().pvrl_cast_weight(_p(w), _p(w_out), _p(wT_out), _dt(ref), rows, cols, _stream()), "pvrl_cast_weight")
+
+
+class CastDesc(ctypes.Structure):
+    _fields_ = [("w", _c_void_p), ("out", _c_void_p), ("outT", _c_void_p), ("rows", _c_int), ("cols", _c_int),
+                ("tile0", _c_int), ("tiles_x", _c_int)]
+
+
+def cast_weight_table(triples):
+    """Device descriptor table for cast_weight_multi: triples of (w fp32 [rows, cols], out, outT) -> (table, n, tiles, dtype)."""
+    arr = (CastDesc * len(triples))()
+    t0 = 0
+    for i, (w, o, oT) in enumerate(triples):
+        rows, cols = w.shape
+        tx = (cols + 31) // 32
+        arr[i] = CastDesc(_p(w), _p(o), _p(oT), rows, cols, t0, tx)
+        t0 += tx * ((rows + 31) // 32)
+    raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(triples[0][0].device)
+    return raw, len(triples), t0, _dt(triples[0][1] if triples[0][1] is not None else triples[0][2])
+
+
+def cast_weight_multi(table):
+    raw, n, tiles, dt = table
+    _check(lib().pvrl_cast_weight_multi(_p(raw), n, tiles, dt, _stream()), "pvrl_cast_weight_multi")
 
 
 def split3(a, out, M, K, pattern, along):

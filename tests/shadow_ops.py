@@ -177,6 +177,15 @@ def colsum(a, out, M, N):
     out += a[:M, :N].float().sum(0)
 
 
+def cast_weight_table(triples):
+    return triples
+
+
+def cast_weight_multi(table):
+    for w, o, oT in table:
+        cast_weight(w, o, oT)
+
+
 def cast_weight(w, w_out, wT_out):
     _launches[0] += 1
     if w_out is not None:

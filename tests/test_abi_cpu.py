@@ -48,7 +48,8 @@ def test_bad_arguments_return_errors_not_crashes(lib):
     assert lib.pvrl_gemm_bf16(ctypes.byref(d), None) == -1
     assert lib.pvrl_layernorm_fwd(16, None, 16, 16, 16, 0, None, 8, 100, 1e-6, 0, ops.Geom(1, 1), None) == -1
     assert lib.pvrl_attn_tc_fwd(16, 16, None, 1, 300, 12, 0.125, None) == -1          # seq > 256
-    assert lib.pvrl_attn_bwd(16, 16, 16, 16, 16, 0, 1, 500, 12, 0.125, None) == -1    # seq > 208
+    assert lib.pvrl_attn_bwd(16, 16, 16, 16, 16, 0, 0, 500, 12, 0.125, None) == -1    # no sequences
+    assert lib.pvrl_attn_tc_bwd(16, 16, 16, 16, 16, 1, 500, 12, 0.125, None) == -1     # seq > 256 on the tcgen05 kernel
     assert lib.pvrl_kl_topk_loss(16, 16, None, None, None, 2, 100, 9, 1.0, None) == -1  # topk > 8
 
 
