@@ -37,18 +37,6 @@ __device__ __forceinline__ void store_row64_bf16(__nv_bfloat16* dst, const float
   }
 }
 
-__device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const float* v) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint4 u;
-    u.x = pack_bf16x2(v[8 * i], v[8 * i + 1]);
-    u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-    u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-    u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-    reinterpret_cast<uint4*>(dst)[i] = u;
-  }
-}
-
 // =====================================================================================================
 // forward: one CTA per (sequence, head, 128-query tile).  160 threads: warps 0-3 softmax / epilogue (one
 // query row per thread), warp 4 = TMA + MMA issuer.  smem: [Q | K] (overlaid by P once S is done) + V.
@@ -202,6 +190,23 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 4) tmem_dealloc<256>(tmem);
 }
 
+// Coalesced store of a [128 rows][64 bf16] result tile: each thread drops its 32 fp32 values (row r, dims [32*half, +32))
+// into a swizzled staging tile, then the 8 warps write whole 128-byte rows (8 lanes per row).  `rows_valid` rows exist.
+__device__ __forceinline__ void store_tile_coalesced(uint8_t* stage, const float (&v)[32], int r, int half, int warp,
+                                                     int lane, __nv_bfloat16* gbase, long long gpitch, int rows_valid) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) st_piece(stage, r, half * 4 + q, v + 8 * q);
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = warp * 16 + i * 4 + (lane >> 3), piece = lane & 7;
+    if (row < rows_valid)
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(gbase + row * gpitch) + piece * 16) =
+          *reinterpret_cast<const uint4*>(stage + swz(row, piece));
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");   // staging tile reusable
+}
+
 // =====================================================================================================
 // backward: one CTA per (sequence, head); Q, K, V, dO resident (two 128-row tiles each), loop over 128-key tiles
 // kt and 128-query tiles mt:   S = Q K^T, dP = dO V^T  ->  P = exp(S*scale - lse), dS = P*(dP - delta)*scale  ->
@@ -214,8 +219,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 constexpr int BWD_THREADS = 288;
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                   const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
-                   const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, int seq, int H, float scale) {
+                   const __grid_constant__ CUtensorMap tmO, const float* __restrict__ lse,
+                   __nv_bfloat16* __restrict__ dqkv, int seq, int H, float scale) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -239,6 +244,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     if (lane == 0) {
       tma_prefetch_desc(&tmQKV);
       tma_prefetch_desc(&tmDO);
+      tma_prefetch_desc(&tmO);
       mbar_init(bar_load0, 1);
       mbar_init(bar_load1, 1);
       mbar_init(bar_sdp, 1);
@@ -258,13 +264,17 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   if (warp == 8) {
     if (lane == 0) {
       // tile 0 of every operand first (all the first iteration needs), tile 1 behind it
-      mbar_expect_tx(bar_load0, 4 * TILE_BYTES);
+      // O rides along into the P region, which is idle until the first P tile is written: delta = dO . O is then
+      // read from shared memory instead of 32 uncoalesced 16-byte global loads per thread
+      mbar_expect_tx(bar_load0, 5 * TILE_BYTES);
+      tma_load_3d(sP, &tmO, bar_load0, h * 64, 0, s_idx);
       tma_load_3d(sQ, &tmQKV, bar_load0, h * 64, 0, s_idx);
       tma_load_3d(sK, &tmQKV, bar_load0, C + h * 64, 0, s_idx);
       tma_load_3d(sV, &tmQKV, bar_load0, 2 * C + h * 64, 0, s_idx);
       tma_load_3d(sdO, &tmDO, bar_load0, h * 64, 0, s_idx);
       if (n_tiles > 1) {
-        mbar_expect_tx(bar_load1, 4 * TILE_BYTES);
+        mbar_expect_tx(bar_load1, 5 * TILE_BYTES);
+        tma_load_3d(sP + TILE_BYTES, &tmO, bar_load1, h * 64, 128, s_idx);
         tma_load_3d(sQ + TILE_BYTES, &tmQKV, bar_load1, h * 64, 128, s_idx);
         tma_load_3d(sK + TILE_BYTES, &tmQKV, bar_load1, C + h * 64, 128, s_idx);
         tma_load_3d(sV + TILE_BYTES, &tmQKV, bar_load1, 2 * C + h * 64, 128, s_idx);
@@ -321,30 +331,30 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     const int r = quarter * 32 + lane;
     const uint32_t trow = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
     const long long pitch = 3LL * C;
-    // per-row constants for both query tiles: lse and delta = dO . O
+    // per-row constants for both query tiles: lse and delta = dO . O (both operands from shared memory)
     float lse_l2[2], delta[2];
-    bool qvalid[2];
+    const uint8_t* pdO = smem + 6 * TILE_BYTES;
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
       const int qi = mt * 128 + r;
-      qvalid[mt] = mt < n_tiles && qi < seq;
       lse_l2[mt] = 0.f, delta[mt] = 0.f;
-      if (qvalid[mt]) {
-        const uint4* po = reinterpret_cast<const uint4*>(out + ((long long)s_idx * seq + qi) * C + h * 64);
-        const uint4* pd = reinterpret_cast<const uint4*>(dout + ((long long)s_idx * seq + qi) * C + h * 64);
+      if (mt < n_tiles) {
+        mbar_wait(mt == 0 ? bar_load0 : bar_load1, 0);
         float acc = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const uint4 a = __ldg(po + i), b = __ldg(pd + i);
+          const uint4 a = *reinterpret_cast<const uint4*>(pP + mt * TILE_BYTES + swz(r, i));
+          const uint4 b = *reinterpret_cast<const uint4*>(pdO + mt * TILE_BYTES + swz(r, i));
           const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
           const float2 b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y), b2 = unpack_bf16x2(b.z), b3 = unpack_bf16x2(b.w);
           acc += a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y + a3.x * b3.x +
                  a3.y * b3.y;
         }
-        delta[mt] = acc;
-        lse_l2[mt] = lse[(long long)pair * seq + qi] * LOG2E;
+        delta[mt] = acc;                       // rows past seq are zero-filled -> delta = 0
+        if (qi < seq) lse_l2[mt] = lse[(long long)pair * seq + qi] * LOG2E;
       }
     }
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // every O row has been read before any P tile overwrites it
     const float sl2 = scale * LOG2E;
     for (int it = 0; it < n_iter; ++it) {
       const int kt = it / n_tiles, mt = it % n_tiles;
@@ -380,34 +390,35 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       tc_fence_before();
       mbar_arrive(bar_pds);
       if (mt == n_tiles - 1) {   // key tile finished: dK_kt / dV_kt, this thread = key kt*128 + r, 32 of the 64 dims
-        mbar_wait(bar_mma2, it & 1);
+        mbar_wait(bar_mma2, it & 1);   // all MMAs of this iteration are done: the P / dS tiles are free as staging
         tc_fence_after();
-        const int kj = kt * 128 + r;
+        const int rows_valid = min(128, seq - kt * 128);
+        __nv_bfloat16* gk = dqkv + ((long long)s_idx * seq + kt * 128) * pitch + C + h * 64;
         uint32_t raw[32];
         float v[32];
         tmem_ld32(trow + COL_DK + half * 32, raw);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        if (kj < seq) store_row32_bf16(dqkv + ((long long)s_idx * seq + kj) * pitch + C + h * 64 + half * 32, v);
+        store_tile_coalesced(pP, v, r, half, warp, lane, gk, pitch, rows_valid);
         tmem_ld32(trow + COL_DV + half * 32, raw);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        if (kj < seq) store_row32_bf16(dqkv + ((long long)s_idx * seq + kj) * pitch + 2 * C + h * 64 + half * 32, v);
+        store_tile_coalesced(pP, v, r, half, warp, lane, gk + C, pitch, rows_valid);
         tc_fence_before();
       }
     }
     // dQ tiles (the last bar_mma2 wait above covers every MMA)
     for (int mt = 0; mt < n_tiles; ++mt) {
-      const int qi = mt * 128 + r;
       uint32_t raw[32];
       float v[32];
       tmem_ld32(trow + COL_DQ + mt * 64 + half * 32, raw);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-      if (qi < seq) store_row32_bf16(dqkv + ((long long)s_idx * seq + qi) * pitch + h * 64 + half * 32, v);
+      store_tile_coalesced(pP, v, r, half, warp, lane, dqkv + ((long long)s_idx * seq + mt * 128) * pitch + h * 64,
+                           pitch, min(128, seq - mt * 128));
     }
   }
   tc_fence_before();
@@ -462,10 +473,11 @@ extern "C" int pvrl_attn_tc_bwd(const void* qkv, const void* out, const void* do
                                 int32_t n_seq, int32_t seq, int32_t H, float scale, void* stream) {
   PVRL_CHECK_ARG(qkv && out && dout && lse && dqkv && n_seq > 0 && H > 0, "pvrl_attn_tc_bwd: bad arguments");
   PVRL_CHECK_ARG(seq > 0 && seq <= 256, "pvrl_attn_tc_bwd: seq=%d must be in [1, 256]", seq);
-  CUtensorMap tqkv, tdo;
+  CUtensorMap tqkv, tdo, to;
   int rc;
   if ((rc = make_tmap_3d(&tqkv, qkv, 3ull * H * 64, seq, n_seq, 128))) return rc;
   if ((rc = make_tmap_3d(&tdo, dout, 1ull * H * 64, seq, n_seq, 128))) return rc;
+  if ((rc = make_tmap_3d(&to, out, 1ull * H * 64, seq, n_seq, 128))) return rc;
   const size_t smem = 12 * TILE_BYTES + 64 + 1024;
   static bool configured = false;
   if (!configured) {
@@ -473,7 +485,6 @@ extern "C" int pvrl_attn_tc_bwd(const void* qkv, const void* out, const void* do
     configured = true;
   }
   attn_tc_bwd_kernel<<<n_seq * H, BWD_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
-      tqkv, tdo, static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), lse,
-      static_cast<__nv_bfloat16*>(dqkv), seq, H, scale);
+      tqkv, tdo, to, lse, static_cast<__nv_bfloat16*>(dqkv), seq, H, scale);
   return launched("attn_tc_bwd_kernel");
 }

@@ -279,14 +279,23 @@ int gemm2_dispatch(const pvrl_gemm_t* d, cudaStream_t stream) {
   int splits = 1;
   if (d->epilogue == PVRL_EPI_ATOMIC) {
     splits = d->k_splits;
-    if (splits <= 0) {   // fill whole waves of CTA pairs
+    if (splits <= 0) {
+      // Fill one whole wave of CTA pairs (PVRL_GEMM2_WAVES = 2 / 3: more, shorter tiles per pair so that the atomic
+      // epilogue of one hides behind the MMAs of the next -- measured within noise of a single wave, at twice the
+      // red.add traffic, so one wave stays the default).
+      static const int waves_env = [] {
+        const char* e = getenv("PVRL_GEMM2_WAVES");
+        return e ? atoi(e) : 1;
+      }();
       const int pairs = num_sms() / 2;
       double best = -1.0;
       splits = 1;
       for (int s = 1; s <= 64 && s <= num_kb; ++s) {
-        if (s > 1 && (num_kb + s - 1) / s < 4) break;
+        if (s > 1 && (num_kb + s - 1) / s < 8) break;
         const int work = tiles * s;
-        const double util = static_cast<double>(work) / (((work + pairs - 1) / pairs) * pairs);
+        const int waves = (work + pairs - 1) / pairs;
+        if (waves > waves_env) break;
+        const double util = static_cast<double>(work) / (waves * pairs) + 0.05 * (waves == waves_env);
         if (util > best + 0.02) best = util, splits = s;
       }
     }
