@@ -122,7 +122,7 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ x_cl
 // One warp per row, NVEC float4 per lane (D = 128 * NVEC); per-lane column sums of dy*xhat / dy live in registers
 // across the rows a warp visits and are folded block-wide through shared memory, then one atomicAdd per column.
 template <typename InT, int NVEC>
-__global__ void __launch_bounds__(LN_WARPS * 32, 2)
+__global__ void __launch_bounds__(LN_WARPS * 32, NVEC <= 4 ? 2 : 1)
 layernorm_bwd_kernel(const InT* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ x_cls,
                      const float* __restrict__ w, const float* __restrict__ stats, float* __restrict__ dx,
                      float* __restrict__ dw, float* __restrict__ db, int M, int map, Geom g) {
@@ -140,11 +140,13 @@ layernorm_bwd_kernel(const InT* __restrict__ dy, const float* __restrict__ x, co
     const long long xr = cls ? ((-r - 1) / g.T) * (long long)g.S : r;
     const float* xp = (cls ? x_cls : x) + xr * D;
     const float2 st = reinterpret_cast<const float2*>(stats)[m];
-    float4 xh[NVEC], gg[NVEC];
+    float4 xh[NVEC], gg[NVEC], cur[NVEC];
+    float* dp = dx + xr * D;
 #pragma unroll
-    for (int i = 0; i < NVEC; ++i) {   // all loads of the row in flight before any use
-      xh[i] = __ldg(reinterpret_cast<const float4*>(xp) + i * 32 + lane);
-      gg[i] = load4<InT>(dy + (long long)m * D + (i * 32 + lane) * 4);
+    for (int i = 0; i < NVEC; ++i) {   // every load of the row -- including the dx it accumulates into -- is in flight
+      xh[i] = __ldg(reinterpret_cast<const float4*>(xp) + i * 32 + lane);   // before the first use: one memory round
+      gg[i] = load4<InT>(dy + (long long)m * D + (i * 32 + lane) * 4);       // trip per row instead of two
+      if (!cls) cur[i] = *(reinterpret_cast<const float4*>(dp) + i * 32 + lane);
     }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -161,7 +163,6 @@ layernorm_bwd_kernel(const InT* __restrict__ dy, const float* __restrict__ x, co
       s2 += gg[i].x * xh[i].x + gg[i].y * xh[i].y + gg[i].z * xh[i].z + gg[i].w * xh[i].w;
     }
     const float c1 = warp_sum(s1) * (1.0f / D), c2 = warp_sum(s2) * (1.0f / D);
-    float* dp = dx + xr * D;
 #pragma unroll
     for (int i = 0; i < NVEC; ++i) {
       const float4 o = make_float4(st.y * (gg[i].x - c1 - xh[i].x * c2), st.y * (gg[i].y - c1 - xh[i].y * c2),
@@ -170,9 +171,7 @@ layernorm_bwd_kernel(const InT* __restrict__ dy, const float* __restrict__ x, co
       if (cls) {  // T frames of one clip share the cls row (vit.py:138-140)
         atomicAdd(p, o.x), atomicAdd(p + 1, o.y), atomicAdd(p + 2, o.z), atomicAdd(p + 3, o.w);
       } else {
-        float4 cur = *reinterpret_cast<float4*>(p);
-        cur.x += o.x, cur.y += o.y, cur.z += o.z, cur.w += o.w;
-        *reinterpret_cast<float4*>(p) = cur;
+        *reinterpret_cast<float4*>(p) = make_float4(cur[i].x + o.x, cur[i].y + o.y, cur[i].z + o.z, cur[i].w + o.w);
       }
     }
   }
@@ -195,7 +194,7 @@ template <typename InT>
 int layernorm_bwd_launch(const void* dy, const float* x, const float* x_cls, const float* w, const float* stats,
                          float* dx, float* dw, float* db, int M, int D, int map, Geom gg, cudaStream_t stream) {
   int grid = (M + LN_WARPS - 1) / LN_WARPS;
-  if (grid > 148 * 4) grid = 148 * 4;
+  if (grid > 148 * 2) grid = 148 * 2;   // persistent row loop; 1-2 blocks are resident per SM (register-bound)
   const InT* d = static_cast<const InT*>(dy);
   switch (D / 128) {
     case 2: layernorm_bwd_kernel<InT, 2><<<grid, LN_WARPS * 32, 0, stream>>>(d, x, x_cls, w, stats, dx, dw, db, M, map, gg); break;
