@@ -48,6 +48,7 @@ class EncoderEngine:
         self.use_tc_attention = True      # tcgen05 spatial attention in bf16 mode (the fp32 parity mode uses CUDA cores)
         self._wepoch = 0
         self.grad_sink = None             # optional dict name -> fp32 tensor: backward accumulates straight into it
+        self.on_block_bwd_done = None     # optional callable(i): block i's parameter gradients are complete (bucketed all-reduce)
         self._wcache = {}      # name -> (version, W operand [N, K'], W^T operand [K, N'])
         self.grad_names = self._grad_names()
 
@@ -317,6 +318,8 @@ class EncoderEngine:
         for i in reversed(range(self.depth)):
             self._block_bwd(i, st["blocks"][i], dx, G, Bc, T, HW)
             st["blocks"][i] = None                 # free this block's activations
+            if self.on_block_bwd_done is not None:
+                self.on_block_bwd_done(i)
 
         # embeddings (vit.py:370-407): patch conv, cls token, pos / time embeddings
         KP = 3 * self.patch * self.patch

@@ -5,9 +5,36 @@ tools/train_net.py:146-191; no tracing compiler involved -- the graph is a recor
 Gradients live in ONE flat fp32 buffer (`.grad`s are views of it): the engine's dW/db kernels accumulate straight
 into it, and data-parallel replicas synchronise with a single NCCL all-reduce over that buffer (SURVEY.md 8e:
 the only collective on the path)."""
+import os
+
 import torch
 
 from . import functional as PF
+
+
+def bucket_ranges(named_sizes, depth, blocks_per_bucket):
+    """Partition of the flat gradient buffer (parameters in `named_sizes` order) for the overlapped exchange:
+    ({first block index of a bucket -> (start, end)}, front_end, tail_start).  A bucket is fired when the backward has
+    finished its first (lowest) block; [0, front_end) -- embeddings and the first blocks -- and [tail_start, total) --
+    final norm, head, order transformer -- are exchanged at the end.  Buckets, front and tail tile the buffer exactly."""
+    offs, off = {}, 0
+    for n, sz in named_sizes:
+        offs[n] = (off, off + sz)
+        off += sz
+    blk = []
+    for i in range(depth):
+        r = [v for k, v in offs.items() if f".blocks.{i}." in k]
+        blk.append((min(a for a, _ in r), max(b for _, b in r)))
+    assert all(blk[i][1] == blk[i + 1][0] for i in range(depth - 1)), "encoder blocks must be contiguous in the flat buffer"
+    ranges, front_end, hi = {}, blk[0][0], depth
+    while hi > 0:
+        lo = max(0, hi - blocks_per_bucket)
+        if lo > 0:
+            ranges[lo] = (blk[lo][0], blk[hi - 1][1])
+        else:
+            front_end = blk[hi - 1][1]
+        hi = lo
+    return ranges, front_end, blk[depth - 1][1]
 
 
 class PretrainStep:
@@ -30,9 +57,30 @@ class PretrainStep:
         eng.grad_sink = {n: by_name[n].grad for n in eng.grad_names}
         assert all(g is not None for g in eng.grad_sink.values()), "every encoder parameter must be trainable here"
         self.opt = torch.optim.AdamW(self.params, lr=lr, weight_decay=weight_decay, fused=True, capturable=use_graph)
+        # Data-parallel gradient exchange (the only collective).  Default: ONE NCCL all-reduce of the flat buffer
+        # after the backward (measured on 2 B200s: 34.4 ms/step).  PVRL_AR_BLOCKS_PER_BUCKET = n > 0 instead exchanges
+        # buckets of n encoder blocks on a side stream as soon as the backward has finished them (part of the captured
+        # CUDA graph); on 2 GPUs that measured 34.9 ms -- the NCCL kernels take SMs away from the persistent GEMMs for
+        # longer than the ~0.3 ms the exposed exchange costs -- so it stays opt-in until it is measured on 8 GPUs.
+        self.blocks_per_bucket = int(os.environ.get("PVRL_AR_BLOCKS_PER_BUCKET", "0"))
+        self._ar_stream = torch.cuda.Stream() if self.world > 1 else None
+        self._ar_ranges = None
+        if self.world > 1 and self.blocks_per_bucket > 0:
+            names = [(n, p.numel()) for n, p in model.named_parameters() if p.requires_grad]
+            self._ar_ranges, self._ar_front_end, self._ar_tail_start = bucket_ranges(names, eng.depth,
+                                                                                     self.blocks_per_bucket)
+            eng.on_block_bwd_done = self._bucket_ready
         self.use_graph = use_graph
         self.graph = None
         self.static = None
+
+    def _bucket_ready(self, i):
+        rng = self._ar_ranges.get(i)
+        if rng is None:
+            return
+        self._ar_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._ar_stream):
+            torch.distributed.all_reduce(self.flat_grad[rng[0]:rng[1]], op=torch.distributed.ReduceOp.AVG, group=self.pg)
 
     def _eager(self, frames, meta):
         self.inner.engine().invalidate_weights()
@@ -41,7 +89,13 @@ class PretrainStep:
         loss, _, _ = PF.pretrain_loss(pred, teacher, mse, topk=self.topk)
         loss.backward()
         if self.world > 1:
-            torch.distributed.all_reduce(self.flat_grad, op=torch.distributed.ReduceOp.AVG, group=self.pg)
+            if self._ar_ranges is None:
+                torch.distributed.all_reduce(self.flat_grad, op=torch.distributed.ReduceOp.AVG, group=self.pg)
+            else:      # what the block buckets did not cover: [embeddings | first blocks) and (norm | head | order transformer]
+                AVG = torch.distributed.ReduceOp.AVG
+                torch.distributed.all_reduce(self.flat_grad[:self._ar_front_end], op=AVG, group=self.pg)
+                torch.distributed.all_reduce(self.flat_grad[self._ar_tail_start:], op=AVG, group=self.pg)
+                torch.cuda.current_stream().wait_stream(self._ar_stream)
         self.opt.step()
         return loss.detach()
 

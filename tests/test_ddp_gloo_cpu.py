@@ -93,3 +93,22 @@ def test_two_rank_gradients_match_full_batch(gold_dir, tmp_path):
         from procedurevrl_b200.lib.models.vit import VisionTransformer
         importlib.reload(ops)
         VisionTransformer._require_cuda = True
+
+
+def test_allreduce_bucket_ranges_tile_the_flat_buffer():
+    """Host logic of the overlapped gradient exchange (trainer.bucket_ranges): block buckets + front + tail cover every
+    element of the flat gradient buffer exactly once, for every bucket size."""
+    from procedurevrl_b200.trainer import bucket_ranges
+    names = [("model.cls_token", 768), ("model.pos_embed", 197 * 768), ("model.patch_embed.proj.weight", 768 * 768)]
+    for i in range(12):
+        names += [(f"model.blocks.{i}.norm1.weight", 768), (f"model.blocks.{i}.attn.qkv.weight", 2304 * 768),
+                  (f"model.blocks.{i}.mlp.fc2.bias", 768)]
+    names += [("model.norm.weight", 768), ("model.head.weight", 512 * 768),
+              ("model.order_tfm.temporalModelling.resblocks.0.ln_1.weight", 512)]
+    total = sum(s for _, s in names)
+    for bpb in (1, 2, 3, 4, 5, 12, 20):
+        ranges, front_end, tail_start = bucket_ranges(names, 12, bpb)
+        cover = [(0, front_end)] + sorted(ranges.values()) + [(tail_start, total)]
+        assert cover[0][0] == 0 and cover[-1][1] == total
+        assert all(cover[k][1] == cover[k + 1][0] for k in range(len(cover) - 1)), (bpb, cover)
+        assert all(lo > 0 for lo in ranges)          # block 0's bucket always rides with the final exchange
