@@ -70,26 +70,31 @@ __device__ __forceinline__ void mul4(float4& a, float s) { a.x *= s, a.y *= s, a
 struct RowCtx {
   int orow;         // residual-stream / output row (map_row); < 0 = cls row of a spatial sequence
   float rs;         // DropPath factor of the row (1 when none)
+  // Addresses of this lane's 4 columns of the row in chunk 0 of the tile; chunk c adds the constant 32 * c elements, so
+  // the unrolled epilogue addresses every access as pointer + immediate (no per-store 64-bit arithmetic).
+  uint8_t* o1;        // out (or, for the cls rows of a spatial sequence, the side buffer out2)
+  uint8_t* o2;        // GELU: out2
+  const uint8_t* sd;  // RESID: residual, DGELU: saved gelu'
 };
 
 // "side" operand of one 4-column piece: the fp32 residual (RESID) or the saved GELU derivative (DGELU).  It does not
 // depend on the accumulator, so the epilogue fetches it one 32-column chunk ahead (see the kernel) and the HBM latency
 // of these loads overlaps the MMAs / the previous chunk instead of sitting between the TMEM read and the store.
 template <int EPI, typename OutT>
-__device__ __forceinline__ float4 load_side(const GemmArgs& p, int m, const RowCtx& rc, int n) {
+__device__ __forceinline__ float4 load_side(const GemmArgs& p, int m, const RowCtx& rc, int coff) {
   if (EPI == PVRL_EPI_RESID) {
-    if (p.resid != nullptr && m < p.M && rc.orow >= 0) return ld_vec4<float>(p.resid + (long long)rc.orow * p.ldo + n);
+    if (p.resid != nullptr && m < p.M && rc.orow >= 0) return ld_vec4<float>(reinterpret_cast<const float*>(rc.sd) + coff);
   } else if (EPI == PVRL_EPI_DGELU) {
-    if (m < p.M) return ld_vec4<OutT>(reinterpret_cast<const OutT*>(p.aux) + (long long)m * p.ld_aux + n);
+    if (m < p.M) return ld_vec4<OutT>(reinterpret_cast<const OutT*>(rc.sd) + coff);
   }
   return make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 template <int EPI, typename OutT>
-__device__ __forceinline__ void epilogue_vec4(const GemmArgs& p, int m, const RowCtx& rc, int n, float4& v,
+__device__ __forceinline__ void epilogue_vec4(const GemmArgs& p, int m, const RowCtx& rc, int coff, int n, float4& v,
                                               const float4& bias4, const float4& side) {
   if (EPI == PVRL_EPI_ATOMIC) {
-    float* dst = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + n;
+    float* dst = reinterpret_cast<float*>(rc.o1) + coff;
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
     return;
@@ -99,16 +104,15 @@ __device__ __forceinline__ void epilogue_vec4(const GemmArgs& p, int m, const Ro
     float4 a, d;
     gelu_both<OutT>(v.x, a.x, d.x), gelu_both<OutT>(v.y, a.y, d.y), gelu_both<OutT>(v.z, a.z, d.z),
         gelu_both<OutT>(v.w, a.w, d.w);
-    st_vec4<OutT>(reinterpret_cast<OutT*>(p.out) + (long long)m * p.ldo + n, d);
-    st_vec4<OutT>(reinterpret_cast<OutT*>(p.out2) + (long long)m * p.ldo + n, a);
+    st_vec4<OutT>(reinterpret_cast<OutT*>(rc.o1) + coff, d);
+    st_vec4<OutT>(reinterpret_cast<OutT*>(rc.o2) + coff, a);
     return;
   }
   if (EPI == PVRL_EPI_DGELU) v.x *= side.x, v.y *= side.y, v.z *= side.z, v.w *= side.w;
   mul4(v, rc.rs);
   if (EPI == PVRL_EPI_RESID) {
-    float* out = reinterpret_cast<float*>(p.out);
-    if (rc.orow < 0) {  // cls row of a spatial sequence: park it for the mean over frames (vit.py:147-149)
-      st_vec4<float>(reinterpret_cast<float*>(p.out2) + (long long)(-rc.orow - 1) * p.ldo + n, v);
+    if (rc.orow < 0) {  // cls row of a spatial sequence: park it for the mean over frames (vit.py:147-149); o1 -> out2
+      st_vec4<float>(reinterpret_cast<float*>(rc.o1) + coff, v);
       return;
     }
     add4(v, side);
@@ -117,11 +121,11 @@ __device__ __forceinline__ void epilogue_vec4(const GemmArgs& p, int m, const Ro
       add4(v, ld_vec4<float>(p.add_pos + (long long)(1 + m - bt * p.g.HW) * p.N + n));
       add4(v, ld_vec4<float>(p.add_time + (long long)(bt % p.g.T) * p.N + n));
     }
-    st_vec4<float>(out + (long long)rc.orow * p.ldo + n, v);
+    st_vec4<float>(reinterpret_cast<float*>(rc.o1) + coff, v);
     return;
   }
   // STORE / DGELU
-  st_vec4<OutT>(reinterpret_cast<OutT*>(p.out) + (long long)rc.orow * p.ldo + n, v);
+  st_vec4<OutT>(reinterpret_cast<OutT*>(rc.o1) + coff, v);
 }
 
 // pvrl_gemm_t -> kernel argument block (the split-K fields are filled in by the launcher)
@@ -180,6 +184,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stg, u
     const int src = 4 * i + rsub;
     rc[i].orow = __shfl_sync(0xffffffffu, own.orow, src);
     rc[i].rs = (EPI != PVRL_EPI_ATOMIC && EPI != PVRL_EPI_GELU) ? __shfl_sync(0xffffffffu, own.rs, src) : 1.0f;
+    constexpr int OSZ = (EPI == PVRL_EPI_RESID || EPI == PVRL_EPI_ATOMIC) ? 4 : static_cast<int>(sizeof(OutT));
+    const long long oel = (long long)(rc[i].orow >= 0 ? rc[i].orow : -rc[i].orow - 1) * p.ldo + n_base + piece * 4;
+    rc[i].o1 = reinterpret_cast<uint8_t*>((EPI == PVRL_EPI_RESID && rc[i].orow < 0) ? p.out2 : p.out) + oel * OSZ;
+    rc[i].o2 = EPI == PVRL_EPI_GELU ? reinterpret_cast<uint8_t*>(p.out2) + oel * OSZ : nullptr;
+    rc[i].sd = nullptr;
+    if (EPI == PVRL_EPI_RESID) rc[i].sd = reinterpret_cast<const uint8_t*>(p.resid) + oel * 4;
+    if (EPI == PVRL_EPI_DGELU)
+      rc[i].sd = reinterpret_cast<const uint8_t*>(p.aux) +
+                 ((long long)(m_base + src) * p.ld_aux + n_base + piece * 4) * static_cast<int>(sizeof(OutT));
   }
   constexpr int NCH = HALF_COLS / 32;
   constexpr bool HAS_SIDE = EPI == PVRL_EPI_RESID || EPI == PVRL_EPI_DGELU;
@@ -199,14 +212,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stg, u
       for (int i = 0; i < 8; ++i) {
         const int m = m_base + 4 * i + rsub;
         sidep[c][i] = (m < p.M && n < p.N)
-                          ? __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) +
-                                                                 (long long)m * p.ld_aux + n))
+                          ? __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(rc[i].sd) + c * 32))
                           : make_uint2(0u, 0u);
       }
     }
   } else if (HAS_SIDE && n_first < p.N) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) side[0][i] = load_side<EPI, OutT>(p, m_base + 4 * i + rsub, rc[i], n_first);
+    for (int i = 0; i < 8; ++i) side[0][i] = load_side<EPI, OutT>(p, m_base + 4 * i + rsub, rc[i], 0);
   }
   mbar_wait(tfull, tfull_phase);
   tc_fence_after();
@@ -217,7 +229,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stg, u
       if (HAS_SIDE && !SIDE_PACKED && c + 1 < NCH && n0 + 32 < p.N) {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          side[(c + 1) & 1][i] = load_side<EPI, OutT>(p, m_base + 4 * i + rsub, rc[i], n0 + 32 + piece * 4);
+          side[(c + 1) & 1][i] = load_side<EPI, OutT>(p, m_base + 4 * i + rsub, rc[i], (c + 1) * 32);
       }
       uint32_t raw[32];
       tmem_ld32(tmem_cols + c * 32, raw);
@@ -244,7 +256,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stg, u
           } else if (HAS_SIDE) {
             sd = side[c & 1][i];
           }
-          epilogue_vec4<EPI, OutT>(p, m, rc[i], n, v, bias4, sd);
+          epilogue_vec4<EPI, OutT>(p, m, rc[i], c * 32, n, v, bias4, sd);
           if (HAS_COLSUM) add4(csum, v);
         }
       }
