@@ -16,26 +16,32 @@ namespace pvrl {
 namespace {
 
 constexpr int STAGES = 4;
-template <int BN>
+// EW = epilogue warps: 8 (two 128- / 96-column groups per TMEM lane quarter) or, for the GELU / gelu' epilogues whose
+// per-element arithmetic makes the epilogue the longer phase of a K = 768 tile, 12 with BN = 192 (three 64-column groups):
+// half the elements per thread, 3 instead of 2 warps per scheduler to hide the MUFU / FMA latencies.
+template <int BN, int EW>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;                // 32 KB (BN 256) / 24 KB (BN 192)
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
-  static constexpr int SMEM_BYTES = PIPE_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align*/ + 128 /*barriers*/;
+  static constexpr int THREADS = 128 + 32 * EW;
+  static constexpr int GROUP_COLS = BN / (EW / 4);
+  static constexpr int SMEM_BYTES = PIPE_BYTES + EW * EPI_STAGE_BYTES + 1024 /*align*/ + 128 /*barriers*/;
+  static_assert(GROUP_COLS % 32 == 0 && SMEM_BYTES <= 232448, "tile configuration");
 };
 
 
-template <int EPI, typename OutT, bool TN, int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int EPI, typename OutT, bool TN, int BN, int EW>
+__global__ void __launch_bounds__(128 + 32 * EW, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, EW>;
   constexpr int STAGE_BYTES = C::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
   uint8_t* smem = smem_raw + (tiles_addr - raw_addr);
   const uint32_t epi_addr = tiles_addr + C::PIPE_BYTES;
-  constexpr int BAR_OFF = C::PIPE_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES;
+  constexpr int BAR_OFF = C::PIPE_BYTES + EW * EPI_STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
   const uint32_t bars_addr = tiles_addr + BAR_OFF;
   // barrier slots: full[0..3], empty[4..7], tmem_full[8..9], tmem_empty[10..11], tmem ptr at slot 12
@@ -64,7 +70,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), NUM_EPI_WARPS);
+      mbar_init(tempty_bar(s), EW);
     }
     fence_mbar_init();
   }
@@ -144,8 +150,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue: TMEM -> regs -> smem transpose -> global
     const int quarter = warp & 3;          // TMEM lanes [32*quarter, +32) are the only ones this warp may read
-    const int half = (warp - 4) >> 2;      // column half of the BN-wide accumulator
-    constexpr int HALF_COLS = BN / 2;
+    const int half = (warp - 4) >> 2;      // column group of the BN-wide accumulator
+    constexpr int HALF_COLS = C::GROUP_COLS;
     uint8_t* stg = smem + C::PIPE_BYTES + (warp - 4) * EPI_STAGE_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -249,10 +255,10 @@ int num_sms() {
 
 namespace {
 
-template <int EPI, typename OutT, bool TN, int BN>
+template <int EPI, typename OutT, bool TN, int BN, int EW>
 int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t stream) {
-  auto kern = gemm_bf16_kernel<EPI, OutT, TN, BN>;
-  constexpr int SMEM_BYTES = Cfg<BN>::SMEM_BYTES;
+  auto kern = gemm_bf16_kernel<EPI, OutT, TN, BN, EW>;
+  constexpr int SMEM_BYTES = Cfg<BN, EW>::SMEM_BYTES;
   static bool configured = false;
   if (!configured) {
     PVRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -261,14 +267,19 @@ int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs&
   const int m_tiles = (a.M + BM - 1) / BM, n_tiles = (a.N + BN - 1) / BN;
   const int total = m_tiles * n_tiles * a.k_splits;
   const int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, a);
+  kern<<<grid, Cfg<BN, EW>::THREADS, SMEM_BYTES, stream>>>(ta, tb, a);
   return launched("gemm_bf16_kernel");
 }
 
 template <int EPI, typename OutT, bool TN>
 int launch_gemm(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t stream) {
-  return bn == 192 ? launch_gemm_bn<EPI, OutT, TN, 192>(ta, tb, a, stream)
-                   : launch_gemm_bn<EPI, OutT, TN, 256>(ta, tb, a, stream);
+  // bf16 GELU / gelu' epilogues on 192-wide tiles: 12 epilogue warps (see Cfg)
+  constexpr bool HEAVY = (EPI == PVRL_EPI_GELU || EPI == PVRL_EPI_DGELU) && sizeof(OutT) == 2;
+  if (bn == 192) {
+    if (HEAVY) return launch_gemm_bn<EPI, OutT, TN, 192, HEAVY ? 12 : 8>(ta, tb, a, stream);
+    return launch_gemm_bn<EPI, OutT, TN, 192, 8>(ta, tb, a, stream);
+  }
+  return launch_gemm_bn<EPI, OutT, TN, 256, 8>(ta, tb, a, stream);
 }
 
 // Tile width and split-K count for one problem: the (BN, splits) pair whose tiles fill whole waves of SMs best
@@ -337,7 +348,11 @@ extern "C" int pvrl_gemm_bf16(const pvrl_gemm_t* d, void* stream_) {
     const char* e = getenv("PVRL_GEMM_BN");   // development knob: pin the tile width (192 / 256)
     return e ? atoi(e) : 0;
   }();
-  pick_tiling(d->M, d->N, num_kb, d->epilogue == PVRL_EPI_ATOMIC, d->k_splits, forced_bn, &bn, &splits);
+  int want_bn = forced_bn;
+  if (want_bn == 0 && (d->epilogue == PVRL_EPI_GELU || d->epilogue == PVRL_EPI_DGELU) && d->out_dtype == PVRL_BF16 &&
+      d->N % 192 == 0)
+    want_bn = 192;   // the 12-epilogue-warp variant
+  pick_tiling(d->M, d->N, num_kb, d->epilogue == PVRL_EPI_ATOMIC, d->k_splits, want_bn, &bn, &splits);
   if (splits > num_kb) splits = num_kb;
   a.kb_per_split = (num_kb + splits - 1) / splits;
   a.k_splits = (num_kb + a.kb_per_split - 1) / a.kb_per_split;  // no empty split
