@@ -207,51 +207,65 @@ int layernorm_bwd_launch(const void* dy, const float* x, const float* x_cls, con
 }
 
 // ---------------------------------------------------------------------------------------- gather + cast
-// One block = D/4 threads, thread c owns 4 feature columns and walks the block's rows (4 rows in flight): every row
-// access is one contiguous D*4-byte burst, and because a thread keeps its columns the bias gradient colsum(out) comes
-// for free (registers -> one fp32 atomic per column and block) -- the separate pvrl_colsum pass over dY disappears.
-template <typename OutT>
-__global__ void __launch_bounds__(256)
+// One warp per row (NVEC float4 per lane, the whole row in flight), persistent over the rows like the LayerNorm kernels
+// -- the access pattern that streams HBM at ~5 TB/s here.  Because a lane keeps its columns across the rows its warp
+// visits, the bias gradient colsum(out) comes for free: per-lane partial sums -> shared memory -> one fp32 atomic per
+// column and block, and the separate pvrl_colsum pass over dY disappears.
+template <typename OutT, int NVEC>
+__global__ void __launch_bounds__(LN_WARPS * 32)
 gather_cast_kernel(const float* __restrict__ src, OutT* __restrict__ out, const float* __restrict__ rowscale, int rs_div,
-                   int M, int D, int map, Geom g, float* __restrict__ colsum) {
-  constexpr int R = 8;                      // rows in flight per thread
-  const int c = threadIdx.x * 4;
-  const int lane = threadIdx.x & 31;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int m0 = blockIdx.x * R; m0 < M; m0 += gridDim.x * R) {
-    // the row map (integer divisions) and the DropPath factor are the same for every thread of the block: lanes 0..R-1
-    // of each warp evaluate them once, the others pick them up by shuffle
-    long long r_l = 0;
-    float f_l = 0.f;
-    if (lane < R) {
-      const int m = min(m0 + lane, M - 1);
-      r_l = map_row(map, m, g);
-      f_l = rowscale != nullptr ? __ldg(rowscale + m / rs_div) : 1.0f;
-      if (r_l < 0) {  // cls row of a spatial sequence: d(mean over T) = 1/T
-        r_l = ((-r_l - 1) / g.T) * (long long)g.S;
-        f_l *= 1.0f / g.T;
-      }
-    }
-    float4 v[R];
-    float f[R];
+                   int M, int map, Geom g, float* __restrict__ colsum) {
+  constexpr int D = NVEC * 128;
+  __shared__ float sacc[D];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 acc[NVEC];
 #pragma unroll
-    for (int u = 0; u < R; ++u) {
-      const long long r = __shfl_sync(0xffffffffu, r_l, u);
-      f[u] = __shfl_sync(0xffffffffu, f_l, u);
-      v[u] = __ldg(reinterpret_cast<const float4*>(src + r * D + c));
+  for (int i = 0; i < NVEC; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int m = blockIdx.x * LN_WARPS + warp; m < M; m += gridDim.x * LN_WARPS) {
+    long long r = map_row(map, m, g);
+    float f = rowscale != nullptr ? __ldg(rowscale + m / rs_div) : 1.0f;
+    if (r < 0) {  // cls row of a spatial sequence: d(mean over T) = 1/T
+      r = ((-r - 1) / g.T) * (long long)g.S;
+      f *= 1.0f / g.T;
     }
+    float4 v[NVEC];
 #pragma unroll
-    for (int u = 0; u < R; ++u)
-      if (m0 + u < M) {
-        const float4 o = make_float4(v[u].x * f[u], v[u].y * f[u], v[u].z * f[u], v[u].w * f[u]);
-        store4<OutT>(out + (long long)(m0 + u) * D + c, o.x, o.y, o.z, o.w);
-        acc.x += o.x, acc.y += o.y, acc.z += o.z, acc.w += o.w;
-      }
+    for (int i = 0; i < NVEC; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(src + r * D) + i * 32 + lane);
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      const float4 o = make_float4(v[i].x * f, v[i].y * f, v[i].z * f, v[i].w * f);
+      store4<OutT>(out + (long long)m * D + (i * 32 + lane) * 4, o.x, o.y, o.z, o.w);
+      acc[i].x += o.x, acc[i].y += o.y, acc[i].z += o.z, acc[i].w += o.w;
+    }
   }
   if (colsum != nullptr) {
-    atomicAdd(colsum + c, acc.x), atomicAdd(colsum + c + 1, acc.y), atomicAdd(colsum + c + 2, acc.z),
-        atomicAdd(colsum + c + 3, acc.w);
+    for (int i = threadIdx.x; i < D; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      atomicAdd(&sacc[c], acc[i].x), atomicAdd(&sacc[c + 1], acc[i].y), atomicAdd(&sacc[c + 2], acc[i].z),
+          atomicAdd(&sacc[c + 3], acc[i].w);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < D; i += blockDim.x) atomicAdd(colsum + i, sacc[i]);
   }
+}
+
+template <typename OutT>
+int gather_cast_launch(const float* src, void* out, const float* rowscale, int rs_div, int M, int D, int map, Geom gg,
+                       float* colsum, cudaStream_t stream) {
+  int grid = (M + LN_WARPS - 1) / LN_WARPS;
+  if (grid > 148 * 6) grid = 148 * 6;
+  OutT* o = static_cast<OutT*>(out);
+  switch (D / 128) {
+    case 2: gather_cast_kernel<OutT, 2><<<grid, LN_WARPS * 32, 0, stream>>>(src, o, rowscale, rs_div, M, map, gg, colsum); break;
+    case 4: gather_cast_kernel<OutT, 4><<<grid, LN_WARPS * 32, 0, stream>>>(src, o, rowscale, rs_div, M, map, gg, colsum); break;
+    case 6: gather_cast_kernel<OutT, 6><<<grid, LN_WARPS * 32, 0, stream>>>(src, o, rowscale, rs_div, M, map, gg, colsum); break;
+    case 8: gather_cast_kernel<OutT, 8><<<grid, LN_WARPS * 32, 0, stream>>>(src, o, rowscale, rs_div, M, map, gg, colsum); break;
+    default: return fail(-1, "pvrl_gather_cast: D=%d not in {256, 512, 768, 1024}", D);
+  }
+  return launched("gather_cast_kernel");
 }
 
 __global__ void cls_merge_kernel(const float* __restrict__ x0, const float* __restrict__ side, float* __restrict__ x2,
@@ -463,17 +477,9 @@ extern "C" int pvrl_gather_cast(const float* src, void* out, int32_t out_dtype, 
   PVRL_CHECK_ARG(src && out && M > 0 && D % 4 == 0 && D <= 4096, "pvrl_gather_cast: bad arguments");
   PVRL_CHECK_ARG(rowscale == nullptr || rs_div > 0, "pvrl_gather_cast: rowscale needs rs_div > 0");
   const Geom gg(g.T > 0 ? g.T : 1, g.HW > 0 ? g.HW : 1);
-  PVRL_CHECK_ARG(D % 128 == 0 && D <= 1024, "pvrl_gather_cast: D=%d must be a multiple of 128, <= 1024", D);
-  const int block = D / 4;                  // whole warps: the row map is shared through warp shuffles
-  int grid = (M + 7) / 8;
-  if (grid > 148 * 5) grid = 148 * 5;
-  if (out_dtype == PVRL_F32)
-    gather_cast_kernel<float><<<grid, block, 0, STREAM>>>(src, static_cast<float*>(out), rowscale,
-                                                          rs_div > 0 ? rs_div : 1, M, D, map, gg, colsum);
-  else
-    gather_cast_kernel<__nv_bfloat16><<<grid, block, 0, STREAM>>>(src, static_cast<__nv_bfloat16*>(out), rowscale,
-                                                                  rs_div > 0 ? rs_div : 1, M, D, map, gg, colsum);
-  return launched("gather_cast_kernel");
+  const int rd = rs_div > 0 ? rs_div : 1;
+  return out_dtype == PVRL_F32 ? gather_cast_launch<float>(src, out, rowscale, rd, M, D, map, gg, colsum, STREAM)
+                               : gather_cast_launch<__nv_bfloat16>(src, out, rowscale, rd, M, D, map, gg, colsum, STREAM);
 }
 
 extern "C" int pvrl_cls_merge(const float* x0, const float* side, float* x2, int32_t Bc, int32_t T, int32_t S,

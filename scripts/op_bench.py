@@ -14,10 +14,25 @@ from procedurevrl_b200 import ops  # noqa: E402
 
 
 WARM = 3
+COLD = None      # when set: a buffer larger than L2 that is rewritten between timed launches (every launch sees a cold L2,
+                 # as inside the real step where ~14 GB stream through between two uses of a tensor)
 
 
 def timeit(fn, iters, warm=None):
     warm = WARM if warm is None else warm
+    if COLD is not None:
+        for _ in range(warm):
+            fn()
+        tot = 0.0
+        for _ in range(iters):
+            COLD.add_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / iters * 1e3
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -38,9 +53,12 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--warm", type=int, default=3)
     ap.add_argument("--json", default="")
+    ap.add_argument("--cold", action="store_true", help="flush L2 (rewrite a 512 MB buffer) before every timed launch")
     a = ap.parse_args()
-    global WARM
+    global WARM, COLD
     WARM = a.warm
+    if a.cold:
+        COLD = torch.zeros(128 * 1024 * 1024, device="cuda")
     dev = torch.device("cuda")
     Bc, T, HW, D, H, Hd = a.clips, a.frames, 196, 768, 12, 3072
     L, S = HW * T, 1 + HW * T
