@@ -85,8 +85,10 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ x_cl
                      const float* __restrict__ b, OutT* __restrict__ y, float* __restrict__ stats, int M, int D,
                      float eps, int map, Geom g) {
   const int lane = threadIdx.x & 31;
-  const int m = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
-  if (m >= M) return;
+  // Rows are visited from the LAST to the first: the GEMM epilogue that produced x wrote its highest rows last (they are
+  // still in the 126 MB L2), and the GEMM that consumes y starts at row 0 -- which this kernel therefore writes last.
+  const int m = M - 1 - (blockIdx.x * LN_WARPS + (threadIdx.x >> 5));
+  if (m < 0) return;
   const float* xp = ln_src_row(x, x_cls, map, m, g, D);
   const int nvec = D >> 7;
   float4 v[LN_MAX_VEC];
@@ -134,7 +136,10 @@ layernorm_bwd_kernel(const InT* __restrict__ dy, const float* __restrict__ x, co
   float4 aw[NVEC], ab[NVEC];
 #pragma unroll
   for (int i = 0; i < NVEC; ++i) aw[i] = make_float4(0.f, 0.f, 0.f, 0.f), ab[i] = aw[i];
-  for (int m = blockIdx.x * LN_WARPS + warp; m < M; m += gridDim.x * LN_WARPS) {
+  // last row first: dy was just written by a GEMM whose final tiles are still in L2, and the gather that follows reads
+  // dx from row 0 upwards -- the rows this kernel writes last
+  for (int mm = blockIdx.x * LN_WARPS + warp; mm < M; mm += gridDim.x * LN_WARPS) {
+    const int m = M - 1 - mm;
     const long long r = map_row(map, m, g);
     const bool cls = r < 0;
     const long long xr = cls ? ((-r - 1) / g.T) * (long long)g.S : r;
