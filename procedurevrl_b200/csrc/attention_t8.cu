@@ -98,8 +98,10 @@ __global__ void __launch_bounds__(T8_THREADS)
 attn_t8_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
                    int n_pairs, int seq, int H, float scale) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int pa = 2 * (blockIdx.x * (T8_THREADS / 32) + (threadIdx.x >> 5));   // n_pairs < 2^31 (checked on the host)
-  if (pa >= n_pairs) return;
+  // pairs are visited from the last to the first: the GEMM that produced qkv / dO wrote its highest rows last, and they
+  // are still in L2
+  const int pa = ((n_pairs + 1) / 2 - 1 - (blockIdx.x * (T8_THREADS / 32) + (threadIdx.x >> 5))) * 2;   // n_pairs < 2^31
+  if (pa < 0) return;
   const int pb = pa + 1;
   const bool has_b = pb < n_pairs, row_ok = g < seq;
   const int C = H * 64;
@@ -146,8 +148,10 @@ attn_t8_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
                    const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
                    __nv_bfloat16* __restrict__ dqkv, int n_pairs, int seq, int H, float scale) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int pa = 2 * (blockIdx.x * (T8_THREADS / 32) + (threadIdx.x >> 5));   // n_pairs < 2^31 (checked on the host)
-  if (pa >= n_pairs) return;
+  // pairs are visited from the last to the first: the GEMM that produced qkv / dO wrote its highest rows last, and they
+  // are still in L2
+  const int pa = ((n_pairs + 1) / 2 - 1 - (blockIdx.x * (T8_THREADS / 32) + (threadIdx.x >> 5))) * 2;   // n_pairs < 2^31
+  if (pa < 0) return;
   const int pb = pa + 1;
   const bool has_b = pb < n_pairs, row_ok = g < seq;
   const int C = H * 64;

@@ -55,7 +55,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + (bars - base) + 32);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pair = blockIdx.x, mt = blockIdx.y;
+  // grid (query tiles, pairs): the two query tiles of a (sequence, head) run back to back, so the second finds K / V in L2;
+  // last sequences first: the freshest rows of the QKV GEMM output are still in L2
+  const int pair = gridDim.y - 1 - blockIdx.y, mt = blockIdx.x;
   const int s_idx = pair / H, h = pair % H;
   const int C = H * 64;
 
@@ -234,7 +236,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 12 * TILE_BYTES + 48);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pair = blockIdx.x;
+  const int pair = gridDim.x - 1 - blockIdx.x;   // last sequences first (dO was just written by the proj dX GEMM)
   const int s_idx = pair / H, h = pair % H;
   const int C = H * 64;
   const int n_tiles = (seq + 127) / 128;   // 1 or 2 (seq <= 256)
@@ -463,7 +465,7 @@ extern "C" int pvrl_attn_tc_fwd(const void* qkv, void* out, float* lse, int32_t 
     PVRL_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  dim3 grid(n_seq * H, (seq + 127) / 128);
+  dim3 grid((seq + 127) / 128, n_seq * H);
   attn_tc_fwd_kernel<<<grid, 160, smem, static_cast<cudaStream_t>(stream)>>>(
       tq, tkv, static_cast<__nv_bfloat16*>(out), lse, seq, H, scale, npad);
   return launched("attn_tc_fwd_kernel");
