@@ -87,6 +87,10 @@ int pvrl_gemm_bf16(const pvrl_gemm_t* d, void* stream);
 /* frames fp32 [Bc,3,T,H,W] -> im2col rows (b,t,ph,pw) x K=(c,kh,kw), act dtype.  vit.py:176-179 */
 int pvrl_patchify(const float* frames, void* out, int32_t out_dtype, int32_t Bc, int32_t T, int32_t H, int32_t W,
                   int32_t patch, void* stream);
+/* The same im2col from uint8 frames [Bc,3,T,H,W] with the loader's normalisation fused (datasets/utils.py:309-326,
+ * defaults.py:510,516): value = (u8/255 - mean3[c]) / std3[c].  mean3 / std3 are HOST arrays of 3 floats. */
+int pvrl_patchify_u8(const uint8_t* frames, void* out, int32_t out_dtype, int32_t Bc, int32_t T, int32_t H, int32_t W,
+                     int32_t patch, const float* mean3, const float* std3, void* stream);
 
 /* x[b,0,:] = cls_token + pos_embed[0]  (vit.py:371-389) */
 int pvrl_cls_init(float* x, const float* cls_token, const float* pos_embed, int32_t Bc, int32_t S, int32_t D,

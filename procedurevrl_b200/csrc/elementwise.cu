@@ -61,6 +61,28 @@ __global__ void patchify_kernel(const float* __restrict__ frames, OutT* __restri
   }
 }
 
+// uint8 frames straight from the decoder (datasets/utils.py:309-326 tensor_normalize happens here instead of on the host:
+// x = (u8 / 255 - mean[c]) / std[c]); 4 pixels per thread, 4x less H2D / HBM read traffic than fp32 frames.
+template <typename OutT>
+__global__ void patchify_u8_kernel(const uint8_t* __restrict__ frames, OutT* __restrict__ out, int Bc, int T, int H, int W,
+                                   int P, long long total_vec, float3 scale, float3 shift) {
+  const int nW = W / P, nH = H / P, KP = 3 * P * P, vec_per_row = KP / 4, pv = P / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / vec_per_row;
+    const int kv = static_cast<int>(i - row * vec_per_row);
+    const int kwv = kv % pv, kh = (kv / pv) % P, c = kv / (pv * P);
+    const int pw = static_cast<int>(row % nW);
+    const int ph = static_cast<int>((row / nW) % nH);
+    const int t = static_cast<int>((row / (nW * nH)) % T);
+    const int b = static_cast<int>(row / ((long long)nW * nH * T));
+    const uint8_t* src = frames + (((long long)(b * 3 + c) * T + t) * H + (ph * P + kh)) * W + pw * P + kwv * 4;
+    const uchar4 v = *reinterpret_cast<const uchar4*>(src);
+    const float sc = c == 0 ? scale.x : (c == 1 ? scale.y : scale.z), sh = c == 0 ? shift.x : (c == 1 ? shift.y : shift.z);
+    store4<OutT>(out + row * KP + kv * 4, fmaf(v.x, sc, sh), fmaf(v.y, sc, sh), fmaf(v.z, sc, sh), fmaf(v.w, sc, sh));
+  }
+}
+
 __global__ void cls_init_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos,
                                 int S, int D) {
   const int b = blockIdx.x;
@@ -439,6 +461,24 @@ extern "C" int pvrl_patchify(const float* frames, void* out, int32_t out_dtype, 
     patchify_kernel<__nv_bfloat16>
         <<<grid, 256, 0, STREAM>>>(frames, static_cast<__nv_bfloat16*>(out), Bc, T, H, W, patch, total_vec);
   return launched("patchify_kernel");
+}
+
+extern "C" int pvrl_patchify_u8(const uint8_t* frames, void* out, int32_t out_dtype, int32_t Bc, int32_t T, int32_t H,
+                                int32_t W, int32_t patch, const float* mean3, const float* std3, void* stream) {
+  PVRL_CHECK_ARG(frames && out && mean3 && std3 && Bc > 0 && T > 0, "pvrl_patchify_u8: bad arguments");
+  PVRL_CHECK_ARG(patch % 4 == 0 && H % patch == 0 && W % patch == 0, "pvrl_patchify_u8: H=%d W=%d patch=%d", H, W, patch);
+  PVRL_CHECK_ARG(std3[0] != 0.f && std3[1] != 0.f && std3[2] != 0.f, "pvrl_patchify_u8: zero std");
+  const long long total_vec = (long long)Bc * T * (H / patch) * (W / patch) * 3 * patch * patch / 4;
+  const int grid = grid_for(total_vec, 256);
+  const float3 scale = make_float3(1.0f / (255.0f * std3[0]), 1.0f / (255.0f * std3[1]), 1.0f / (255.0f * std3[2]));
+  const float3 shift = make_float3(-mean3[0] / std3[0], -mean3[1] / std3[1], -mean3[2] / std3[2]);
+  if (out_dtype == PVRL_F32)
+    patchify_u8_kernel<float><<<grid, 256, 0, STREAM>>>(frames, static_cast<float*>(out), Bc, T, H, W, patch, total_vec,
+                                                        scale, shift);
+  else
+    patchify_u8_kernel<__nv_bfloat16><<<grid, 256, 0, STREAM>>>(frames, static_cast<__nv_bfloat16*>(out), Bc, T, H, W, patch,
+                                                                total_vec, scale, shift);
+  return launched("patchify_u8_kernel");
 }
 
 extern "C" int pvrl_cls_init(float* x, const float* cls_token, const float* pos_embed, int32_t Bc, int32_t S,

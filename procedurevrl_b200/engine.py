@@ -48,6 +48,7 @@ class EncoderEngine:
         self.use_tc_attention = True      # tcgen05 spatial attention in bf16 mode (the fp32 parity mode uses CUDA cores)
         self._wepoch = 0
         self.grad_sink = None             # optional dict name -> fp32 tensor: backward accumulates straight into it
+        self.pixel_mean, self.pixel_std = (0.45, 0.45, 0.45), (0.225, 0.225, 0.225)   # DATA.MEAN / DATA.STD (defaults.py:510,516)
         self.on_block_bwd_done = None     # optional callable(i): block i's parameter gradients are complete (bucketed all-reduce)
         self._wcache = {}      # name -> (version, W operand [N, K'], W^T operand [K, N'])
         self.grad_names = self._grad_names()
@@ -91,6 +92,13 @@ class EncoderEngine:
             ops.split3(wt32, wt, K, N, 1, 1)
         self._wcache[name] = (ver, wb, wt)
         return wb, wt
+
+    def _patchify(self, frames, A):
+        """im2col of the Conv2d patch embedding; uint8 frames are normalised inside the kernel."""
+        if frames.dtype == torch.uint8:
+            ops.patchify_u8(frames, A, self.patch, self.pixel_mean, self.pixel_std)
+        else:
+            ops.patchify(frames, A, self.patch)
 
     def refresh_weights(self):
         """Re-cast every Linear weight whose master changed, in ONE launch (bf16 mode; called at the top of forward)."""
@@ -188,7 +196,7 @@ class EncoderEngine:
         """frames fp32 [Bc, 3, T, H, W] -> (cls feature fp32 [Bc, D], saved state or None).
         drop_scales: optional list (len depth) of dicts {'temporal': [Bc*HW], 'spatial': [Bc*T], 'mlp': [Bc]}
         of DropPath factors mask/keep (vit_utils.py:140-155); None entries = identity."""
-        assert frames.dtype == torch.float32          # ops._p rejects non-CUDA tensors: there is no CPU path
+        assert frames.dtype in (torch.float32, torch.uint8)   # ops._p rejects non-CUDA tensors: there is no CPU path
         frames = frames.contiguous()
         self.refresh_weights()
         if not self.divided:
@@ -203,7 +211,7 @@ class EncoderEngine:
         KP = 3 * P * P
 
         A = self._act(Bc * T * HW, KP, dev)
-        ops.patchify(frames, A, P)
+        self._patchify(frames, A)
         x = torch.empty(Bc, S, D, device=dev, dtype=torch.float32)
         self.linear(A, self.pre + "patch_embed.proj.weight", x, Bc * T * HW, D, KP, epilogue=ops.EPI_RESID,
                     bias=self.p[self.pre + "patch_embed.proj.bias"], map=ops.MAP_PATCH, add_pos=pos, add_time=te,
@@ -429,7 +437,7 @@ def _forward_plain(self, frames, drop_scales, save):
         te = torch.zeros(1, D, **f32)                     # space_only adds no time embedding (vit.py:393)
     KP = 3 * P * P
     A = self._act(Bc * T * HW, KP, dev)
-    ops.patchify(frames, A, P)
+    self._patchify(frames, A)
     x = torch.empty(Bx, Sx, D, **f32)
     self.linear(A, self.pre + "patch_embed.proj.weight", x, Bc * T * HW, D, KP, epilogue=ops.EPI_RESID,
                 bias=self.p[self.pre + "patch_embed.proj.bias"], map=ops.MAP_PATCH, add_pos=pos, add_time=te, ldo=D, **g)

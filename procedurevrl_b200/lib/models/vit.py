@@ -239,7 +239,11 @@ class VisionTransformer(nn.Module):
         """vit.py:365-423: frames [Bc, 3, T, H, W] -> cls feature [Bc, D]."""
         Bc, _, T, H, W = x.shape
         HW = (H // self.patch_size) * (W // self.patch_size)
-        return encode(self.engine(), x.float(), self._drop_scales(Bc, T, HW, x.device))
+        # uint8 frames go to the kernels as they are (normalisation with DATA.MEAN / DATA.STD is fused into the im2col)
+        eng = self.engine()
+        if "DATA" in self.cfg:
+            eng.pixel_mean, eng.pixel_std = tuple(self.cfg.DATA.MEAN), tuple(self.cfg.DATA.STD)
+        return encode(eng, x if x.dtype == torch.uint8 else x.float(), self._drop_scales(Bc, T, HW, x.device))
 
     def check_device_norm(self, label_emb, device, norm=False):
         """vit.py:435-440 with its GPU semantics: rows are L2-normalised when the bank first reaches the device."""

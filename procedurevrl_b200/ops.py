@@ -37,6 +37,8 @@ class GemmDesc(ctypes.Structure):
 _SIGS = {
     "pvrl_gemm_bf16": [ctypes.POINTER(GemmDesc), _c_void_p],
     "pvrl_patchify": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
+    "pvrl_patchify_u8": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, ctypes.POINTER(_c_float),
+                         ctypes.POINTER(_c_float), _c_void_p],
     "pvrl_cls_init": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
     "pvrl_layernorm_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int,
                            _c_float, _c_int, Geom, _c_void_p],
@@ -168,6 +170,15 @@ def patchify(frames, out, patch=16):
     Bc, C, T, H, W = frames.shape
     assert C == 3 and frames.dtype == torch.float32 and frames.is_contiguous()
     _check(lib().pvrl_patchify(_p(frames), _p(out), _dt(out), Bc, T, H, W, patch, _stream()), "pvrl_patchify")
+    return out
+
+
+def patchify_u8(frames, out, patch, mean, std):
+    """uint8 frames [Bc, 3, T, H, W] -> normalised im2col rows (the host-side tensor_normalize fused into the kernel)."""
+    Bc, C, T, H, W = frames.shape
+    assert C == 3 and frames.dtype == torch.uint8 and frames.is_contiguous()
+    m3, s3 = (_c_float * 3)(*[float(v) for v in mean]), (_c_float * 3)(*[float(v) for v in std])
+    _check(lib().pvrl_patchify_u8(_p(frames), _p(out), _dt(out), Bc, T, H, W, patch, m3, s3, _stream()), "pvrl_patchify_u8")
     return out
 
 

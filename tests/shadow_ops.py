@@ -97,6 +97,12 @@ def patchify(frames, out, patch=16):
     return out
 
 
+def patchify_u8(frames, out, patch, mean, std):
+    m = torch.tensor(mean, dtype=torch.float32, device=frames.device).view(1, 3, 1, 1, 1)
+    s = torch.tensor(std, dtype=torch.float32, device=frames.device).view(1, 3, 1, 1, 1)
+    return patchify((frames.float() / 255.0 - m) / s, out, patch)
+
+
 def cls_init(x, cls_token, pos_embed):
     _launches[0] += 1
     x[:, 0] = cls_token.reshape(-1) + pos_embed.reshape(-1, x.shape[-1])[0]

@@ -191,3 +191,15 @@ def test_attention_type_variants(shadow, gold_dir, name):
         rn = p[k].grad.norm().item()
         assert abs(prm.grad.norm().item() - rn) <= 5e-3 * rn + 1e-7, k
         torch.testing.assert_close(prm.grad, p[k].grad, rtol=5e-3, atol=5e-3 * rn / prm.numel() ** 0.5 + 1e-7, msg=k)
+
+
+def test_uint8_frames_equal_normalised_float_frames(shadow, gold_dir):
+    """uint8 frames with the loader's normalisation (datasets/utils.py:309-326) fused into the im2col."""
+    cfg = coin_cfg(gold_dir, 2, 8, "bf16x3")
+    m = MODEL_REGISTRY.get("vit_base_patch16_224_develop")(cfg)
+    m.load_state_dict(O.seeded_state(depth=2, frames=8, seed=3), strict=True)
+    m.eval()
+    u8 = torch.randint(0, 256, (2, 3, 8, 224, 224), generator=torch.Generator().manual_seed(1), dtype=torch.uint8)
+    xf = (u8.float() / 255.0 - 0.45) / 0.225
+    with torch.no_grad():
+        torch.testing.assert_close(m(u8), m(xf), rtol=1e-4, atol=1e-6)

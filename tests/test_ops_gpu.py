@@ -489,3 +489,16 @@ def test_order_levels_vs_torch_modules(ops):
     for n, p in m.named_parameters():
         if p.grad is not None:
             _close("order grad " + n, got[n], p.grad, 2e-3)
+
+
+def test_patchify_u8(ops):
+    """uint8 frames + fused normalisation == patchify of the normalised fp32 frames."""
+    u8 = torch.randint(0, 256, (2, 3, 4, 64, 96), device="cuda", dtype=torch.uint8)
+    mean, std = (0.45, 0.40, 0.50), (0.225, 0.2, 0.25)
+    xf = (u8.float() / 255.0 - torch.tensor(mean, device="cuda").view(1, 3, 1, 1, 1)) / torch.tensor(std, device="cuda").view(1, 3, 1, 1, 1)
+    rows, KP = 2 * 4 * 4 * 6, 768
+    for dt, tol in ((torch.float32, 1e-5), (torch.bfloat16, 1e-2)):
+        a, b = torch.empty(rows, KP, device="cuda", dtype=dt), torch.empty(rows, KP, device="cuda", dtype=dt)
+        ops.patchify_u8(u8, a, 16, mean, std)
+        ops.patchify(xf.contiguous(), b, 16)
+        assert _report(f"patchify_u8 {dt}", a, b)[1] < tol
