@@ -97,6 +97,8 @@ __device__ __forceinline__ void pair_apply(uint32_t wa, uint32_t wb, const Row16
 __global__ void __launch_bounds__(T8_THREADS)
 attn_t8_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
                    int n_pairs, int seq, int H, float scale) {
+  if (PDL_EARLY_TRIGGER) pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   // pairs are visited from the last to the first: the GEMM that produced qkv / dO wrote its highest rows last, and they
   // are still in L2
@@ -147,6 +149,8 @@ __global__ void __launch_bounds__(T8_THREADS)
 attn_t8_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
                    const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
                    __nv_bfloat16* __restrict__ dqkv, int n_pairs, int seq, int H, float scale) {
+  if (PDL_EARLY_TRIGGER) pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   // pairs are visited from the last to the first: the GEMM that produced qkv / dO wrote its highest rows last, and they
   // are still in L2
@@ -207,8 +211,8 @@ int attn_t8_fwd_launch(const void* qkv, void* out, float* lse, int n_seq, int se
   const int n_pairs = n_seq * H;
   const int warps = (n_pairs + 1) / 2;
   const unsigned grid = static_cast<unsigned>((warps + T8_THREADS / 32 - 1) / (T8_THREADS / 32));
-  attn_t8_fwd_kernel<<<grid, T8_THREADS, 0, stream>>>(static_cast<const __nv_bfloat16*>(qkv),
-                                                      static_cast<__nv_bfloat16*>(out), lse, n_pairs, seq, H, scale);
+  PVRL_CUDA(launch_pdl(attn_t8_fwd_kernel, dim3(grid), dim3(T8_THREADS), 0, stream, static_cast<const __nv_bfloat16*>(qkv),
+                       static_cast<__nv_bfloat16*>(out), lse, n_pairs, seq, H, scale));
   return launched("attn_t8_fwd_kernel");
 }
 
@@ -218,9 +222,10 @@ int attn_t8_bwd_launch(const void* qkv, const void* out, const void* dout, const
   const int n_pairs = n_seq * H;
   const int warps = (n_pairs + 1) / 2;
   const unsigned grid = static_cast<unsigned>((warps + T8_THREADS / 32 - 1) / (T8_THREADS / 32));
-  attn_t8_bwd_kernel<<<grid, T8_THREADS, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(out),
-      static_cast<const __nv_bfloat16*>(dout), lse, static_cast<__nv_bfloat16*>(dqkv), n_pairs, seq, H, scale);
+  PVRL_CUDA(launch_pdl(attn_t8_bwd_kernel, dim3(grid), dim3(T8_THREADS), 0, stream,
+                       static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(out),
+                       static_cast<const __nv_bfloat16*>(dout), lse, static_cast<__nv_bfloat16*>(dqkv), n_pairs, seq, H,
+                       scale));
   return launched("attn_t8_bwd_kernel");
 }
 

@@ -78,6 +78,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (PDL_EARLY_TRIGGER) pdl_launch_dependents();
+  pdl_wait();   // barrier init / TMEM allocation above overlapped the previous kernel's tail
 
   if (warp == 4) {
     if (lane == 0) {
@@ -261,6 +263,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (PDL_EARLY_TRIGGER) pdl_launch_dependents();
+  pdl_wait();   // barrier init / TMEM allocation above overlapped the previous kernel's tail
   constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DK = 256, COL_DV = 320, COL_DQ = 384;
 
   if (warp == 8) {
@@ -466,8 +470,8 @@ extern "C" int pvrl_attn_tc_fwd(const void* qkv, void* out, float* lse, int32_t 
     configured = true;
   }
   dim3 grid((seq + 127) / 128, n_seq * H);
-  attn_tc_fwd_kernel<<<grid, 160, smem, static_cast<cudaStream_t>(stream)>>>(
-      tq, tkv, static_cast<__nv_bfloat16*>(out), lse, seq, H, scale, npad);
+  PVRL_CUDA(launch_pdl(attn_tc_fwd_kernel, grid, dim3(160), smem, static_cast<cudaStream_t>(stream), tq, tkv,
+                       static_cast<__nv_bfloat16*>(out), lse, seq, H, scale, npad));
   return launched("attn_tc_fwd_kernel");
 }
 
@@ -486,7 +490,7 @@ extern "C" int pvrl_attn_tc_bwd(const void* qkv, const void* out, const void* do
     PVRL_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  attn_tc_bwd_kernel<<<n_seq * H, BWD_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
-      tqkv, tdo, to, lse, static_cast<__nv_bfloat16*>(dqkv), seq, H, scale);
+  PVRL_CUDA(launch_pdl(attn_tc_bwd_kernel, dim3(n_seq * H), dim3(BWD_THREADS), smem, static_cast<cudaStream_t>(stream), tqkv,
+                       tdo, to, lse, static_cast<__nv_bfloat16*>(dqkv), seq, H, scale));
   return launched("attn_tc_bwd_kernel");
 }

@@ -106,6 +106,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ x_cls, const float* __restrict__ w,
                      const float* __restrict__ b, OutT* __restrict__ y, float* __restrict__ stats, int M, int D,
                      float eps, int map, Geom g) {
+  if (PDL_EARLY_TRIGGER) pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   // Rows are visited from the LAST to the first: the GEMM epilogue that produced x wrote its highest rows last (they are
   // still in the 126 MB L2), and the GEMM that consumes y starts at row 0 -- which this kernel therefore writes last.
@@ -150,6 +152,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NVEC <= 4 ? 2 : 1)
 layernorm_bwd_kernel(const InT* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ x_cls,
                      const float* __restrict__ w, const float* __restrict__ stats, float* __restrict__ dx,
                      float* __restrict__ dw, float* __restrict__ db, int M, int map, Geom g) {
+  if (PDL_EARLY_TRIGGER) pdl_launch_dependents();
+  pdl_wait();
   constexpr int D = NVEC * 128;
   __shared__ float sacc[2 * D];
   for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sacc[i] = 0.f;
@@ -224,10 +228,10 @@ int layernorm_bwd_launch(const void* dy, const float* x, const float* x_cls, con
   if (grid > 148 * 2) grid = 148 * 2;   // persistent row loop; 1-2 blocks are resident per SM (register-bound)
   const InT* d = static_cast<const InT*>(dy);
   switch (D / 128) {
-    case 2: layernorm_bwd_kernel<InT, 2><<<grid, LN_WARPS * 32, 0, stream>>>(d, x, x_cls, w, stats, dx, dw, db, M, map, gg); break;
-    case 4: layernorm_bwd_kernel<InT, 4><<<grid, LN_WARPS * 32, 0, stream>>>(d, x, x_cls, w, stats, dx, dw, db, M, map, gg); break;
-    case 6: layernorm_bwd_kernel<InT, 6><<<grid, LN_WARPS * 32, 0, stream>>>(d, x, x_cls, w, stats, dx, dw, db, M, map, gg); break;
-    case 8: layernorm_bwd_kernel<InT, 8><<<grid, LN_WARPS * 32, 0, stream>>>(d, x, x_cls, w, stats, dx, dw, db, M, map, gg); break;
+    case 2: launch_pdl(layernorm_bwd_kernel<InT, 2>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, d, x, x_cls, w, stats, dx, dw, db, M, map, gg); break;
+    case 4: launch_pdl(layernorm_bwd_kernel<InT, 4>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, d, x, x_cls, w, stats, dx, dw, db, M, map, gg); break;
+    case 6: launch_pdl(layernorm_bwd_kernel<InT, 6>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, d, x, x_cls, w, stats, dx, dw, db, M, map, gg); break;
+    case 8: launch_pdl(layernorm_bwd_kernel<InT, 8>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, d, x, x_cls, w, stats, dx, dw, db, M, map, gg); break;
     default: return fail(-1, "pvrl_layernorm_bwd: D=%d not in {256, 512, 768, 1024}", D);
   }
   return launched("layernorm_bwd_kernel");
@@ -242,6 +246,8 @@ template <typename OutT, int NVEC>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 gather_cast_kernel(const float* __restrict__ src, OutT* __restrict__ out, const float* __restrict__ rowscale, int rs_div,
                    int M, int map, Geom g, float* __restrict__ colsum) {
+  if (PDL_EARLY_TRIGGER) pdl_launch_dependents();
+  pdl_wait();
   constexpr int D = NVEC * 128;
   __shared__ float sacc[D];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -286,10 +292,10 @@ int gather_cast_launch(const float* src, void* out, const float* rowscale, int r
   if (grid > 148 * 6) grid = 148 * 6;
   OutT* o = static_cast<OutT*>(out);
   switch (D / 128) {
-    case 2: gather_cast_kernel<OutT, 2><<<grid, LN_WARPS * 32, 0, stream>>>(src, o, rowscale, rs_div, M, map, gg, colsum); break;
-    case 4: gather_cast_kernel<OutT, 4><<<grid, LN_WARPS * 32, 0, stream>>>(src, o, rowscale, rs_div, M, map, gg, colsum); break;
-    case 6: gather_cast_kernel<OutT, 6><<<grid, LN_WARPS * 32, 0, stream>>>(src, o, rowscale, rs_div, M, map, gg, colsum); break;
-    case 8: gather_cast_kernel<OutT, 8><<<grid, LN_WARPS * 32, 0, stream>>>(src, o, rowscale, rs_div, M, map, gg, colsum); break;
+    case 2: launch_pdl(gather_cast_kernel<OutT, 2>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, src, o, rowscale, rs_div, M, map, gg, colsum); break;
+    case 4: launch_pdl(gather_cast_kernel<OutT, 4>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, src, o, rowscale, rs_div, M, map, gg, colsum); break;
+    case 6: launch_pdl(gather_cast_kernel<OutT, 6>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, src, o, rowscale, rs_div, M, map, gg, colsum); break;
+    case 8: launch_pdl(gather_cast_kernel<OutT, 8>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, src, o, rowscale, rs_div, M, map, gg, colsum); break;
     default: return fail(-1, "pvrl_gather_cast: D=%d not in {256, 512, 768, 1024}", D);
   }
   return launched("gather_cast_kernel");
@@ -297,6 +303,8 @@ int gather_cast_launch(const float* src, void* out, const float* rowscale, int r
 
 __global__ void cls_merge_kernel(const float* __restrict__ x0, const float* __restrict__ side, float* __restrict__ x2,
                                  int T, int S, int D) {
+  if (PDL_EARLY_TRIGGER) pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float s = 0.f;
@@ -309,6 +317,8 @@ __global__ void cls_merge_kernel(const float* __restrict__ x0, const float* __re
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ a, long long lda, float* __restrict__ out, int M, int N,
                               int rows_per_block) {
+  if (PDL_EARLY_TRIGGER) pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[8][128];
   const int col = blockIdx.x * 128 + threadIdx.x * 4;  // blockDim = (32, 8)
   const int r0 = blockIdx.y * rows_per_block;
@@ -497,11 +507,11 @@ extern "C" int pvrl_layernorm_fwd(const float* x, const float* x_cls, const floa
   const Geom gg(g.T > 0 ? g.T : 1, g.HW > 0 ? g.HW : 1);
   const int grid = (M + LN_WARPS - 1) / LN_WARPS;
   if (y_dtype == PVRL_F32)
-    layernorm_fwd_kernel<float>
-        <<<grid, LN_WARPS * 32, 0, STREAM>>>(x, x_cls, w, b, static_cast<float*>(y), stats, M, D, eps, map, gg);
+    launch_pdl(layernorm_fwd_kernel<float>, dim3(grid), dim3(LN_WARPS * 32), 0, STREAM, x, x_cls, w, b,
+               static_cast<float*>(y), stats, M, D, eps, map, gg);
   else
-    layernorm_fwd_kernel<__nv_bfloat16><<<grid, LN_WARPS * 32, 0, STREAM>>>(
-        x, x_cls, w, b, static_cast<__nv_bfloat16*>(y), stats, M, D, eps, map, gg);
+    launch_pdl(layernorm_fwd_kernel<__nv_bfloat16>, dim3(grid), dim3(LN_WARPS * 32), 0, STREAM, x, x_cls, w, b,
+               static_cast<__nv_bfloat16*>(y), stats, M, D, eps, map, gg);
   return launched("layernorm_fwd_kernel");
 }
 
@@ -530,7 +540,7 @@ extern "C" int pvrl_gather_cast(const float* src, void* out, int32_t out_dtype, 
 extern "C" int pvrl_cls_merge(const float* x0, const float* side, float* x2, int32_t Bc, int32_t T, int32_t S,
                               int32_t D, void* stream) {
   PVRL_CHECK_ARG(x0 && side && x2 && Bc > 0 && T > 0, "pvrl_cls_merge: bad arguments");
-  cls_merge_kernel<<<Bc, 256, 0, STREAM>>>(x0, side, x2, T, S, D);
+  launch_pdl(cls_merge_kernel, dim3(Bc), dim3(256), 0, STREAM, x0, side, x2, T, S, D);
   return launched("cls_merge_kernel");
 }
 
@@ -540,10 +550,11 @@ extern "C" int pvrl_colsum(const void* a, int32_t a_dtype, int64_t lda, float* o
   const int rows_per_block = 256;
   dim3 grid((N + 127) / 128, (M + rows_per_block - 1) / rows_per_block), block(32, 8);
   if (a_dtype == PVRL_F32)
-    colsum_kernel<float><<<grid, block, 0, STREAM>>>(static_cast<const float*>(a), lda, out, M, N, rows_per_block);
+    launch_pdl(colsum_kernel<float>, grid, block, 0, STREAM, static_cast<const float*>(a), (long long)lda, out, M, N,
+               rows_per_block);
   else
-    colsum_kernel<__nv_bfloat16>
-        <<<grid, block, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(a), lda, out, M, N, rows_per_block);
+    launch_pdl(colsum_kernel<__nv_bfloat16>, grid, block, 0, STREAM, static_cast<const __nv_bfloat16*>(a), (long long)lda,
+               out, M, N, rows_per_block);
   return launched("colsum_kernel");
 }
 

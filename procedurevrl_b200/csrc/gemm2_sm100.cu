@@ -128,6 +128,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / TMA completion can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (PDL_EARLY_TRIGGER) pdl_launch_dependents();
+  pdl_wait();   // the set-up above overlapped the tail of the previous kernel
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs, own halves)
@@ -265,7 +267,7 @@ int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a
   const int total = m_tiles * n_tiles * a.k_splits;
   const int cap = g_pairs_override > 0 ? g_pairs_override : pairs_max;
   const int clusters = total < cap ? total : cap;
-  kern<<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(ta, tb, a);
+  PVRL_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(NUM_THREADS), SMEM2_BYTES, stream, ta, tb, a));
   return launched("gemm2_bf16_kernel");
 }
 

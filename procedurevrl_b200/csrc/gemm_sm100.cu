@@ -79,6 +79,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (PDL_EARLY_TRIGGER) pdl_launch_dependents();
+  pdl_wait();   // everything above overlapped the tail of the previous kernel; from here on its outputs are read
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -267,7 +269,7 @@ int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs&
   const int m_tiles = (a.M + BM - 1) / BM, n_tiles = (a.N + BN - 1) / BN;
   const int total = m_tiles * n_tiles * a.k_splits;
   const int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, Cfg<BN, EW>::THREADS, SMEM_BYTES, stream>>>(ta, tb, a);
+  PVRL_CUDA(launch_pdl(kern, dim3(grid), dim3(Cfg<BN, EW>::THREADS), SMEM_BYTES, stream, ta, tb, a));
   return launched("gemm_bf16_kernel");
 }
 

@@ -7,6 +7,8 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <utility>
 
 #include "../../include/pvrl.h"
 
@@ -41,6 +43,32 @@ inline int launched(const char* what) {
     cudaError_t e__ = (expr);                                                                   \
     if (e__ != cudaSuccess) return ::pvrl::fail(static_cast<int>(e__), "%s: %s", #expr, cudaGetErrorString(e__)); \
   } while (0)
+
+// Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream is still draining (its
+// CTAs take SMs as the predecessor's CTAs exit, run their prologue -- barrier init, TMEM allocation, descriptor prefetch --
+// and then block in griddepcontrol.wait until the predecessor has completed and flushed).  Every kernel launched through
+// this helper calls pdl_wait() before its first dependent global access.
+// Measured on the 18-clip step (profiles/README.md): with every kernel releasing its dependents at its start the step got
+// 6 % SLOWER (35.0 vs 32.9 ms), with the implicit trigger at grid completion it is neutral (33.1 vs 33.1 ms) -- the
+// kernels here are long enough that launch latency is already hidden by the CUDA graph.  So it is opt-in: PVRL_PDL=1.
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("PVRL_PDL");
+    return e != nullptr && atoi(e) != 0;
+  }();
+  return on;
+}
+template <typename Kern, typename... Args>
+inline cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

@@ -49,6 +49,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// programmatic dependent launch (see launch_pdl in pvrl_host.h); both are no-ops for a kernel launched without the attribute
+#ifndef PDL_EARLY_TRIGGER
+#define PDL_EARLY_TRIGGER 0   // 1: every kernel releases its dependents at its start (measured slower: see DESIGN.md)
+#endif
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
