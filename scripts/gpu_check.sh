@@ -1,0 +1,12 @@
+# What the round-end driver runs on a B200 box, plus the profiling captures kept under profiles/ (see profiles/README.md).
+#   gpurun --timeout 2400 -- 'bash scripts/gpu_check.sh'
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 400 python bench.py > gpurun_out/bench.log 2>&1; tail -n 1 gpurun_out/bench.log
+timeout 400 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.log 2>&1; tail -n 1 gpurun_out/bench_ref.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none --csv --log-file gpurun_out/launches.csv python bench.py --profile --steps 1 > gpurun_out/ncu_launch.log 2>&1
+timeout 600 ncu --set full --clock-control none -k regex:gemm -s 300 -c 14 --csv --page raw --log-file gpurun_out/prof_gemm_raw.csv python bench.py --profile --steps 1 > gpurun_out/ncu_gemm.log 2>&1
+python scripts/summarize_launches.py gpurun_out/launches.csv | head -30
+python scripts/summarize_ncu_raw.py gpurun_out/prof_gemm_raw.csv | cut -c1-200
