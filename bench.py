@@ -233,12 +233,33 @@ def run_b200(args):
     gemm_flops = sum(f for _, _, f in gemm_events)
     n_gemm = len(gemm_events)
 
-    # end to end: pinned host frames -> device every step, loss read back every step
+    # end to end: pinned host frames -> device every step, loss read back (a host sync) every step.  As in the reference's
+    # loop (non_blocking .cuda() copies of a pinned DataLoader batch, train_net.py:103-107) the H2D copy of step i+1 is
+    # issued on a copy stream while step i computes; each step's input still crosses PCIe inside the timed region
+    # (exactly `steps` copies), and the step consumes it through a device-to-device copy into the graph's static input.
     barrier()
+    n_e2e = 0 if args.profile else args.steps
+    copy_stream = torch.cuda.Stream()
+    stage = torch.empty_like(frames)
+    staged, consumed = torch.cuda.Event(), torch.cuda.Event()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(0 if args.profile else args.steps):
-        frames.copy_(frames_pin, non_blocking=True)
+
+    def issue_h2d():
+        copy_stream.wait_event(consumed)                     # the previous step has read the staging buffer
+        with torch.cuda.stream(copy_stream):
+            stage.copy_(frames_pin, non_blocking=True)
+            staged.record(copy_stream)
+
+    consumed.record()
+    if n_e2e:
+        issue_h2d()
+    for i in range(n_e2e):
+        torch.cuda.current_stream().wait_event(staged)
+        frames.copy_(stage, non_blocking=True)
+        consumed.record()
+        if i + 1 < n_e2e:
+            issue_h2d()
         last = step(frames).item()
     if args.profile:
         last = loss.item()
