@@ -125,7 +125,8 @@ int pvrl_cast_weight(const float* w, void* w_out, void* wT_out, int32_t out_dtyp
                      void* stream);
 
 /* The same for many matrices in one launch.  descs_dev: DEVICE array of n descriptors sorted by tile0, where matrix i
- * owns the 32x32 tiles [tile0, tile0 + tiles_x * ceil(rows/32)), tiles_x = ceil(cols/32); out / outT may be NULL. */
+ * owns the 64x64 tiles [tile0, tile0 + tiles_x * ceil(rows/64)), tiles_x = ceil(cols/64); rows and cols must be even;
+ * out / outT may be NULL. */
 typedef struct pvrl_cast_desc {
   const float* w;
   void* out;

@@ -369,8 +369,22 @@ __global__ void cast_weight_kernel(const float* __restrict__ w, OutT* __restrict
 // All weights of the model in ONE launch (85 cast_weight launches per optimizer step otherwise): the descriptor table
 // lives in device memory, a block finds its matrix by binary search over the tile offsets.
 template <typename OutT>
-__global__ void cast_weight_multi_kernel(const pvrl_cast_desc_t* __restrict__ descs, int n) {
-  __shared__ float tile[32][33];
+__device__ __forceinline__ void st_pair(OutT* dst, float a, float b);
+template <>
+__device__ __forceinline__ void st_pair<float>(float* dst, float a, float b) {
+  *reinterpret_cast<float2*>(dst) = make_float2(a, b);
+}
+template <>
+__device__ __forceinline__ void st_pair<__nv_bfloat16>(__nv_bfloat16* dst, float a, float b) {
+  *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(a, b);
+}
+
+// 64 x 64 tiles, two elements per thread: every global access of the copy AND of the transposed copy is a full
+// 128-byte (bf16) row segment per warp.  rows and cols must be even (all Linear weights here are multiples of 64).
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+cast_weight_multi_kernel(const pvrl_cast_desc_t* __restrict__ descs, int n) {
+  __shared__ float tile[64][65];
   int lo = 0, hi = n - 1;
   while (lo < hi) {   // last descriptor with tile0 <= blockIdx.x
     const int mid = (lo + hi + 1) >> 1;
@@ -384,22 +398,23 @@ __global__ void cast_weight_multi_kernel(const pvrl_cast_desc_t* __restrict__ de
   OutT* o = static_cast<OutT*>(d.out);
   OutT* oT = static_cast<OutT*>(d.outT);
   const int rows = d.rows, cols = d.cols;
-  const int c = bx * 32 + threadIdx.x;
-  for (int j = threadIdx.y; j < 32; j += 8) {
-    const int r = by * 32 + j;
-    float v = 0.f;
+  const int c = bx * 64 + threadIdx.x * 2;
+  for (int j = threadIdx.y; j < 64; j += 8) {
+    const int r = by * 64 + j;
+    float2 v = make_float2(0.f, 0.f);
     if (r < rows && c < cols) {
-      v = w[(long long)r * cols + c];
-      if (o != nullptr) o[(long long)r * cols + c] = static_cast<OutT>(v);
+      v = *reinterpret_cast<const float2*>(w + (long long)r * cols + c);
+      if (o != nullptr) st_pair<OutT>(o + (long long)r * cols + c, v.x, v.y);
     }
-    tile[j][threadIdx.x] = v;
+    tile[j][threadIdx.x * 2] = v.x, tile[j][threadIdx.x * 2 + 1] = v.y;
   }
   __syncthreads();
   if (oT != nullptr) {
-    const int r = by * 32 + threadIdx.x;
-    for (int j = threadIdx.y; j < 32; j += 8) {
-      const int cc = bx * 32 + j;
-      if (r < rows && cc < cols) oT[(long long)cc * rows + r] = static_cast<OutT>(tile[threadIdx.x][j]);
+    const int r = by * 64 + threadIdx.x * 2;   // original rows (2 per thread) -> fast index of the transposed output
+    for (int j = threadIdx.y; j < 64; j += 8) {
+      const int cc = bx * 64 + j;
+      if (r < rows && cc < cols)
+        st_pair<OutT>(oT + (long long)cc * rows + r, tile[threadIdx.x * 2][j], tile[threadIdx.x * 2 + 1][j]);
     }
   }
 }
@@ -573,7 +588,7 @@ extern "C" int pvrl_cast_weight(const float* w, void* w_out, void* wT_out, int32
 
 extern "C" int pvrl_cast_weight_multi(const pvrl_cast_desc_t* descs_dev, int32_t n, int32_t total_tiles,
                                       int32_t out_dtype, void* stream) {
-  PVRL_CHECK_ARG(descs_dev && n > 0 && total_tiles > 0, "pvrl_cast_weight_multi: bad arguments");
+  PVRL_CHECK_ARG(descs_dev && n > 0 && total_tiles > 0, "pvrl_cast_weight_multi: bad arguments");   // 64 x 64 tiles
   dim3 block(32, 8);
   if (out_dtype == PVRL_F32)
     cast_weight_multi_kernel<float><<<total_tiles, block, 0, STREAM>>>(descs_dev, n);

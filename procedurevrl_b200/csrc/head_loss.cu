@@ -140,10 +140,16 @@ __global__ void sim_logits_bwd_kernel(const float* __restrict__ dlogits, const f
       float acc[SIMB_MT];
 #pragma unroll
       for (int mm = 0; mm < SIMB_MT; ++mm) acc[mm] = 0.f;
-      for (int cc = 0; cc < nc; ++cc) {
-        const float l = __ldg(label + (long long)(c0 + cc) * K + k);
+      for (int cc = 0; cc < nc; cc += 8) {   // 8 bank rows in flight per thread: the loop is bound by L2 latency, not FMAs
+        float l[8];
 #pragma unroll
-        for (int mm = 0; mm < SIMB_MT; ++mm) acc[mm] = fmaf(sdl[mm][cc], l, acc[mm]);
+        for (int u = 0; u < 8; ++u) l[u] = cc + u < nc ? __ldg(label + (long long)(c0 + cc + u) * K + k) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int cu = min(cc + u, SIMB_CH - 1);
+#pragma unroll
+          for (int mm = 0; mm < SIMB_MT; ++mm) acc[mm] = fmaf(sdl[mm][cu], l[u], acc[mm]);
+        }
       }
 #pragma unroll
       for (int mm = 0; mm < SIMB_MT; ++mm)

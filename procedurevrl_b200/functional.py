@@ -9,6 +9,12 @@ def _f32(t):
     return t.contiguous().float() if (t.dtype != torch.float32 or not t.is_contiguous()) else t
 
 
+def _few_rows_ok(x, w):
+    """shapes the `pvrl_ot_linear_*` few-row kernels take (they run the 18-26 row head ~10x faster than the generic
+    small-linear kernels): contraction a multiple of 128 up to 2048, output width a multiple of 4."""
+    return x.shape[1] % 128 == 0 and x.shape[1] <= 2048 and w.shape[0] % 4 == 0
+
+
 class _LinearSmall(torch.autograd.Function):
     """y = x @ w.t() + b for a handful of rows: `head` 768->512 (vit.py:301), `head_cls` (vit.py:321)."""
 
@@ -16,7 +22,10 @@ class _LinearSmall(torch.autograd.Function):
     def forward(ctx, x, w, b):
         x, w = _f32(x), _f32(w)
         y = torch.empty(x.shape[0], w.shape[0], device=x.device, dtype=torch.float32)
-        ops.linear_small_fwd(x, w, b, y)
+        if _few_rows_ok(x, w):
+            ops.ot_linear_fwd(x, w, None if b is None else _f32(b), y)
+        else:
+            ops.linear_small_fwd(x, w, b, y)
         ctx.save_for_backward(x, w)
         ctx.has_b = b is not None
         return y
@@ -29,7 +38,13 @@ class _LinearSmall(torch.autograd.Function):
         dx = torch.empty_like(x) if need_x else None
         dw = torch.zeros_like(w) if need_w else None
         db = torch.zeros(w.shape[0], device=w.device) if (need_w and ctx.has_b) else None
-        ops.linear_small_bwd(x, w, dy, dx, dw, db)
+        if _few_rows_ok(x, w):
+            if need_x:
+                ops.ot_linear_dx(dy, w, dx)
+            if need_w:
+                ops.ot_linear_dw(dy, x, dw, db)
+        else:
+            ops.linear_small_bwd(x, w, dy, dx, dw, db)
         if not (ctx.has_b and ctx.needs_input_grad[2]):
             db = None
         return dx, dw, db

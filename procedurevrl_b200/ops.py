@@ -229,9 +229,10 @@ def cast_weight_table(triples):
     t0 = 0
     for i, (w, o, oT) in enumerate(triples):
         rows, cols = w.shape
-        tx = (cols + 31) // 32
+        assert rows % 2 == 0 and cols % 2 == 0, "cast_weight_multi moves element pairs"
+        tx = (cols + 63) // 64
         arr[i] = CastDesc(_p(w), _p(o), _p(oT), rows, cols, t0, tx)
-        t0 += tx * ((rows + 31) // 32)
+        t0 += tx * ((rows + 63) // 64)
     raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(triples[0][0].device)
     return raw, len(triples), t0, _dt(triples[0][1] if triples[0][1] is not None else triples[0][2])
 

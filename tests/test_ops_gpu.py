@@ -502,3 +502,16 @@ def test_patchify_u8(ops):
         ops.patchify_u8(u8, a, 16, mean, std)
         ops.patchify(xf.contiguous(), b, 16)
         assert _report(f"patchify_u8 {dt}", a, b)[1] < tol
+
+
+def test_cast_weight_multi(ops):
+    """All Linear weights of a model in one launch: bf16 copy and transposed bf16 copy of every matrix."""
+    shapes = [(768, 768), (2304, 768), (768, 3072), (130, 66), (64, 64)]
+    ws = [_rand(r, c, seed=i) for i, (r, c) in enumerate(shapes)]
+    outs = [(torch.zeros(r, c, device="cuda", dtype=torch.bfloat16), torch.zeros(c, r, device="cuda", dtype=torch.bfloat16))
+            for r, c in shapes]
+    table = ops.cast_weight_table([(w, o, oT) for w, (o, oT) in zip(ws, outs)])
+    ops.cast_weight_multi(table)
+    for w, (o, oT) in zip(ws, outs):
+        assert torch.equal(o, w.bfloat16())
+        assert torch.equal(oT, w.t().contiguous().bfloat16())
