@@ -226,6 +226,27 @@ int pvrl_ot_embed_fwd(const float* video, const float* src, const float* noise, 
 int pvrl_ot_embed_bwd(const float* dh, const int64_t* mask_inds, const int64_t* pad_start, float* dvideo, float* dtype,
                       float* dpos, float* dpad, float* dtvec, int32_t B, int32_t S, int32_t C, void* stream);
 
+/* ---- optimizer step over flat buffers ------------------------------------------------------ */
+/* Replaces torch.optim.AdamW / Adam / SGD as constructed by lib/models/optimizer.py:90-114 and the
+ * optimizer.step(); optimizer.zero_grad() pair of tools/train_net.py:176-192.  One call per parameter group
+ * (optimizer.py:35-84: weight decay and lr multiplier differ per group); p, g and the state arrays are the group's
+ * slices of flat fp32 buffers laid out identically (same offset from a 16-byte boundary).
+ * lr_dev / step_dev are DEVICE scalars: the learning rate of this iteration (lr_policy.get_lr_at_epoch, set_lr) and
+ * the number of the step being taken (1 for the first), so a CUDA graph of the step can be replayed unchanged;
+ * pvrl_optim_tick increments the counter once per step, before the group calls.
+ * g is multiplied by grad_scale before use (1/world after a SUM all-reduce, 1/micro-steps under accumulation) and,
+ * with zero_grad != 0, cleared for the next backward (whose dW kernels accumulate). */
+int pvrl_optim_tick(float* step_dev, void* stream);
+/* decoupled != 0: AdamW (p *= 1 - lr*wd); decoupled == 0: Adam with the L2 term added to the gradient. */
+int pvrl_adam_flat(float* p, float* g, float* m, float* v, int64_t n, const float* lr_dev, const float* step_dev,
+                   float lr_mult, float beta1, float beta2, float eps, float weight_decay, int32_t decoupled,
+                   float grad_scale, int32_t zero_grad, void* stream);
+/* torch.optim.SGD semantics: g += wd*p; buf = g on step 1 else momentum*buf + (1-dampening)*g;
+ * update = g + momentum*buf (nesterov) or buf; p -= lr*update.  momentum == 0 ignores buf's contents. */
+int pvrl_sgd_flat(float* p, float* g, float* buf, int64_t n, const float* lr_dev, const float* step_dev, float lr_mult,
+                  float momentum, float dampening, int32_t nesterov, float weight_decay, float grad_scale,
+                  int32_t zero_grad, void* stream);
+
 /* ---- misc ----------------------------------------------------------------------------------------------- */
 const char* pvrl_last_error(void);
 int pvrl_abi_version(void);

@@ -1,6 +1,6 @@
 """Config tree with the reference's keys and defaults for everything the hot path reads
 (reference lib/config/defaults.py:40-65 DEV.*, :73-106 TRAIN.*, :383-440 MODEL.*, :463-466 TIMESFORMER.*,
-:504-525 DATA.*, :634-659 NUM_GPUS/NUM_SHARDS/RNG_SEED/DIST_BACKEND/GLOBAL_BATCH_SIZE).
+:504-525 DATA.*, :14-23 BN.*, :576-627 SOLVER.*, :634-659 NUM_GPUS/NUM_SHARDS/RNG_SEED/DIST_BACKEND/GLOBAL_BATCH_SIZE).
 
 The reference uses fvcore/yacs `CfgNode`; neither is a dependency here, so `CfgNode` below is a small
 attribute-dict with the same `merge_from_file / merge_from_list / clone / dump` calls.  Unknown keys found in
@@ -85,7 +85,12 @@ _DEFAULTS = {
         "ORDER_FIX_RECOGNITION": False, "ORDER_STRIDE": 2, "ORDER_TFM_LAYERS": 4, "ORDER_RECOG_BATCH": 9,
     },
     "TRAIN": {"ENABLE": True, "DATASET": "kinetics", "LABEL_EMB": "", "LINEAR": False, "TEXT": "", "TOPK": 5,
-              "BATCH_SIZE": 64},
+              "BATCH_SIZE": 64, "MULT": 1.0},
+    "BN": {"WEIGHT_DECAY": 0.0},
+    "SOLVER": {"BASE_LR": 0.1, "LR_POLICY": "cosine", "COSINE_END_LR": 0.0, "GAMMA": 0.1, "STEP_SIZE": 1, "STEPS": [],
+               "LRS": [], "MAX_EPOCH": 300, "MOMENTUM": 0.9, "DAMPENING": 0.0, "NESTEROV": True, "WEIGHT_DECAY": 1e-4,
+               "WARMUP_FACTOR": 0.1, "WARMUP_EPOCHS": 0.0, "WARMUP_START_LR": 0.01, "OPTIMIZING_METHOD": "sgd",
+               "BASE_LR_SCALE_NUM_SHARDS": False},
     "TEST": {"ENABLE": True, "DATASET": "kinetics", "BATCH_SIZE": 8},
     "MODEL": {"ARCH": "slowfast", "MODEL_NAME": "SlowFast", "NUM_CLASSES": 400, "LOSS_FUNC": "cross_entropy",
               "DROPOUT_RATE": 0.5, "PRETRAINED": True, "MLP": 0, "TEXT_MODEL": "", "TEXT_LP": False, "NUM_SEG": 0,

@@ -1,0 +1,297 @@
+"""Optimizer boundary (reference lib/models/optimizer.py:10-140, lib/utils/lr_policy.py:8-94).
+
+`construct_optimizer(model, cfg)` keeps the reference's parameter grouping (names containing "bn" / "text_model" /
+"head" / "order", TRAIN.LINEAR freezing, TRAIN.MULT learning-rate multipliers, BN.WEIGHT_DECAY vs SOLVER.WEIGHT_DECAY)
+and its SOLVER.OPTIMIZING_METHOD switch (sgd | adam | adamw), but returns a `FlatOptimizer`: parameters, gradients
+and optimizer state of all groups live in flat fp32 buffers (every `p.data` / `p.grad` is a view), and `step()` is ONE
+`pvrl_adam_flat` / `pvrl_sgd_flat` launch per group (csrc/optim.cu) instead of torch's multi-tensor-apply chain.
+Learning rate and step count are device scalars, so the step can sit inside a replayed CUDA graph (trainer.PretrainStep)
+while `set_lr` keeps changing the rate every iteration as tools/train_net.py:123-124 does.
+
+`state_dict()` / `load_state_dict()` use torch.optim's layout (per-parameter `step` / `exp_avg` / `exp_avg_sq` or
+`momentum_buffer`, `param_groups` with integer ids) so `optimizer_state` entries of reference checkpoints
+(lib/utils/checkpoint.py:129,397) round-trip."""
+import math
+
+import torch
+
+from ... import ops
+
+
+# ------------------------------------------------------------------------------------------------ lr policy
+def lr_func_cosine(cfg, cur_epoch):
+    """lr_policy.py:30-48: half-cosine from BASE_LR to COSINE_END_LR over MAX_EPOCH."""
+    s = cfg.SOLVER
+    assert s.COSINE_END_LR < s.BASE_LR
+    return s.COSINE_END_LR + 0.5 * (s.BASE_LR - s.COSINE_END_LR) * (1.0 + math.cos(math.pi * cur_epoch / s.MAX_EPOCH))
+
+
+def get_step_index(cfg, cur_epoch):
+    """lr_policy.py:65-77 (including its quirk: an epoch beyond MAX_EPOCH maps to the second-to-last entry)."""
+    bounds = list(cfg.SOLVER.STEPS) + [cfg.SOLVER.MAX_EPOCH]
+    ind = 0
+    for ind, b in enumerate(bounds):
+        if cur_epoch < b:
+            break
+    return ind - 1
+
+
+def lr_func_steps_with_relative_lrs(cfg, cur_epoch):
+    """lr_policy.py:51-62."""
+    return cfg.SOLVER.LRS[get_step_index(cfg, cur_epoch)] * cfg.SOLVER.BASE_LR
+
+
+_POLICIES = {"cosine": lr_func_cosine, "steps_with_relative_lrs": lr_func_steps_with_relative_lrs}
+
+
+def get_lr_func(lr_policy):
+    if lr_policy not in _POLICIES:
+        raise NotImplementedError("Unknown LR policy: {}".format(lr_policy))
+    return _POLICIES[lr_policy]
+
+
+def get_lr_at_epoch(cfg, cur_epoch):
+    """lr_policy.py:8-27: the policy's value, linearly warmed up from WARMUP_START_LR over WARMUP_EPOCHS."""
+    f = get_lr_func(cfg.SOLVER.LR_POLICY)
+    lr = f(cfg, cur_epoch)
+    w = cfg.SOLVER.WARMUP_EPOCHS
+    if cur_epoch < w:
+        start = cfg.SOLVER.WARMUP_START_LR
+        lr = start + cur_epoch * (f(cfg, w) - start) / w
+    return lr
+
+
+def get_epoch_lr(cur_epoch, cfg):
+    """optimizer.py:118-127."""
+    return get_lr_at_epoch(cfg, cur_epoch)
+
+
+def set_lr(optimizer, new_lr):
+    """optimizer.py:130-140: every group's rate = new_lr x its lr_mult."""
+    for g in optimizer.param_groups:
+        g["lr"] = new_lr * g["lr_mult"] if "lr_mult" in g else new_lr
+
+
+# ------------------------------------------------------------------------------------------------ grouping
+def parameter_groups(model, cfg):
+    """The group lists of optimizer.py:18-84 (same freezing side effects on `requires_grad`)."""
+    sol, mult = cfg.SOLVER, cfg.TRAIN.MULT
+    named = list(model.named_parameters())
+    if mult != 1.0 or cfg.TRAIN.LINEAR:             # fine-tuning: encoder vs head / order transformer (optimizer.py:20-40)
+        enc, head = [], []
+        for name, p in named:
+            if "head" not in name and "order" not in name:
+                enc.append(p)
+                if cfg.TRAIN.LINEAR:
+                    p.requires_grad = False
+            else:
+                head.append(p)
+        if cfg.TRAIN.LINEAR:
+            groups = [{"params": head, "weight_decay": sol.WEIGHT_DECAY, "lr": sol.BASE_LR, "lr_mult": 1.0}]
+        else:
+            groups = [{"params": enc, "weight_decay": cfg.BN.WEIGHT_DECAY, "lr_mult": mult},
+                      {"params": head, "weight_decay": sol.WEIGHT_DECAY, "lr_mult": 1.0}]
+        assert len(named) == len(enc) + len(head)
+        return groups
+    bn, text, rest = [], [], []                     # pre-training (optimizer.py:41-88)
+    for name, p in named:
+        if "bn" in name:
+            bn.append(p)
+        elif "text_model" in name or "text_module" in name:
+            text.append(p)
+            if mult == 0:
+                p.requires_grad = False
+        else:
+            rest.append(p)
+    assert len(named) == len(bn) + len(text) + len(rest)
+    # TRAIN.MULT == 1 here (the branch above took every other value): text parameters join the main group
+    return [{"params": bn, "weight_decay": cfg.BN.WEIGHT_DECAY, "lr_mult": 1.0},
+            {"params": rest + text, "weight_decay": sol.WEIGHT_DECAY, "lr_mult": 1.0}]
+
+
+def construct_optimizer(model, cfg):
+    """optimizer.py:10-114."""
+    sol = cfg.SOLVER
+    groups = parameter_groups(model, cfg)
+    method = sol.OPTIMIZING_METHOD
+    if method == "sgd":
+        return FlatOptimizer(groups, "sgd", lr=sol.BASE_LR, momentum=sol.MOMENTUM, dampening=sol.DAMPENING,
+                             nesterov=sol.NESTEROV, weight_decay=sol.WEIGHT_DECAY)
+    if method in ("adam", "adamw"):
+        return FlatOptimizer(groups, method, lr=sol.BASE_LR, betas=(0.9, 0.999), eps=1e-08,
+                             weight_decay=sol.WEIGHT_DECAY)
+    raise NotImplementedError("Does not support {} optimizer".format(method))
+
+
+# ------------------------------------------------------------------------------------------------ flat optimizer
+class FlatOptimizer:
+    """torch.optim-shaped (param_groups / step / zero_grad / state_dict) optimizer over flat buffers.
+
+    Layout: trainable parameters of group 0, then group 1, ... in the order given; `offsets[i] = (start, end)` of
+    parameter i (torch.optim's numbering) inside `flat_param` / `flat_grad` / the state buffers.  Frozen parameters
+    (`requires_grad == False` at construction) are left alone, as torch leaves parameters without `.grad`."""
+
+    def __init__(self, groups, method="adamw", lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, momentum=0.0,
+                 dampening=0.0, nesterov=False):
+        assert method in ("sgd", "adam", "adamw")
+        if isinstance(groups, (list, tuple)) and groups and not isinstance(groups[0], dict):
+            groups = [{"params": list(groups)}]
+        self.method = method
+        self.defaults = dict(lr=lr, weight_decay=weight_decay)
+        if method == "sgd":
+            if nesterov and (momentum <= 0 or dampening != 0):
+                raise ValueError("Nesterov momentum requires a momentum and zero dampening")
+            self.defaults.update(momentum=momentum, dampening=dampening, nesterov=nesterov)
+        else:
+            self.defaults.update(betas=tuple(betas), eps=eps)
+        self.param_groups, self.offsets, self._ranges = [], [], []
+        total, dev = 0, None
+        for g in groups:
+            g = dict(g)
+            for k, v in self.defaults.items():
+                g.setdefault(k, v)
+            ps = [p for p in g["params"] if p.requires_grad]
+            g["params"] = ps
+            start = total
+            for p in ps:
+                assert p.is_cuda and p.dtype == torch.float32, "FlatOptimizer drives fp32 CUDA parameters (no CPU path)"
+                dev = p.device if dev is None else dev
+                self.offsets.append((total, total + p.numel()))
+                total += p.numel()
+            self._ranges.append((start, total))
+            self.param_groups.append(g)
+        if total == 0:
+            raise ValueError("optimizer got an empty parameter list")
+        self.flat_param = torch.empty(total, device=dev, dtype=torch.float32)
+        self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        n_state = 1 if method == "sgd" else 2
+        self._state = [torch.zeros(total, device=dev, dtype=torch.float32) for _ in range(n_state)]
+        self._params = [p for g in self.param_groups for p in g["params"]]
+        with torch.no_grad():
+            for p, (a, b) in zip(self._params, self.offsets):
+                view = self.flat_param[a:b].view_as(p)
+                view.copy_(p)
+                p.data = view
+                old = p.grad
+                p.grad = self.flat_grad[a:b].view_as(p)
+                if old is not None:
+                    p.grad.copy_(old)
+        self._step_dev = torch.zeros(1, device=dev, dtype=torch.float32)
+        self._lr_dev = torch.zeros(len(self.param_groups), device=dev, dtype=torch.float32)
+        self._lr_host = [None] * len(self.param_groups)
+        self.grad_scale = 1.0
+        self.sync_hyper()
+
+    # -- hyper-parameters that change between steps ---------------------------------------------------------
+    def sync_hyper(self):
+        """Push the groups' current `lr` to the device scalars the kernels read.  Must run OUTSIDE graph capture
+        (PretrainStep calls it before every replay); `step()` calls it itself when no capture is in progress."""
+        lrs = [float(g["lr"]) for g in self.param_groups]
+        if lrs != self._lr_host:
+            self._lr_dev.copy_(torch.tensor(lrs, dtype=torch.float32), non_blocking=False)
+            self._lr_host = lrs
+
+    # -- torch.optim surface --------------------------------------------------------------------------------
+    def zero_grad(self, set_to_none=False):
+        """Gradients stay views of the flat buffer (the engine's dW kernels accumulate into them), so they are cleared,
+        never dropped."""
+        self.flat_grad.zero_()
+
+    def _adopt_foreign_grads(self):
+        """A wrapper (e.g. DistributedDataParallel with gradient_as_bucket_view) may have re-pointed `.grad`: copy
+        such gradients into the flat buffer.  Returns the parameters without any gradient (torch skips those)."""
+        missing = []
+        for i, (p, (a, b)) in enumerate(zip(self._params, self.offsets)):
+            if p.grad is None:
+                missing.append(i)
+            elif p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * a:
+                self.flat_grad[a:b].view_as(p).copy_(p.grad)
+        return missing
+
+    def step(self, closure=None, zero_grad=False):
+        """One update of every group.  `zero_grad=True` also clears the gradients in the same pass (the
+        optimizer.step(); optimizer.zero_grad() pair of train_net.py:191-192 as one read-modify-write)."""
+        loss = closure() if closure is not None else None
+        capturing = torch.cuda.is_current_stream_capturing()
+        missing = []
+        if not capturing:
+            self.sync_hyper()
+            missing = self._adopt_foreign_grads()
+            torch.autograd.graph.increment_version(self._params)   # the kernels write through raw pointers
+        ops.optim_tick(self._step_dev)
+        for gi, (g, (a, b)) in enumerate(zip(self.param_groups, self._ranges)):
+            for s, e in _runs(a, b, [self.offsets[i] for i in missing]):
+                self._launch(gi, g, s, e, zero_grad)
+        return loss
+
+    def _launch(self, gi, g, s, e, zero_grad):
+        lr, sl = self._lr_dev[gi:gi + 1], slice(s, e)
+        if self.method == "sgd":
+            ops.sgd_flat(self.flat_param[sl], self.flat_grad[sl], self._state[0][sl], lr, self._step_dev,
+                         momentum=g["momentum"], dampening=g["dampening"], nesterov=g["nesterov"],
+                         weight_decay=g["weight_decay"], grad_scale=self.grad_scale, zero_grad=zero_grad)
+        else:
+            b1, b2 = g["betas"]
+            ops.adam_flat(self.flat_param[sl], self.flat_grad[sl], self._state[0][sl], self._state[1][sl], lr,
+                          self._step_dev, beta1=b1, beta2=b2, eps=g["eps"], weight_decay=g["weight_decay"],
+                          decoupled=self.method == "adamw", grad_scale=self.grad_scale, zero_grad=zero_grad)
+
+    # -- checkpoints (torch.optim layout) -------------------------------------------------------------------
+    _STATE_KEYS = {"sgd": ("momentum_buffer",), "adam": ("exp_avg", "exp_avg_sq"), "adamw": ("exp_avg", "exp_avg_sq")}
+
+    def state_dict(self):
+        step = float(self._step_dev.item())
+        state, keys = {}, self._STATE_KEYS[self.method]
+        if step > 0:
+            for i, (p, (a, b)) in enumerate(zip(self._params, self.offsets)):
+                st = {k: buf[a:b].view_as(p).clone() for k, buf in zip(keys, self._state)}
+                if self.method != "sgd":
+                    st["step"] = torch.tensor(step)
+                state[i] = st
+        groups, i = [], 0
+        for g in self.param_groups:
+            d = {k: v for k, v in g.items() if k != "params"}
+            d["params"] = list(range(i, i + len(g["params"])))
+            i += len(g["params"])
+            groups.append(d)
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd):
+        groups = sd["param_groups"]
+        if [len(g["params"]) for g in groups] != [len(g["params"]) for g in self.param_groups]:
+            raise ValueError("loaded state dict contains parameter groups that don't match the optimizer's")
+        for mine, theirs in zip(self.param_groups, groups):
+            mine.update({k: v for k, v in theirs.items() if k != "params"})
+        ids = [i for g in groups for i in g["params"]]
+        keys, step = self._STATE_KEYS[self.method], 0.0
+        for buf in self._state:
+            buf.zero_()
+        for pos, pid in enumerate(ids):
+            st = sd["state"].get(pid)
+            if st is None:
+                continue
+            a, b = self.offsets[pos]
+            for k, buf in zip(keys, self._state):
+                if st.get(k) is not None:
+                    buf[a:b].copy_(st[k].reshape(-1))
+            if "step" in st:
+                step = max(step, float(st["step"]))
+        if self.method == "sgd" and sd["state"]:
+            step = max(step, 1.0)                      # momentum buffers exist: the next step is not the first
+        self._step_dev.fill_(step)
+        self._lr_host = [None] * len(self.param_groups)
+        self.sync_hyper()
+
+
+def _runs(a, b, holes):
+    """[a, b) minus the (sorted, disjoint) intervals of `holes`, as a list of non-empty (start, end)."""
+    out, cur = [], a
+    for s, e in holes:
+        if e <= a or s >= b:
+            continue
+        if s > cur:
+            out.append((cur, s))
+        cur = max(cur, e)
+    if cur < b:
+        out.append((cur, b))
+    return out

@@ -81,6 +81,11 @@ _SIGS = {
                           _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
     "pvrl_ot_embed_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int,
                           _c_int, _c_int, _c_void_p],
+    "pvrl_optim_tick": [_c_void_p, _c_void_p],
+    "pvrl_adam_flat": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_i64, _c_void_p, _c_void_p, _c_float, _c_float,
+                       _c_float, _c_float, _c_float, _c_int, _c_float, _c_int, _c_void_p],
+    "pvrl_sgd_flat": [_c_void_p, _c_void_p, _c_void_p, _c_i64, _c_void_p, _c_void_p, _c_float, _c_float, _c_float,
+                      _c_int, _c_float, _c_float, _c_int, _c_void_p],
 }
 
 _lib = None
@@ -401,3 +406,27 @@ def ot_embed_bwd(dh, mask_inds, pad_start, dvideo, dtype, dpos, dpad, dtvec, B, 
     _f32c(dh, dvideo, dtype, dpos, dpad, dtvec)
     _check(lib().pvrl_ot_embed_bwd(_p(dh), _p(mask_inds), _p(pad_start), _p(dvideo), _p(dtype), _p(dpos), _p(dpad),
                                    _p(dtvec), B, S, C, _stream()), "pvrl_ot_embed_bwd")
+
+
+# ---------------------------------------------------------------------------------------------- optimizer (flat buffers)
+def optim_tick(step):
+    _f32c(step)
+    _check(lib().pvrl_optim_tick(_p(step), _stream()), "pvrl_optim_tick")
+
+
+def adam_flat(p, g, m, v, lr, step, *, lr_mult=1.0, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, decoupled=True,
+              grad_scale=1.0, zero_grad=True):
+    """One parameter group of torch.optim.AdamW (decoupled) / Adam on flat fp32 slices; lr / step are device scalars."""
+    _f32c(p, g, m, v, lr, step)
+    assert p.numel() == g.numel() == m.numel() == v.numel()
+    _check(lib().pvrl_adam_flat(_p(p), _p(g), _p(m), _p(v), p.numel(), _p(lr), _p(step), lr_mult, beta1, beta2, eps,
+                                weight_decay, int(decoupled), grad_scale, int(zero_grad), _stream()), "pvrl_adam_flat")
+
+
+def sgd_flat(p, g, buf, lr, step, *, lr_mult=1.0, momentum=0.0, dampening=0.0, nesterov=False, weight_decay=0.0,
+             grad_scale=1.0, zero_grad=True):
+    """One parameter group of torch.optim.SGD on flat fp32 slices; lr / step are device scalars."""
+    _f32c(p, g, buf, lr, step)
+    assert p.numel() == g.numel() == buf.numel()
+    _check(lib().pvrl_sgd_flat(_p(p), _p(g), _p(buf), p.numel(), _p(lr), _p(step), lr_mult, momentum, dampening,
+                               int(nesterov), weight_decay, grad_scale, int(zero_grad), _stream()), "pvrl_sgd_flat")

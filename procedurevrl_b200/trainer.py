@@ -10,6 +10,7 @@ import os
 import torch
 
 from . import functional as PF
+from .lib.models.optimizer import FlatOptimizer
 
 
 def bucket_ranges(named_sizes, depth, blocks_per_bucket):
@@ -38,7 +39,7 @@ def bucket_ranges(named_sizes, depth, blocks_per_bucket):
 
 
 class PretrainStep:
-    def __init__(self, model, cfg, lr=5e-5, weight_decay=1e-4, process_group=None, use_graph=True):
+    def __init__(self, model, cfg, lr=5e-5, weight_decay=1e-4, process_group=None, use_graph=True, optimizer=None):
         self.model = model
         self.inner = model.model                         # VisionTransformer mirror
         self.cfg = cfg
@@ -46,17 +47,17 @@ class PretrainStep:
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         self.params = [p for p in model.parameters() if p.requires_grad]
-        dev = self.params[0].device
-        self.flat_grad = torch.zeros(sum(p.numel() for p in self.params), device=dev, dtype=torch.float32)
-        off = 0
-        for p in self.params:
-            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        # Parameters, gradients and AdamW state in flat fp32 buffers (`p.data` / `p.grad` become views): the engine's
+        # dW / db kernels accumulate straight into flat_grad, the update + the clearing of the gradients for the next
+        # backward is one `pvrl_adam_flat` launch (procedurevrl_adamw.yaml SOLVER: one group, uniform decay).
+        self.opt = optimizer if optimizer is not None else \
+            FlatOptimizer([{"params": self.params, "lr_mult": 1.0}], "adamw", lr=lr, weight_decay=weight_decay)
+        self.flat_grad = self.opt.flat_grad
+        self.opt.grad_scale = 1.0
         eng = self.inner.engine()
         by_name = dict(self.inner.named_parameters())
         eng.grad_sink = {n: by_name[n].grad for n in eng.grad_names}
         assert all(g is not None for g in eng.grad_sink.values()), "every encoder parameter must be trainable here"
-        self.opt = torch.optim.AdamW(self.params, lr=lr, weight_decay=weight_decay, fused=True, capturable=use_graph)
         # Data-parallel gradient exchange (the only collective).  Default: ONE NCCL all-reduce of the flat buffer
         # after the backward (measured on 2 B200s: 34.4 ms/step).  PVRL_AR_BLOCKS_PER_BUCKET = n > 0 instead exchanges
         # buckets of n encoder blocks on a side stream as soon as the backward has finished them (part of the captured
@@ -66,7 +67,8 @@ class PretrainStep:
         self._ar_stream = torch.cuda.Stream() if self.world > 1 else None
         self._ar_ranges = None
         if self.world > 1 and self.blocks_per_bucket > 0:
-            names = [(n, p.numel()) for n, p in model.named_parameters() if p.requires_grad]
+            name_of = {id(p): n for n, p in model.named_parameters()}
+            names = [(name_of[id(p)], p.numel()) for p in self.opt._params]       # the flat buffers' layout order
             self._ar_ranges, self._ar_front_end, self._ar_tail_start = bucket_ranges(names, eng.depth,
                                                                                      self.blocks_per_bucket)
             eng.on_block_bwd_done = self._bucket_ready
@@ -83,8 +85,7 @@ class PretrainStep:
             torch.distributed.all_reduce(self.flat_grad[rng[0]:rng[1]], op=torch.distributed.ReduceOp.AVG, group=self.pg)
 
     def _eager(self, frames, meta):
-        self.inner.engine().invalidate_weights()
-        self.flat_grad.zero_()
+        self.inner.engine().invalidate_weights()     # flat_grad is clean: zero-initialised / cleared by the previous update
         pred, teacher, mse = self.model([frames, meta])
         loss, _, _ = PF.pretrain_loss(pred, teacher, mse, topk=self.topk)
         loss.backward()
@@ -96,7 +97,7 @@ class PretrainStep:
                 torch.distributed.all_reduce(self.flat_grad[:self._ar_front_end], op=AVG, group=self.pg)
                 torch.distributed.all_reduce(self.flat_grad[self._ar_tail_start:], op=AVG, group=self.pg)
                 torch.cuda.current_stream().wait_stream(self._ar_stream)
-        self.opt.step()
+        self.opt.step(zero_grad=True)
         return loss.detach()
 
     def capture(self, frames, meta, warmup=3):
@@ -120,5 +121,6 @@ class PretrainStep:
             return self._eager(frames, meta)
         if frames is not None and frames.data_ptr() != self.static[0].data_ptr():
             self.static[0].copy_(frames, non_blocking=True)
+        self.opt.sync_hyper()                       # learning-rate changes reach the graph through a device scalar
         self.graph.replay()
         return self.static_loss
