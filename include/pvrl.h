@@ -106,6 +106,19 @@ int pvrl_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const f
                        const float* stats, float* dx, float* dw, float* db, int32_t M, int32_t D, int32_t map,
                        pvrl_geom_t g, void* stream);
 
+/* The same, and while each updated dx row is still in registers it is also written out as the operand of the NEXT
+ * sub-layer's backward GEMMs: emit_out (act dtype = dy_dtype) receives exactly what
+ * pvrl_gather_cast(dx, emit_out, emit_map, emit_rowscale, emit_rs_div, emit_colsum) would produce after this call, so
+ * that pass over dx disappears.  Supported (map -> emit_map), the three hand-overs of Block.forward's backward
+ * (vit.py:130-157): IDENT -> SPATIAL (MLP -> spatial branch, cls rows replicated x 1/T), SPATIAL -> SKIPCLS (spatial ->
+ * temporal branch), SKIPCLS -> IDENT (temporal branch -> previous block's MLP; the clips' cls rows, which a SKIPCLS
+ * pass does not touch, are emitted from dx as they are) and SKIPCLS -> PATCH (first block -> patch embedding).
+ * M must cover whole clips. */
+int pvrl_layernorm_bwd_emit(const void* dy, int32_t dy_dtype, const float* x, const float* x_cls, const float* w,
+                            const float* stats, float* dx, float* dw, float* db, int32_t M, int32_t D, int32_t map,
+                            pvrl_geom_t g, void* emit_out, int32_t emit_map, const float* emit_rowscale,
+                            int32_t emit_rs_div, float* emit_colsum, void* stream);
+
 /* out[m] = act( rowscale[m/rs_div] * clsf(m) * src[map(m)] ), fp32 -> act dtype.  clsf = 1/T on the cls rows of
  * MAP_SPATIAL (backward of the mean over frames, vit.py:147-149), else 1.  colsum (NULL or fp32 [D]) += sum_m out[m]:
  * the bias gradient of the Linear whose dY this is, fused so that dY is not read a second time. */
@@ -237,9 +250,10 @@ int pvrl_ot_embed_bwd(const float* dh, const int64_t* mask_inds, const int64_t* 
  * g is multiplied by grad_scale before use (1/world after a SUM all-reduce, 1/micro-steps under accumulation) and,
  * with zero_grad != 0, cleared for the next backward (whose dW kernels accumulate). */
 int pvrl_optim_tick(float* step_dev, void* stream);
-/* decoupled != 0: AdamW (p *= 1 - lr*wd); decoupled == 0: Adam with the L2 term added to the gradient. */
+/* decoupled != 0: AdamW (p *= 1 - lr*wd); decoupled == 0: Adam with the L2 term added to the gradient.  The betas are
+ * doubles because torch derives 1 - beta and the bias corrections from the Python doubles before rounding to fp32. */
 int pvrl_adam_flat(float* p, float* g, float* m, float* v, int64_t n, const float* lr_dev, const float* step_dev,
-                   float lr_mult, float beta1, float beta2, float eps, float weight_decay, int32_t decoupled,
+                   float lr_mult, double beta1, double beta2, float eps, float weight_decay, int32_t decoupled,
                    float grad_scale, int32_t zero_grad, void* stream);
 /* torch.optim.SGD semantics: g += wd*p; buf = g on step 1 else momentum*buf + (1-dampening)*g;
  * update = g + momentum*buf (nesterov) or buf; p -= lr*update.  momentum == 0 ignores buf's contents. */

@@ -379,6 +379,11 @@ int attn_t8_fwd_launch(const void* qkv, void* out, float* lse, int n_seq, int se
                        cudaStream_t stream);
 int attn_t8_bwd_launch(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int n_seq,
                        int seq, int H, float scale, cudaStream_t stream);
+// attention_t32.cu: mma.sync kernels for 9..32 frames (bf16)
+int attn_t32_fwd_launch(const void* qkv, void* out, float* lse, int n_seq, int seq, int H, float scale,
+                        cudaStream_t stream);
+int attn_t32_bwd_launch(const void* qkv, const void* dout, const float* lse, void* dqkv, int n_seq, int seq, int H,
+                        float scale, cudaStream_t stream);
 }  // namespace pvrl
 
 using namespace pvrl;
@@ -430,6 +435,7 @@ extern "C" int pvrl_attn_fwd(const void* qkv, void* out, float* lse, int32_t dty
   PVRL_CHECK_ARG(qkv && out && n_seq > 0 && seq > 0 && H > 0, "pvrl_attn_fwd: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (seq <= 8 && dtype == PVRL_BF16) return attn_t8_fwd_launch(qkv, out, lse, n_seq, seq, H, scale, st);
+  if (seq <= 32 && dtype == PVRL_BF16) return attn_t32_fwd_launch(qkv, out, lse, n_seq, seq, H, scale, st);
   if (seq <= 32)
     return dtype == PVRL_F32 ? attn_small_fwd_launch<float>(qkv, out, lse, n_seq, seq, H, scale, st)
                              : attn_small_fwd_launch<__nv_bfloat16>(qkv, out, lse, n_seq, seq, H, scale, st);
@@ -460,6 +466,7 @@ extern "C" int pvrl_attn_bwd(const void* qkv, const void* out, const void* dout,
     return dtype == PVRL_F32 ? attn_bwd_long_launch<float>(qkv, out, dout, lse, dqkv, n_seq, seq, H, scale, st)
                              : attn_bwd_long_launch<__nv_bfloat16>(qkv, out, dout, lse, dqkv, n_seq, seq, H, scale, st);
   if (seq <= 8 && dtype == PVRL_BF16) return attn_t8_bwd_launch(qkv, out, dout, lse, dqkv, n_seq, seq, H, scale, st);
+  if (seq <= 32 && dtype == PVRL_BF16) return attn_t32_bwd_launch(qkv, dout, lse, dqkv, n_seq, seq, H, scale, st);
   if (seq <= 32)
     return dtype == PVRL_F32
                ? attn_small_bwd_launch<float>(qkv, out, dout, lse, dqkv, n_seq, seq, H, scale, st)

@@ -147,21 +147,79 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ x_cl
 // dx[src(m)] += rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * w;  dw += dy * xhat;  db += dy.
 // One warp per row, NVEC float4 per lane (D = 128 * NVEC); per-lane column sums of dy*xhat / dy live in registers
 // across the rows a warp visits and are folded block-wide through shared memory, then one atomicAdd per column.
-template <typename InT, int NVEC>
+// What the EMIT variant writes next to dx: the operand the NEXT sub-layer's backward GEMMs read -- exactly what
+// pvrl_gather_cast(dx, out, map, rowscale, rs_div, colsum) would produce afterwards -- while the updated row is still in
+// registers, so dx is not read a second time (36 gather launches per step disappear).
+struct LnEmit {
+  void* out;               // act dtype = dy's dtype, [rows of `map`][D]
+  const float* rowscale;   // DropPath factors of the next sub-layer (NULL = 1), indexed by emitted row / rs_div
+  float* colsum;           // += column sums of the emitted rows (bias gradient of the next Linear), NULL = skip
+  int map, rs_div;
+  int extra_cls;           // > 0: that many clips' cls rows (untouched by a MAP_SKIPCLS pass) are emitted from dx as they are
+};
+
+// emit dx row `xr` (values v, this lane's columns) to every row of em.map that addresses it
+template <typename OutT, int NVEC>
+__device__ __forceinline__ void ln_emit_row(const LnEmit& em, const Geom& g, long long xr, const float4 (&v)[NVEC],
+                                            float4 (&ec)[NVEC], int lane) {
+  constexpr int D = NVEC * 128;
+  const int xi = static_cast<int>(xr);      // residual-stream rows fit 31 bits (checked by the host: M is an int)
+  const int b = xi / g.S, pos = xi - b * g.S;
+  long long m2 = xr;
+  int reps = 1;
+  float ef = 1.0f;
+  if (em.map != PVRL_MAP_IDENT) {
+    if (pos > 0) {
+      const int n = (pos - 1) / g.T, t = (pos - 1) - n * g.T;
+      m2 = em.map == PVRL_MAP_SKIPCLS ? xr - b - 1
+           : em.map == PVRL_MAP_SPATIAL ? ((long long)b * g.T + t) * (g.HW + 1) + 1 + n
+                                        : ((long long)b * g.T + t) * g.HW + n;
+    } else if (em.map == PVRL_MAP_SPATIAL) {   // the clip's cls row feeds the cls row of each of its T frames, x 1/T (mean)
+      m2 = (long long)b * g.T * (g.HW + 1);
+      reps = g.T;
+      ef = 1.0f / g.T;
+    } else {
+      return;                                  // MAP_SKIPCLS / MAP_PATCH have no cls rows
+    }
+  }
+  OutT* out = static_cast<OutT*>(em.out);
+  for (int r = 0; r < reps; ++r, m2 += g.HW + 1) {
+    const float f = em.rowscale != nullptr ? __ldg(em.rowscale + static_cast<int>(m2) / em.rs_div) * ef : ef;
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      const float4 o = make_float4(v[i].x * f, v[i].y * f, v[i].z * f, v[i].w * f);
+      store4<OutT>(out + m2 * D + (i * 32 + lane) * 4, o.x, o.y, o.z, o.w);
+      ec[i].x += o.x, ec[i].y += o.y, ec[i].z += o.z, ec[i].w += o.w;
+    }
+  }
+}
+
+template <typename InT, int NVEC, bool EMIT>
 __global__ void __launch_bounds__(LN_WARPS * 32, NVEC <= 4 ? 2 : 1)
 layernorm_bwd_kernel(const InT* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ x_cls,
                      const float* __restrict__ w, const float* __restrict__ stats, float* __restrict__ dx,
-                     float* __restrict__ dw, float* __restrict__ db, int M, int map, Geom g) {
+                     float* __restrict__ dw, float* __restrict__ db, int M, int map, Geom g, LnEmit em) {
   if (PDL_EARLY_TRIGGER) pdl_launch_dependents();
   pdl_wait();
   constexpr int D = NVEC * 128;
-  __shared__ float sacc[2 * D];
-  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sacc[i] = 0.f;
+  __shared__ float sacc[(EMIT ? 3 : 2) * D];
+  for (int i = threadIdx.x; i < (EMIT ? 3 : 2) * D; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float4 aw[NVEC], ab[NVEC];
+  float4 aw[NVEC], ab[NVEC], ec[NVEC];   // ec: column sums of the emitted rows (dead code without EMIT)
 #pragma unroll
   for (int i = 0; i < NVEC; ++i) aw[i] = make_float4(0.f, 0.f, 0.f, 0.f), ab[i] = aw[i];
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i) ec[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if constexpr (EMIT) {   // cls rows this pass does not touch: copied out of dx as they are (complete since the previous kernel)
+    for (int b = blockIdx.x * LN_WARPS + warp; b < em.extra_cls; b += gridDim.x * LN_WARPS) {
+      const long long xr = (long long)b * g.S;
+      float4 cur[NVEC];
+#pragma unroll
+      for (int i = 0; i < NVEC; ++i) cur[i] = *(reinterpret_cast<const float4*>(dx + xr * D) + i * 32 + lane);
+      ln_emit_row<InT, NVEC>(em, g, xr, cur, ec, lane);
+    }
+  }
   // last row first: dy was just written by a GEMM whose final tiles are still in L2, and the gather that follows reads
   // dx from row 0 upwards -- the rows this kernel writes last
   for (int mm = blockIdx.x * LN_WARPS + warp; mm < M; mm += gridDim.x * LN_WARPS) {
@@ -202,8 +260,12 @@ layernorm_bwd_kernel(const InT* __restrict__ dy, const float* __restrict__ x, co
       if (cls) {  // T frames of one clip share the cls row (vit.py:138-140)
         atomicAdd(p, o.x), atomicAdd(p + 1, o.y), atomicAdd(p + 2, o.z), atomicAdd(p + 3, o.w);
       } else {
-        *reinterpret_cast<float4*>(p) = make_float4(cur[i].x + o.x, cur[i].y + o.y, cur[i].z + o.z, cur[i].w + o.w);
+        cur[i] = make_float4(cur[i].x + o.x, cur[i].y + o.y, cur[i].z + o.z, cur[i].w + o.w);
+        *reinterpret_cast<float4*>(p) = cur[i];
       }
+    }
+    if constexpr (EMIT) {
+      if (!cls) ln_emit_row<InT, NVEC>(em, g, xr, cur, ec, lane);
     }
   }
 #pragma unroll
@@ -214,24 +276,33 @@ layernorm_bwd_kernel(const InT* __restrict__ dy, const float* __restrict__ x, co
     atomicAdd(&sacc[D + c], ab[i].x), atomicAdd(&sacc[D + c + 1], ab[i].y), atomicAdd(&sacc[D + c + 2], ab[i].z),
         atomicAdd(&sacc[D + c + 3], ab[i].w);
   }
+  if (EMIT && em.colsum != nullptr) {
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      atomicAdd(&sacc[2 * D + c], ec[i].x), atomicAdd(&sacc[2 * D + c + 1], ec[i].y);
+      atomicAdd(&sacc[2 * D + c + 2], ec[i].z), atomicAdd(&sacc[2 * D + c + 3], ec[i].w);
+    }
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < D; i += blockDim.x) {
     if (dw != nullptr) atomicAdd(dw + i, sacc[i]);
     if (db != nullptr) atomicAdd(db + i, sacc[D + i]);
+    if (EMIT && em.colsum != nullptr) atomicAdd(em.colsum + i, sacc[2 * D + i]);
   }
 }
 
-template <typename InT>
+template <typename InT, bool EMIT>
 int layernorm_bwd_launch(const void* dy, const float* x, const float* x_cls, const float* w, const float* stats,
-                         float* dx, float* dw, float* db, int M, int D, int map, Geom gg, cudaStream_t stream) {
+                         float* dx, float* dw, float* db, int M, int D, int map, Geom gg, LnEmit em, cudaStream_t stream) {
   int grid = (M + LN_WARPS - 1) / LN_WARPS;
   if (grid > 148 * 2) grid = 148 * 2;   // persistent row loop; 1-2 blocks are resident per SM (register-bound)
   const InT* d = static_cast<const InT*>(dy);
   switch (D / 128) {
-    case 2: launch_pdl(layernorm_bwd_kernel<InT, 2>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, d, x, x_cls, w, stats, dx, dw, db, M, map, gg); break;
-    case 4: launch_pdl(layernorm_bwd_kernel<InT, 4>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, d, x, x_cls, w, stats, dx, dw, db, M, map, gg); break;
-    case 6: launch_pdl(layernorm_bwd_kernel<InT, 6>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, d, x, x_cls, w, stats, dx, dw, db, M, map, gg); break;
-    case 8: launch_pdl(layernorm_bwd_kernel<InT, 8>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, d, x, x_cls, w, stats, dx, dw, db, M, map, gg); break;
+    case 2: launch_pdl(layernorm_bwd_kernel<InT, 2, EMIT>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, d, x, x_cls, w, stats, dx, dw, db, M, map, gg, em); break;
+    case 4: launch_pdl(layernorm_bwd_kernel<InT, 4, EMIT>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, d, x, x_cls, w, stats, dx, dw, db, M, map, gg, em); break;
+    case 6: launch_pdl(layernorm_bwd_kernel<InT, 6, EMIT>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, d, x, x_cls, w, stats, dx, dw, db, M, map, gg, em); break;
+    case 8: launch_pdl(layernorm_bwd_kernel<InT, 8, EMIT>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, d, x, x_cls, w, stats, dx, dw, db, M, map, gg, em); break;
     default: return fail(-1, "pvrl_layernorm_bwd: D=%d not in {256, 512, 768, 1024}", D);
   }
   return launched("layernorm_bwd_kernel");
@@ -537,9 +608,36 @@ extern "C" int pvrl_layernorm_bwd(const void* dy, int32_t dy_dtype, const float*
   PVRL_CHECK_ARG(D % 128 == 0 && D <= 128 * LN_MAX_VEC, "pvrl_layernorm_bwd: D=%d must be a multiple of 128, <= 1024", D);
   PVRL_CHECK_ARG(map != PVRL_MAP_SPATIAL || x_cls != nullptr, "pvrl_layernorm_bwd: MAP_SPATIAL needs x_cls");
   const Geom gg(g.T > 0 ? g.T : 1, g.HW > 0 ? g.HW : 1);
+  const LnEmit none = {};
   return dy_dtype == PVRL_F32
-             ? layernorm_bwd_launch<float>(dy, x, x_cls, w, stats, dx, dw, db, M, D, map, gg, STREAM)
-             : layernorm_bwd_launch<__nv_bfloat16>(dy, x, x_cls, w, stats, dx, dw, db, M, D, map, gg, STREAM);
+             ? layernorm_bwd_launch<float, false>(dy, x, x_cls, w, stats, dx, dw, db, M, D, map, gg, none, STREAM)
+             : layernorm_bwd_launch<__nv_bfloat16, false>(dy, x, x_cls, w, stats, dx, dw, db, M, D, map, gg, none, STREAM);
+}
+
+extern "C" int pvrl_layernorm_bwd_emit(const void* dy, int32_t dy_dtype, const float* x, const float* x_cls,
+                                       const float* w, const float* stats, float* dx, float* dw, float* db, int32_t M,
+                                       int32_t D, int32_t map, pvrl_geom_t g, void* emit_out, int32_t emit_map,
+                                       const float* emit_rowscale, int32_t emit_rs_div, float* emit_colsum,
+                                       void* stream) {
+  PVRL_CHECK_ARG(dy && x && w && stats && dx && M > 0 && emit_out, "pvrl_layernorm_bwd_emit: bad arguments");
+  PVRL_CHECK_ARG(D % 128 == 0 && D <= 128 * LN_MAX_VEC, "pvrl_layernorm_bwd_emit: D=%d must be a multiple of 128, <= 1024", D);
+  PVRL_CHECK_ARG(map != PVRL_MAP_SPATIAL || x_cls != nullptr, "pvrl_layernorm_bwd_emit: MAP_SPATIAL needs x_cls");
+  PVRL_CHECK_ARG(emit_rowscale == nullptr || emit_rs_div > 0, "pvrl_layernorm_bwd_emit: rowscale needs rs_div > 0");
+  const Geom gg(g.T > 0 ? g.T : 1, g.HW > 0 ? g.HW : 1);
+  // the pairs for which "every row of emit_map is addressed by a row this pass completes" holds (vit.py:130-157 backward)
+  const bool ok = (map == PVRL_MAP_IDENT && emit_map == PVRL_MAP_SPATIAL) ||
+                  (map == PVRL_MAP_SPATIAL && emit_map == PVRL_MAP_SKIPCLS) ||
+                  (map == PVRL_MAP_SKIPCLS && (emit_map == PVRL_MAP_IDENT || emit_map == PVRL_MAP_PATCH));
+  PVRL_CHECK_ARG(ok, "pvrl_layernorm_bwd_emit: map %d cannot emit map %d", map, emit_map);
+  const int rows_per_clip = map == PVRL_MAP_IDENT ? gg.S : map == PVRL_MAP_SPATIAL ? gg.T * (gg.HW + 1) : gg.L;
+  PVRL_CHECK_ARG(M % rows_per_clip == 0, "pvrl_layernorm_bwd_emit: M=%d is not a whole number of clips", M);
+  LnEmit em;
+  em.out = emit_out, em.rowscale = emit_rowscale, em.colsum = emit_colsum, em.map = emit_map;
+  em.rs_div = emit_rs_div > 0 ? emit_rs_div : 1;
+  em.extra_cls = (map == PVRL_MAP_SKIPCLS && emit_map == PVRL_MAP_IDENT) ? M / rows_per_clip : 0;
+  return dy_dtype == PVRL_F32
+             ? layernorm_bwd_launch<float, true>(dy, x, x_cls, w, stats, dx, dw, db, M, D, map, gg, em, STREAM)
+             : layernorm_bwd_launch<__nv_bfloat16, true>(dy, x, x_cls, w, stats, dx, dw, db, M, D, map, gg, em, STREAM);
 }
 
 extern "C" int pvrl_gather_cast(const float* src, void* out, int32_t out_dtype, const float* rowscale, int32_t rs_div,

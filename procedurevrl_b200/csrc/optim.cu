@@ -20,14 +20,15 @@ struct AdamCoef {
   float inv_sqrt_bc2;
 };
 
-__device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, const AdamCoef& c, float beta1,
-                                          float beta2, float eps, float wd, bool decoupled) {
+// omb1 / omb2 = 1 - beta, rounded from the double difference (what torch's kernels use), not from 1.f - float(beta)
+__device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, const AdamCoef& c, float omb1,
+                                          float omb2, float eps, float wd, bool decoupled) {
   if (decoupled)
     p -= c.lr_wd * p;           // AdamW: p *= 1 - lr * wd
   else
     g = fmaf(wd, p, g);         // Adam: L2 term joins the gradient
-  m = fmaf(1.f - beta1, g - m, m);
-  v = fmaf(1.f - beta2, g * g - v, v);
+  m = fmaf(omb1, g - m, m);
+  v = fmaf(omb2, g * g - v, v);
   const float denom = sqrtf(v) * c.inv_sqrt_bc2 + eps;
   p -= c.step_size * (m / denom);
 }
@@ -36,17 +37,18 @@ template <bool ZERO>
 __global__ void __launch_bounds__(THREADS)
 adam_flat_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                  long long n, const float* __restrict__ lr_dev, const float* __restrict__ step_dev, float lr_mult,
-                 float beta1, float beta2, float eps, float wd, int decoupled, float grad_scale) {
+                 double beta1d, double beta2d, float eps, float wd, int decoupled, float grad_scale) {
   __shared__ AdamCoef sc;
   if (threadIdx.x == 0) {
     const double t = static_cast<double>(*step_dev);
     const float lr = *lr_dev * lr_mult;
     sc.lr_wd = lr * wd;
-    sc.step_size = static_cast<float>(static_cast<double>(lr) / (1.0 - pow(static_cast<double>(beta1), t)));
-    sc.inv_sqrt_bc2 = static_cast<float>(1.0 / sqrt(1.0 - pow(static_cast<double>(beta2), t)));
+    sc.step_size = static_cast<float>(static_cast<double>(lr) / (1.0 - pow(beta1d, t)));
+    sc.inv_sqrt_bc2 = static_cast<float>(1.0 / sqrt(1.0 - pow(beta2d, t)));
   }
   __syncthreads();
   const AdamCoef c = sc;
+  const float omb1 = static_cast<float>(1.0 - beta1d), omb2 = static_cast<float>(1.0 - beta2d);
   const bool dec = decoupled != 0;
   // scalar head up to the first 16-byte boundary (all four arrays share their misalignment: checked by the host)
   const long long head = min(n, static_cast<long long>(((16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15) >> 2));
@@ -56,7 +58,7 @@ adam_flat_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict
     for (long long i = threadIdx.x; i < head + (n - tail0); i += THREADS) {
       const long long j = i < head ? i : tail0 + (i - head);
       float pp = p[j], mm = m[j], vv = v[j];
-      adam_elem(pp, g[j] * grad_scale, mm, vv, c, beta1, beta2, eps, wd, dec);
+      adam_elem(pp, g[j] * grad_scale, mm, vv, c, omb1, omb2, eps, wd, dec);
       p[j] = pp, m[j] = mm, v[j] = vv;
       if (ZERO) g[j] = 0.f;
     }
@@ -77,10 +79,10 @@ adam_flat_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict
     for (int u = 0; u < UNROLL; ++u) {
       const long long i = i0 + u * stride;
       if (i < nvec) {
-        adam_elem(pp[u].x, gg[u].x * grad_scale, mm[u].x, vv[u].x, c, beta1, beta2, eps, wd, dec);
-        adam_elem(pp[u].y, gg[u].y * grad_scale, mm[u].y, vv[u].y, c, beta1, beta2, eps, wd, dec);
-        adam_elem(pp[u].z, gg[u].z * grad_scale, mm[u].z, vv[u].z, c, beta1, beta2, eps, wd, dec);
-        adam_elem(pp[u].w, gg[u].w * grad_scale, mm[u].w, vv[u].w, c, beta1, beta2, eps, wd, dec);
+        adam_elem(pp[u].x, gg[u].x * grad_scale, mm[u].x, vv[u].x, c, omb1, omb2, eps, wd, dec);
+        adam_elem(pp[u].y, gg[u].y * grad_scale, mm[u].y, vv[u].y, c, omb1, omb2, eps, wd, dec);
+        adam_elem(pp[u].z, gg[u].z * grad_scale, mm[u].z, vv[u].z, c, omb1, omb2, eps, wd, dec);
+        adam_elem(pp[u].w, gg[u].w * grad_scale, mm[u].w, vv[u].w, c, omb1, omb2, eps, wd, dec);
         p4[i] = pp[u], m4[i] = mm[u], v4[i] = vv[u];
         if (ZERO) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
@@ -168,7 +170,7 @@ extern "C" int pvrl_optim_tick(float* step_dev, void* stream) {
 }
 
 extern "C" int pvrl_adam_flat(float* p, float* g, float* m, float* v, int64_t n, const float* lr_dev,
-                              const float* step_dev, float lr_mult, float beta1, float beta2, float eps,
+                              const float* step_dev, float lr_mult, double beta1, double beta2, float eps,
                               float weight_decay, int32_t decoupled, float grad_scale, int32_t zero_grad, void* stream) {
   PVRL_CHECK_ARG(p && g && m && v && lr_dev && step_dev && n > 0, "pvrl_adam_flat: bad arguments");
   PVRL_CHECK_ARG((reinterpret_cast<uintptr_t>(p) & 3) == 0 && same_misalignment(p, g) && same_misalignment(p, m) &&

@@ -20,6 +20,8 @@ accumulates hi*hi + hi*lo + lo*hi in fp32 (product error ~2^-17 instead of 2^-9)
 """
 import math
 
+import os
+
 import torch
 
 from . import ops
@@ -49,6 +51,9 @@ class EncoderEngine:
         self._wepoch = 0
         self.grad_sink = None             # optional dict name -> fp32 tensor: backward accumulates straight into it
         self.pixel_mean, self.pixel_std = (0.45, 0.45, 0.45), (0.225, 0.225, 0.225)   # DATA.MEAN / DATA.STD (defaults.py:510,516)
+        # every LayerNorm backward also writes the next sub-layer's dY operand (pvrl_layernorm_bwd_emit) instead of a
+        # separate pvrl_gather_cast pass over dx; PVRL_FUSE_GATHER=0 restores the separate passes
+        self.fuse_gather = os.environ.get("PVRL_FUSE_GATHER", "1") != "0"
         self.on_block_bwd_done = None     # optional callable(i): block i's parameter gradients are complete (bucketed all-reduce)
         self._wcache = {}      # name -> (version, W operand [N, K'], W^T operand [K, N'])
         self.grad_names = self._grad_names()
@@ -323,17 +328,30 @@ class EncoderEngine:
         dx = torch.zeros(Bc, S, D, device=dev, dtype=torch.float32)
         ops.layernorm_bwd(dfeat.contiguous(), st["x_last"], P[self.pre + "norm.weight"], st["st_f"], dx,
                           G[self.pre + "norm.weight"], G[self.pre + "norm.bias"], Bc, D, ops.MAP_CLS, **g)
+        KP = 3 * self.patch * self.patch
+        Mp = Bc * T * HW
+        dY = None                                  # block i's MLP operand, emitted by block i+1's last LayerNorm backward
         for i in reversed(range(self.depth)):
-            self._block_bwd(i, st["blocks"][i], dx, G, Bc, T, HW)
+            # what this block's last LayerNorm backward hands to its successor in the backward order: the MLP dY of
+            # block i-1 (DropPath factors and fc2 bias gradient of THAT block), or the patch-embedding dY below block 0
+            if not self.fuse_gather:
+                nxt = None
+            elif i > 0:
+                nxt = (self._act(Bc * S, D, dev), ops.MAP_IDENT, st["blocks"][i - 1]["dp"].get("mlp"), S,
+                       G[f"{self.pre}blocks.{i - 1}.mlp.fc2.bias"])
+            else:
+                nxt = (self._act(Mp, D, dev), ops.MAP_PATCH, None, 0, G[self.pre + "patch_embed.proj.bias"])
+            self._block_bwd(i, st["blocks"][i], dx, G, Bc, T, HW, dY, nxt)
+            dY = nxt[0] if nxt is not None else None
             st["blocks"][i] = None                 # free this block's activations
             if self.on_block_bwd_done is not None:
                 self.on_block_bwd_done(i)
 
         # embeddings (vit.py:370-407): patch conv, cls token, pos / time embeddings
-        KP = 3 * self.patch * self.patch
-        Mp = Bc * T * HW
-        dYp = self._act(Mp, D, dev)
-        ops.gather_cast(dx, dYp, Mp, D, ops.MAP_PATCH, colsum=G[self.pre + "patch_embed.proj.bias"], **g)
+        dYp = dY
+        if dYp is None:
+            dYp = self._act(Mp, D, dev)
+            ops.gather_cast(dx, dYp, Mp, D, ops.MAP_PATCH, colsum=G[self.pre + "patch_embed.proj.bias"], **g)
         self.linear_dw(dYp, st["A"], G[self.pre + "patch_embed.proj.weight"].view(D, KP), None, Mp, D, KP)
         gpos, gte = G[self.pre + "pos_embed"][0], G[self.pre + "time_embed"][0]
         dpos = gpos if st["pos_idx"] is None else torch.zeros(HW + 1, D, device=dev)
@@ -345,7 +363,11 @@ class EncoderEngine:
             gte.index_add_(0, st["te_idx"], dte)
         return G
 
-    def _block_bwd(self, i, sv, dx, G, Bc, T, HW):
+    def _block_bwd(self, i, sv, dx, G, Bc, T, HW, dY=None, nxt=None):
+        """dY: this block's MLP operand if the previous call already emitted it; nxt = (out, map, rowscale, rs_div, colsum):
+        what the temporal LayerNorm backward emits for the next call (see `backward`).  With `fuse_gather` every
+        LayerNorm backward writes the next sub-layer's GEMM operand itself (pvrl_layernorm_bwd_emit); otherwise a
+        pvrl_gather_cast pass re-reads dx."""
         D, H, Hd = self.D, self.H, self.hidden
         L, S = HW * T, 1 + HW * T
         Mt, Ms, Mm = Bc * L, Bc * T * (HW + 1), Bc * S
@@ -354,10 +376,12 @@ class EncoderEngine:
         P = self.p
         g = dict(T=T, HW=HW)
         dp = sv["dp"]
+        fuse = self.fuse_gather
 
         # ---- MLP: x3 = x2 + s_m * (fc2(gelu(fc1(LN(x2)))))
-        dY = self._act(Mm, D, dev)
-        ops.gather_cast(dx, dY, Mm, D, ops.MAP_IDENT, rowscale=dp.get("mlp"), rs_div=S, colsum=G[b + "mlp.fc2.bias"])
+        if dY is None:
+            dY = self._act(Mm, D, dev)
+            ops.gather_cast(dx, dY, Mm, D, ops.MAP_IDENT, rowscale=dp.get("mlp"), rs_div=S, colsum=G[b + "mlp.fc2.bias"])
         self.linear_dw(dY, sv["hid"], G[b + "mlp.fc2.weight"], None, Mm, D, Hd)
         d_pre = self._act(Mm, Hd, dev)
         self.linear_dx(dY, b + "mlp.fc2.weight", d_pre, Mm, Hd, D, epilogue=ops.EPI_DGELU, aux=sv["dact"],
@@ -365,14 +389,16 @@ class EncoderEngine:
         self.linear_dw(d_pre, sv["ln_m"], G[b + "mlp.fc1.weight"], None, Mm, Hd, D)
         d_ln = self._act(Mm, D, dev)
         self.linear_dx(d_pre, b + "mlp.fc1.weight", d_ln, Mm, D, Hd)
-        del d_pre
+        del d_pre, dY
+        dYs = self._act(Ms, D, dev)
+        emit = (dYs, ops.MAP_SPATIAL, dp.get("spatial"), HW + 1, G[b + "attn.proj.bias"]) if fuse else None
         ops.layernorm_bwd(d_ln, sv["x2"], P[b + "norm2.weight"], sv["st_m"], dx, G[b + "norm2.weight"],
-                          G[b + "norm2.bias"], Mm, D, ops.MAP_IDENT)
+                          G[b + "norm2.bias"], Mm, D, ops.MAP_IDENT, emit=emit, **g)
 
         # ---- spatial: tokens x2 = x1 + s_s * proj(attn(LN(gather(x0 cls, x1)))), cls = x0 cls + mean_t(...)
-        dYs = self._act(Ms, D, dev)
-        ops.gather_cast(dx, dYs, Ms, D, ops.MAP_SPATIAL, rowscale=dp.get("spatial"), rs_div=HW + 1,
-                        colsum=G[b + "attn.proj.bias"], **g)
+        if not fuse:
+            ops.gather_cast(dx, dYs, Ms, D, ops.MAP_SPATIAL, rowscale=dp.get("spatial"), rs_div=HW + 1,
+                            colsum=G[b + "attn.proj.bias"], **g)
         self.linear_dw(dYs, sv["o_s"], G[b + "attn.proj.weight"], None, Ms, D, D)
         d_o = self._act(Ms, D, dev)
         self.linear_dx(dYs, b + "attn.proj.weight", d_o, Ms, D, D)
@@ -381,12 +407,15 @@ class EncoderEngine:
         self.linear_dw(dqkv, sv["ln_s"], G[b + "attn.qkv.weight"], G[b + "attn.qkv.bias"], Ms, 3 * D, D)
         d_ln = self._act(Ms, D, dev)
         self.linear_dx(dqkv, b + "attn.qkv.weight", d_ln, Ms, D, 3 * D)
+        del dYs
+        dYf = self._act(Mt, D, dev)
+        emit = (dYf, ops.MAP_SKIPCLS, None, 0, G[b + "temporal_fc.bias"]) if fuse else None
         ops.layernorm_bwd(d_ln, sv["x1"], P[b + "norm1.weight"], sv["st_s"], dx, G[b + "norm1.weight"],
-                          G[b + "norm1.bias"], Ms, D, ops.MAP_SPATIAL, x_cls=sv["x0"], **g)
+                          G[b + "norm1.bias"], Ms, D, ops.MAP_SPATIAL, x_cls=sv["x0"], emit=emit, **g)
 
         # ---- temporal: x1 = x0[:,1:] + fc(s_t * proj(attn(LN(x0[:,1:]))))
-        dYf = self._act(Mt, D, dev)
-        ops.gather_cast(dx, dYf, Mt, D, ops.MAP_SKIPCLS, colsum=G[b + "temporal_fc.bias"], **g)
+        if not fuse:
+            ops.gather_cast(dx, dYf, Mt, D, ops.MAP_SKIPCLS, colsum=G[b + "temporal_fc.bias"], **g)
         self.linear_dw(dYf, sv["p_t"], G[b + "temporal_fc.weight"], None, Mt, D, D)
         d_p = self._act(Mt, D, dev)
         self.linear_dx(dYf, b + "temporal_fc.weight", d_p, Mt, D, D, rowscale=dp.get("temporal"), rs_div=T,
@@ -400,7 +429,8 @@ class EncoderEngine:
         d_ln = self._act(Mt, D, dev)
         self.linear_dx(dqkv, b + "temporal_attn.qkv.weight", d_ln, Mt, D, 3 * D)
         ops.layernorm_bwd(d_ln, sv["x0"], P[b + "temporal_norm1.weight"], sv["st_t"], dx,
-                          G[b + "temporal_norm1.weight"], G[b + "temporal_norm1.bias"], Mt, D, ops.MAP_SKIPCLS, **g)
+                          G[b + "temporal_norm1.weight"], G[b + "temporal_norm1.bias"], Mt, D, ops.MAP_SKIPCLS,
+                          emit=nxt, **g)
 
 
 # ---------------------------------------------------------------------------------------------- plain ViT schedules

@@ -44,6 +44,9 @@ _SIGS = {
                            _c_float, _c_int, Geom, _c_void_p],
     "pvrl_layernorm_bwd": [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                            _c_void_p, _c_int, _c_int, _c_int, Geom, _c_void_p],
+    "pvrl_layernorm_bwd_emit": [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                _c_void_p, _c_int, _c_int, _c_int, Geom, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p,
+                                _c_void_p],
     "pvrl_gather_cast": [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int, Geom, _c_void_p,
                          _c_void_p],
     "pvrl_cls_merge": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],
@@ -82,8 +85,8 @@ _SIGS = {
     "pvrl_ot_embed_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int,
                           _c_int, _c_int, _c_void_p],
     "pvrl_optim_tick": [_c_void_p, _c_void_p],
-    "pvrl_adam_flat": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_i64, _c_void_p, _c_void_p, _c_float, _c_float,
-                       _c_float, _c_float, _c_float, _c_int, _c_float, _c_int, _c_void_p],
+    "pvrl_adam_flat": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_i64, _c_void_p, _c_void_p, _c_float,
+                       ctypes.c_double, ctypes.c_double, _c_float, _c_float, _c_int, _c_float, _c_int, _c_void_p],
     "pvrl_sgd_flat": [_c_void_p, _c_void_p, _c_void_p, _c_i64, _c_void_p, _c_void_p, _c_float, _c_float, _c_float,
                       _c_int, _c_float, _c_float, _c_int, _c_void_p],
 }
@@ -198,9 +201,18 @@ def layernorm_fwd(x, w, b, y, stats, M, D, eps, map=MAP_IDENT, x_cls=None, T=1, 
     return y
 
 
-def layernorm_bwd(dy, x, w, stats, dx, dw, db, M, D, map=MAP_IDENT, x_cls=None, T=1, HW=1):
-    _check(lib().pvrl_layernorm_bwd(_p(dy), _dt(dy), _p(x), _p(x_cls), _p(w), _p(stats), _p(dx), _p(dw), _p(db), M, D,
-                                    map, _geom(T, HW), _stream()), "pvrl_layernorm_bwd")
+def layernorm_bwd(dy, x, w, stats, dx, dw, db, M, D, map=MAP_IDENT, x_cls=None, T=1, HW=1, emit=None):
+    """emit = (out, map, rowscale, rs_div, colsum): also write what gather_cast(dx, out, ..., map, rowscale, rs_div,
+    colsum) would produce after this call (see pvrl_layernorm_bwd_emit for the supported map pairs)."""
+    if emit is None:
+        _check(lib().pvrl_layernorm_bwd(_p(dy), _dt(dy), _p(x), _p(x_cls), _p(w), _p(stats), _p(dx), _p(dw), _p(db), M, D,
+                                        map, _geom(T, HW), _stream()), "pvrl_layernorm_bwd")
+        return
+    out, emap, rowscale, rs_div, colsum = emit
+    assert out.dtype == dy.dtype, "the emitted operand has the dtype of dy"
+    _check(lib().pvrl_layernorm_bwd_emit(_p(dy), _dt(dy), _p(x), _p(x_cls), _p(w), _p(stats), _p(dx), _p(dw), _p(db), M, D,
+                                         map, _geom(T, HW), _p(out), emap, _p(rowscale), rs_div or 0, _p(colsum),
+                                         _stream()), "pvrl_layernorm_bwd_emit")
 
 
 def gather_cast(src, out, M, D, map=MAP_IDENT, rowscale=None, rs_div=0, T=1, HW=1, colsum=None):

@@ -133,7 +133,20 @@ def layernorm_fwd(x, w, b, y, stats, M, D, eps, map=MAP_IDENT, x_cls=None, T=1, 
     return y
 
 
-def layernorm_bwd(dy, x, w, stats, dx, dw, db, M, D, map=MAP_IDENT, x_cls=None, T=1, HW=1):
+def layernorm_bwd(dy, x, w, stats, dx, dw, db, M, D, map=MAP_IDENT, x_cls=None, T=1, HW=1, emit=None):
+    _layernorm_bwd(dy, x, w, stats, dx, dw, db, M, D, map, x_cls, T, HW)
+    if emit is not None:        # pvrl_layernorm_bwd_emit == the gather_cast that would follow, for the supported map pairs
+        out, emap, rowscale, rs_div, colsum = emit
+        assert (map, emap) in ((MAP_IDENT, MAP_SPATIAL), (MAP_SPATIAL, MAP_SKIPCLS), (MAP_SKIPCLS, MAP_IDENT),
+                               (MAP_SKIPCLS, MAP_PATCH)) and out.dtype == dy.dtype
+        L, S = T * HW, 1 + T * HW
+        Bc = M // {MAP_IDENT: S, MAP_SPATIAL: T * (HW + 1), MAP_SKIPCLS: L}[map]
+        M2 = Bc * {MAP_SPATIAL: T * (HW + 1), MAP_SKIPCLS: L, MAP_IDENT: S, MAP_PATCH: L}[emap]
+        _launches[0] -= 1
+        gather_cast(dx, out, M2, D, emap, rowscale=rowscale, rs_div=rs_div, T=T, HW=HW, colsum=colsum)
+
+
+def _layernorm_bwd(dy, x, w, stats, dx, dw, db, M, D, map=MAP_IDENT, x_cls=None, T=1, HW=1):
     _launches[0] += 1
     src, rows = _ln_src(x, x_cls, M, D, map, T, HW)
     d = dy[:M].float()

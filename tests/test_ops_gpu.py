@@ -265,7 +265,8 @@ def test_gather_cast_clsmerge_colsum_castweight_embedbwd(ops):
 
 
 # ------------------------------------------------------------------------------------------------ attention
-@pytest.mark.parametrize("n_seq,seq,H", [(37, 8, 12), (5, 4, 12), (3, 7, 5), (1, 1, 1), (3528, 8, 12), (3, 32, 12), (4, 197, 12), (1, 460, 2)])
+@pytest.mark.parametrize("n_seq,seq,H", [(37, 8, 12), (5, 4, 12), (3, 7, 5), (1, 1, 1), (3528, 8, 12), (3, 32, 12), (4, 197, 12), (1, 460, 2),
+                                         (50, 32, 12), (7, 16, 12), (5, 9, 3), (3, 17, 5), (2, 24, 12), (3, 29, 2), (1, 12, 1), (393, 32, 12)])
 def test_attn_simt(ops, n_seq, seq, H):
     C = H * 64
     scale = 64 ** -0.5
@@ -515,3 +516,46 @@ def test_cast_weight_multi(ops):
     for w, (o, oT) in zip(ws, outs):
         assert torch.equal(o, w.bfloat16())
         assert torch.equal(oT, w.t().contiguous().bfloat16())
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("pair", ["mlp->spatial", "spatial->temporal", "temporal->mlp", "temporal->patch"])
+def test_layernorm_bwd_emit(ops, pair, dt):
+    """pvrl_layernorm_bwd_emit == pvrl_layernorm_bwd followed by pvrl_gather_cast: same dx / dw / db, the emitted operand
+    bit-equal to the separate gather (same arithmetic on the same fp32 row), its column sums equal up to summation order."""
+    Bc, T, HW, D = 3, 5, 7, 768
+    L, S = T * HW, 1 + T * HW
+    lmap, emap = {"mlp->spatial": (ops.MAP_IDENT, ops.MAP_SPATIAL), "spatial->temporal": (ops.MAP_SPATIAL, ops.MAP_SKIPCLS),
+                  "temporal->mlp": (ops.MAP_SKIPCLS, ops.MAP_IDENT), "temporal->patch": (ops.MAP_SKIPCLS, ops.MAP_PATCH)}[pair]
+    rows = {ops.MAP_IDENT: Bc * S, ops.MAP_SPATIAL: Bc * T * (HW + 1), ops.MAP_SKIPCLS: Bc * L, ops.MAP_PATCH: Bc * L}
+    M, M2 = rows[lmap], rows[emap]
+    rs_div = {ops.MAP_SPATIAL: HW + 1, ops.MAP_IDENT: S}.get(emap, 0)
+    x, x_cls, w = _rand(Bc, S, D, seed=1), _rand(Bc, S, D, seed=2), _rand(D, seed=3)
+    dy = _rand(M, D, seed=4, dtype=dt)
+    stats = torch.empty(M, 2, device="cuda")
+    y = torch.empty(M, D, device="cuda", dtype=dt)
+    ops.layernorm_fwd(x, w, _rand(D, seed=5), y, stats, M, D, 1e-6, lmap, x_cls=x_cls, T=T, HW=HW)
+    for use_rs in ([False, True] if rs_div else [False]):
+        rowscale = (torch.rand(M2 // rs_div, device="cuda") > 0.3).float() / 0.7 if use_rs else None
+        res = []
+        for fused in (False, True):
+            dx = _rand(Bc, S, D, seed=6)
+            dw, db, cs = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda"), torch.full((D,), 0.5, device="cuda")
+            out = torch.full((M2, D), float("nan"), device="cuda", dtype=dt)
+            emit = (out, emap, rowscale, rs_div, cs) if fused else None
+            ops.layernorm_bwd(dy, x, w, stats, dx, dw, db, M, D, lmap, x_cls=x_cls, T=T, HW=HW, emit=emit)
+            if not fused:
+                ops.gather_cast(dx, out, M2, D, emap, rowscale=rowscale, rs_div=rs_div, T=T, HW=HW, colsum=cs)
+            torch.cuda.synchronize()
+            res.append((dx, dw, db, out, cs))
+        (dx0, dw0, db0, out0, cs0), (dx1, dw1, db1, out1, cs1) = res
+        assert not torch.isnan(out1.float()).any()
+        if lmap == ops.MAP_SPATIAL:      # the cls rows are accumulated with atomics: order-dependent in the last bits
+            torch.testing.assert_close(dx1, dx0, rtol=1e-5, atol=1e-5)
+        else:
+            assert torch.equal(dx1, dx0)
+        assert torch.equal(out1, out0)
+        assert _report(f"emit colsum {pair}", cs1, cs0)[1] < 1e-5
+        assert _report("emit dw", dw1, dw0)[1] < 1e-5 and _report("emit db", db1, db0)[1] < 1e-5
+    with pytest.raises(RuntimeError, match="cannot emit"):
+        ops.layernorm_bwd(dy, x, w, stats, dx, dw, db, M, D, lmap, x_cls=x_cls, T=T, HW=HW, emit=(out, ops.MAP_CLS, None, 0, None))
