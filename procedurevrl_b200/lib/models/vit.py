@@ -218,21 +218,27 @@ class VisionTransformer(nn.Module):
             return self.fixed_drop_scales
         if not self.training or max(self.dpr) == 0.0:
             return None
-        out = []
-        for r in self.dpr:
-            if r == 0.0:
-                out.append(None)
-                continue
-            keep = 1.0 - r
-            if self.attention_type != "divided_space_time":      # plain blocks: one row per sequence of the view (vit.py:125-126)
-                n = Bc * T if self.attention_type == "space_only" else Bc
-                s = torch.floor(keep + torch.rand(2 * n, device=dev)) / keep
-                out.append({"attn": s[:n].contiguous(), "mlp": s[n:].contiguous()})
-                continue
-            u = torch.rand(Bc * HW + Bc * T + Bc, device=dev)
-            s = torch.floor(keep + u) / keep
-            out.append({"temporal": s[:Bc * HW].contiguous(), "spatial": s[Bc * HW:Bc * HW + Bc * T].contiguous(),
-                        "mlp": s[Bc * HW + Bc * T:].contiguous()})
+        # one draw for all blocks (4 tiny kernels per step instead of 4 per block); block i's slice = its rows in view order
+        plain = self.attention_type != "divided_space_time"
+        if plain:       # plain blocks: one row per sequence of the view (vit.py:125-126)
+            n = Bc * T if self.attention_type == "space_only" else Bc
+            parts = (("attn", n), ("mlp", n))
+        else:
+            parts = (("temporal", Bc * HW), ("spatial", Bc * T), ("mlp", Bc))
+        per_block = sum(n for _, n in parts)
+        live = [i for i, r in enumerate(self.dpr) if r != 0.0]
+        key = (per_block, len(live), str(dev))
+        if getattr(self, "_keep_key", None) != key:
+            self._keep_vec = torch.tensor([1.0 - self.dpr[i] for i in live], device=dev).repeat_interleave(per_block)
+            self._keep_key = key
+        s = torch.floor(self._keep_vec + torch.rand(per_block * len(live), device=dev)) / self._keep_vec
+        out, off = [None] * len(self.dpr), 0
+        for i in live:
+            d = {}
+            for name, n in parts:
+                d[name] = s[off:off + n]
+                off += n
+            out[i] = d
         return out
 
     def forward_features(self, x):

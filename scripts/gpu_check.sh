@@ -6,7 +6,14 @@ timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 timeout 400 python bench.py > gpurun_out/bench.log 2>&1; tail -n 1 gpurun_out/bench.log
 timeout 400 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.log 2>&1; tail -n 1 gpurun_out/bench_ref.log
+# launch list of the steady-state step (durations only; absolute times under ncu are serialised, the SHARES are what count)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none --csv --log-file gpurun_out/launches.csv python bench.py --profile --steps 1 > gpurun_out/ncu_launch.log 2>&1
+# full-set captures inside the real step: GEMMs; the HBM-bound kernels added last (LayerNorm backward + emit, flat AdamW,
+# weight cast); the 9..32-frame temporal attention at T = 32
 timeout 600 ncu --set full --clock-control none -k regex:gemm -s 300 -c 14 --csv --page raw --log-file gpurun_out/prof_gemm_raw.csv python bench.py --profile --steps 1 > gpurun_out/ncu_gemm.log 2>&1
+timeout 600 ncu --set full --clock-control none -k "regex:layernorm_bwd|adam_flat|cast_weight_multi" -s 38 -c 6 --csv --page raw --log-file gpurun_out/prof_hbm_raw.csv python bench.py --profile --steps 1 > gpurun_out/ncu_hbm.log 2>&1
+timeout 600 ncu --set full --clock-control none -k regex:attn_t32 -s 10 -c 4 --csv --page raw --log-file gpurun_out/prof_t32_raw.csv python bench.py --frames 32 --profile --steps 1 > gpurun_out/ncu_t32.log 2>&1
 python scripts/summarize_launches.py gpurun_out/launches.csv | head -30
 python scripts/summarize_ncu_raw.py gpurun_out/prof_gemm_raw.csv | cut -c1-200
+python scripts/summarize_ncu_raw.py gpurun_out/prof_hbm_raw.csv | cut -c1-200
+python scripts/summarize_ncu_raw.py gpurun_out/prof_t32_raw.csv | cut -c1-200
