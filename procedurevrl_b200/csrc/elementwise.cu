@@ -159,9 +159,24 @@ struct LnEmit {
 };
 
 // emit dx row `xr` (values v, this lane's columns) to every row of em.map that addresses it
-template <typename OutT, int NVEC>
+// Column-sum accumulation of the LayerNorm backward.  SMEM = false: per-lane registers (folded through shared memory at the
+// end of the kernel); SMEM = true: straight into the block's shared accumulators, laid out [component j][float4 index q]
+// (column 4q + j) so that a warp's 32 adds hit 32 different banks -- 72 fewer live registers at D = 768, which is what
+// lets two blocks (16 warps) share an SM.
+template <bool SMEM, int NVEC>
+__device__ __forceinline__ void ln_acc(float4 (&reg)[NVEC], float* sm, int i, int lane, float a, float b, float c, float d) {
+  if constexpr (SMEM) {
+    constexpr int Q = NVEC * 32;
+    float* p = sm + i * 32 + lane;
+    atomicAdd(p, a), atomicAdd(p + Q, b), atomicAdd(p + 2 * Q, c), atomicAdd(p + 3 * Q, d);
+  } else {
+    reg[i].x += a, reg[i].y += b, reg[i].z += c, reg[i].w += d;
+  }
+}
+
+template <typename OutT, int NVEC, bool SMEM>
 __device__ __forceinline__ void ln_emit_row(const LnEmit& em, const Geom& g, long long xr, const float4 (&v)[NVEC],
-                                            float4 (&ec)[NVEC], int lane) {
+                                            float4 (&ec)[NVEC], float* sm_ec, int lane) {
   constexpr int D = NVEC * 128;
   const int xi = static_cast<int>(xr);      // residual-stream rows fit 31 bits (checked by the host: M is an int)
   const int b = xi / g.S, pos = xi - b * g.S;
@@ -189,13 +204,13 @@ __device__ __forceinline__ void ln_emit_row(const LnEmit& em, const Geom& g, lon
     for (int i = 0; i < NVEC; ++i) {
       const float4 o = make_float4(v[i].x * f, v[i].y * f, v[i].z * f, v[i].w * f);
       store4<OutT>(out + m2 * D + (i * 32 + lane) * 4, o.x, o.y, o.z, o.w);
-      ec[i].x += o.x, ec[i].y += o.y, ec[i].z += o.z, ec[i].w += o.w;
+      ln_acc<SMEM, NVEC>(ec, sm_ec, i, lane, o.x, o.y, o.z, o.w);
     }
   }
 }
 
-template <typename InT, int NVEC, bool EMIT>
-__global__ void __launch_bounds__(LN_WARPS * 32, NVEC <= 4 ? 2 : 1)
+template <typename InT, int NVEC, bool EMIT, bool SMEM>
+__global__ void __launch_bounds__(LN_WARPS * 32, (SMEM || NVEC <= 4) ? 2 : 1)
 layernorm_bwd_kernel(const InT* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ x_cls,
                      const float* __restrict__ w, const float* __restrict__ stats, float* __restrict__ dx,
                      float* __restrict__ dw, float* __restrict__ db, int M, int map, Geom g, LnEmit em) {
@@ -217,7 +232,7 @@ layernorm_bwd_kernel(const InT* __restrict__ dy, const float* __restrict__ x, co
       float4 cur[NVEC];
 #pragma unroll
       for (int i = 0; i < NVEC; ++i) cur[i] = *(reinterpret_cast<const float4*>(dx + xr * D) + i * 32 + lane);
-      ln_emit_row<InT, NVEC>(em, g, xr, cur, ec, lane);
+      ln_emit_row<InT, NVEC, SMEM>(em, g, xr, cur, ec, sacc + 2 * D, lane);
     }
   }
   // last row first: dy was just written by a GEMM whose final tiles are still in L2, and the gather that follows reads
@@ -244,9 +259,8 @@ layernorm_bwd_kernel(const InT* __restrict__ dy, const float* __restrict__ x, co
       const float4 d = gg[i];
       xh[i] = make_float4((xh[i].x - st.x) * st.y, (xh[i].y - st.x) * st.y, (xh[i].z - st.x) * st.y,
                           (xh[i].w - st.x) * st.y);
-      aw[i].x = fmaf(d.x, xh[i].x, aw[i].x), aw[i].y = fmaf(d.y, xh[i].y, aw[i].y);
-      aw[i].z = fmaf(d.z, xh[i].z, aw[i].z), aw[i].w = fmaf(d.w, xh[i].w, aw[i].w);
-      ab[i].x += d.x, ab[i].y += d.y, ab[i].z += d.z, ab[i].w += d.w;
+      ln_acc<SMEM, NVEC>(aw, sacc, i, lane, d.x * xh[i].x, d.y * xh[i].y, d.z * xh[i].z, d.w * xh[i].w);
+      ln_acc<SMEM, NVEC>(ab, sacc + D, i, lane, d.x, d.y, d.z, d.w);
       gg[i] = make_float4(d.x * wv.x, d.y * wv.y, d.z * wv.z, d.w * wv.w);
       s1 += gg[i].x + gg[i].y + gg[i].z + gg[i].w;
       s2 += gg[i].x * xh[i].x + gg[i].y * xh[i].y + gg[i].z * xh[i].z + gg[i].w * xh[i].w;
@@ -265,47 +279,66 @@ layernorm_bwd_kernel(const InT* __restrict__ dy, const float* __restrict__ x, co
       }
     }
     if constexpr (EMIT) {
-      if (!cls) ln_emit_row<InT, NVEC>(em, g, xr, cur, ec, lane);
+      if (!cls) ln_emit_row<InT, NVEC, SMEM>(em, g, xr, cur, ec, sacc + 2 * D, lane);
     }
   }
-#pragma unroll
-  for (int i = 0; i < NVEC; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    atomicAdd(&sacc[c], aw[i].x), atomicAdd(&sacc[c + 1], aw[i].y), atomicAdd(&sacc[c + 2], aw[i].z),
-        atomicAdd(&sacc[c + 3], aw[i].w);
-    atomicAdd(&sacc[D + c], ab[i].x), atomicAdd(&sacc[D + c + 1], ab[i].y), atomicAdd(&sacc[D + c + 2], ab[i].z),
-        atomicAdd(&sacc[D + c + 3], ab[i].w);
-  }
-  if (EMIT && em.colsum != nullptr) {
+  if constexpr (!SMEM) {
 #pragma unroll
     for (int i = 0; i < NVEC; ++i) {
       const int c = (i * 32 + lane) * 4;
-      atomicAdd(&sacc[2 * D + c], ec[i].x), atomicAdd(&sacc[2 * D + c + 1], ec[i].y);
-      atomicAdd(&sacc[2 * D + c + 2], ec[i].z), atomicAdd(&sacc[2 * D + c + 3], ec[i].w);
+      atomicAdd(&sacc[c], aw[i].x), atomicAdd(&sacc[c + 1], aw[i].y), atomicAdd(&sacc[c + 2], aw[i].z),
+          atomicAdd(&sacc[c + 3], aw[i].w);
+      atomicAdd(&sacc[D + c], ab[i].x), atomicAdd(&sacc[D + c + 1], ab[i].y), atomicAdd(&sacc[D + c + 2], ab[i].z),
+          atomicAdd(&sacc[D + c + 3], ab[i].w);
+    }
+    if (EMIT && em.colsum != nullptr) {
+#pragma unroll
+      for (int i = 0; i < NVEC; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        atomicAdd(&sacc[2 * D + c], ec[i].x), atomicAdd(&sacc[2 * D + c + 1], ec[i].y);
+        atomicAdd(&sacc[2 * D + c + 2], ec[i].z), atomicAdd(&sacc[2 * D + c + 3], ec[i].w);
+      }
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < D; i += blockDim.x) {
-    if (dw != nullptr) atomicAdd(dw + i, sacc[i]);
-    if (db != nullptr) atomicAdd(db + i, sacc[D + i]);
-    if (EMIT && em.colsum != nullptr) atomicAdd(em.colsum + i, sacc[2 * D + i]);
+    const int at = SMEM ? (i & 3) * (D / 4) + (i >> 2) : i;      // where column i's sum sits (see ln_acc)
+    if (dw != nullptr) atomicAdd(dw + i, sacc[at]);
+    if (db != nullptr) atomicAdd(db + i, sacc[D + at]);
+    if (EMIT && em.colsum != nullptr) atomicAdd(em.colsum + i, sacc[2 * D + at]);
   }
+}
+
+// PVRL_LN_SMEM_ACC=0 selects the register-accumulator variant (one 8-warp block per SM at D = 768)
+inline bool ln_smem_acc() {
+  static const bool on = [] {
+    const char* e = getenv("PVRL_LN_SMEM_ACC");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  return on;
+}
+
+template <typename InT, bool EMIT, bool SMEM>
+int layernorm_bwd_launch2(const void* dy, const float* x, const float* x_cls, const float* w, const float* stats,
+                          float* dx, float* dw, float* db, int M, int D, int map, Geom gg, LnEmit em, cudaStream_t stream) {
+  int grid = (M + LN_WARPS - 1) / LN_WARPS;
+  if (grid > 148 * 2) grid = 148 * 2;   // persistent row loop; 1-2 blocks are resident per SM (register-bound)
+  const InT* d = static_cast<const InT*>(dy);
+  switch (D / 128) {
+    case 2: launch_pdl(layernorm_bwd_kernel<InT, 2, EMIT, SMEM>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, d, x, x_cls, w, stats, dx, dw, db, M, map, gg, em); break;
+    case 4: launch_pdl(layernorm_bwd_kernel<InT, 4, EMIT, SMEM>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, d, x, x_cls, w, stats, dx, dw, db, M, map, gg, em); break;
+    case 6: launch_pdl(layernorm_bwd_kernel<InT, 6, EMIT, SMEM>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, d, x, x_cls, w, stats, dx, dw, db, M, map, gg, em); break;
+    case 8: launch_pdl(layernorm_bwd_kernel<InT, 8, EMIT, SMEM>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, d, x, x_cls, w, stats, dx, dw, db, M, map, gg, em); break;
+    default: return fail(-1, "pvrl_layernorm_bwd: D=%d not in {256, 512, 768, 1024}", D);
+  }
+  return launched("layernorm_bwd_kernel");
 }
 
 template <typename InT, bool EMIT>
 int layernorm_bwd_launch(const void* dy, const float* x, const float* x_cls, const float* w, const float* stats,
                          float* dx, float* dw, float* db, int M, int D, int map, Geom gg, LnEmit em, cudaStream_t stream) {
-  int grid = (M + LN_WARPS - 1) / LN_WARPS;
-  if (grid > 148 * 2) grid = 148 * 2;   // persistent row loop; 1-2 blocks are resident per SM (register-bound)
-  const InT* d = static_cast<const InT*>(dy);
-  switch (D / 128) {
-    case 2: launch_pdl(layernorm_bwd_kernel<InT, 2, EMIT>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, d, x, x_cls, w, stats, dx, dw, db, M, map, gg, em); break;
-    case 4: launch_pdl(layernorm_bwd_kernel<InT, 4, EMIT>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, d, x, x_cls, w, stats, dx, dw, db, M, map, gg, em); break;
-    case 6: launch_pdl(layernorm_bwd_kernel<InT, 6, EMIT>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, d, x, x_cls, w, stats, dx, dw, db, M, map, gg, em); break;
-    case 8: launch_pdl(layernorm_bwd_kernel<InT, 8, EMIT>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, d, x, x_cls, w, stats, dx, dw, db, M, map, gg, em); break;
-    default: return fail(-1, "pvrl_layernorm_bwd: D=%d not in {256, 512, 768, 1024}", D);
-  }
-  return launched("layernorm_bwd_kernel");
+  return ln_smem_acc() ? layernorm_bwd_launch2<InT, EMIT, true>(dy, x, x_cls, w, stats, dx, dw, db, M, D, map, gg, em, stream)
+                       : layernorm_bwd_launch2<InT, EMIT, false>(dy, x, x_cls, w, stats, dx, dw, db, M, D, map, gg, em, stream);
 }
 
 // ---------------------------------------------------------------------------------------- gather + cast

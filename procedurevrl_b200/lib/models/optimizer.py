@@ -129,7 +129,10 @@ class FlatOptimizer:
 
     Layout: trainable parameters of group 0, then group 1, ... in the order given; `offsets[i] = (start, end)` of
     parameter i (torch.optim's numbering) inside `flat_param` / `flat_grad` / the state buffers.  Frozen parameters
-    (`requires_grad == False` at construction) are left alone, as torch leaves parameters without `.grad`."""
+    (`requires_grad == False` at construction) are left alone, as torch leaves parameters without `.grad`.
+    One deliberate difference: gradients are views that are cleared, never dropped, so a trainable parameter that the
+    backward does not reach is updated with a zero gradient (it still sees weight decay and its moments decay) where
+    torch would skip it; setting `p.grad = None` before `step()` restores torch's behaviour for that step."""
 
     def __init__(self, groups, method="adamw", lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, momentum=0.0,
                  dampening=0.0, nesterov=False):

@@ -85,6 +85,7 @@ class DiffusionTransformer(nn.Module):
         self.register_buffer("sqrt_alphas_cumprod", torch.sqrt(ac), persistent=False)
         self.register_buffer("sqrt_one_minus_alphas_cumprod", torch.sqrt(1.0 - ac), persistent=False)
         self._sqrt_ac, self._sqrt_1mac = torch.sqrt(ac).tolist(), torch.sqrt(1.0 - ac).tolist()   # host copies: no sync
+        self.grad_into_params = False   # trainer.PretrainStep: block gradients accumulate straight into the flat .grad views
         self.fixed_draws = None      # tests inject (mask_inds, pad_start, noise[levels,B,C]) to replay the reference's draws
 
     def initialize_parameters(self):
@@ -139,7 +140,7 @@ class DiffusionTransformer(nn.Module):
         inter = order_levels(self.temporalModelling.resblocks, x, tvecs, self.type_embedding.weight,
                              self.temporalEmbedding.weight[:S], self.pad_embedding.weight, x0.detach(),
                              noise.float().contiguous(), mask_inds, pad_start, B, S, self.tfm_heads, coef,
-                             eps=self.temporalModelling.resblocks[0].ln_1.eps)
+                             eps=self.temporalModelling.resblocks[0].ln_1.eps, grad_into_params=self.grad_into_params)
         den = inter[(L - 1) * B:]
         x0_target = x0.unsqueeze(0).expand(self.total_levels, -1, -1).reshape(-1, C)
         return den, mask_inds, [x0_target, inter], inter

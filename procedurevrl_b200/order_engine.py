@@ -79,7 +79,8 @@ class OrderLevels(torch.autograd.Function):
         f32 = dict(device=dev, dtype=torch.float32)
         d_inter = d_inter.contiguous().float()
         # one zero-filled buffer for everything the kernels accumulate into
-        sizes = [M * C, 2 * C, S * C, C, LM * C] + [int(torch.Size(s).numel()) for s in pshapes]
+        sink = cfg.get("sink")                           # the parameters' own .grad buffers: the kernels accumulate in place
+        sizes = [M * C, 2 * C, S * C, C, LM * C] + ([] if sink is not None else [int(torch.Size(s).numel()) for s in pshapes])
         flat = torch.zeros(sum(sizes), **f32)
         views, off = [], 0
         for sz in sizes:
@@ -87,7 +88,7 @@ class OrderLevels(torch.autograd.Function):
             off += sz
         dvideo, dtype, dpos, dpad = views[0].view(M, C), views[1].view(2, C), views[2].view(S, C), views[3].view(1, C)
         dh = views[4].view(LM, C)                        # gradient w.r.t. the block outputs of all levels, rows as saved
-        G = [v.view(s) for v, s in zip(views[5:], pshapes)]
+        G = sink if sink is not None else [v.view(s) for v, s in zip(views[5:], pshapes)]
         rows_all = (mask_rows.unsqueeze(0) + torch.arange(L, device=dev).unsqueeze(1) * M).reshape(-1)
         dh.index_copy_(0, rows_all, d_inter)
         for i in reversed(range(nblk)):
@@ -119,15 +120,22 @@ class OrderLevels(torch.autograd.Function):
         for lvl in range(L):
             ops.ot_embed_bwd(dh[lvl * M:(lvl + 1) * M], mask_inds, pad_start, dvideo, dtype, dpos, dpad, dtvecs[lvl], B, S)
         ctx.saved = None
+        if sink is not None:
+            return (None, dvideo, dtvecs, dtype, dpos, dpad, None, None, None, None) + (None,) * len(pshapes)
         return (None, dvideo, dtvecs, dtype, dpos, dpad, None, None, None, None) + tuple(G)
 
 
 def order_levels(blocks, video, tvecs, type_w, pos_w, pad_w, x0, noise, mask_inds, pad_start, B, S, heads, coef,
-                 eps=1e-5):
-    """blocks: the ResidualAttentionBlock modules (parameter containers); returns inter [L*B, C]."""
+                 eps=1e-5, grad_into_params=False):
+    """blocks: the ResidualAttentionBlock modules (parameter containers); returns inter [L*B, C].
+    grad_into_params: the backward accumulates the block parameters' gradients straight into their existing `.grad`
+    buffers (trainer.PretrainStep: views of the flat gradient) instead of returning 48 tensors for autograd to add."""
     params = []
     for blk in blocks:
         sd = dict(blk.named_parameters())
         params += [sd[n] for n in BLOCK_PARAMS]
     cfg = dict(B=B, S=S, heads=heads, eps=eps, coef=coef)
+    if grad_into_params and torch.is_grad_enabled():
+        cfg["sink"] = [p.grad for p in params]
+        assert all(g is not None and g.is_contiguous() and g.dtype == torch.float32 for g in cfg["sink"])
     return OrderLevels.apply(cfg, video, tvecs, type_w, pos_w, pad_w, x0, noise, mask_inds, pad_start, *params)

@@ -39,7 +39,8 @@ def bucket_ranges(named_sizes, depth, blocks_per_bucket):
 
 
 class PretrainStep:
-    def __init__(self, model, cfg, lr=5e-5, weight_decay=1e-4, process_group=None, use_graph=True, optimizer=None):
+    def __init__(self, model, cfg, lr=5e-5, weight_decay=1e-4, process_group=None, use_graph=True, optimizer=None,
+                 accum_steps=1):
         self.model = model
         self.inner = model.model                         # VisionTransformer mirror
         self.cfg = cfg
@@ -53,11 +54,20 @@ class PretrainStep:
         self.opt = optimizer if optimizer is not None else \
             FlatOptimizer([{"params": self.params, "lr_mult": 1.0}], "adamw", lr=lr, weight_decay=weight_decay)
         self.flat_grad = self.opt.flat_grad
-        self.opt.grad_scale = 1.0
+        # Gradient accumulation (train_net.py:99-100,182-192: GLOBAL_BATCH_SIZE // (NUM_SHARDS * TRAIN.BATCH_SIZE) micro-steps,
+        # `p.grad /= num_iters`, then step + zero_grad): the dW kernels accumulate across micro-steps by construction,
+        # the division rides in the optimizer pass (grad_scale), and -- unlike the reference's DDP, which all-reduces on
+        # every micro-step -- the replicas exchange the accumulated gradient once, before the update (same mean).
+        self.accum_steps = int(accum_steps)
+        assert self.accum_steps >= 1
+        self.opt.grad_scale = 1.0 / self.accum_steps
+        self._micro = 0
         eng = self.inner.engine()
         by_name = dict(self.inner.named_parameters())
         eng.grad_sink = {n: by_name[n].grad for n in eng.grad_names}
         assert all(g is not None for g in eng.grad_sink.values()), "every encoder parameter must be trainable here"
+        if getattr(self.inner, "order_tfm", None) is not None:
+            self.inner.order_tfm.grad_into_params = True      # same for the order transformer's 48 block parameters
         # Data-parallel gradient exchange (the only collective).  Default: ONE NCCL all-reduce of the flat buffer
         # after the backward (measured on 2 B200s: 34.4 ms/step).  PVRL_AR_BLOCKS_PER_BUCKET = n > 0 instead exchanges
         # buckets of n encoder blocks on a side stream as soon as the backward has finished them (part of the captured
@@ -84,11 +94,15 @@ class PretrainStep:
         with torch.cuda.stream(self._ar_stream):
             torch.distributed.all_reduce(self.flat_grad[rng[0]:rng[1]], op=torch.distributed.ReduceOp.AVG, group=self.pg)
 
-    def _eager(self, frames, meta):
-        self.inner.engine().invalidate_weights()     # flat_grad is clean: zero-initialised / cleared by the previous update
+    def _eager(self, frames, meta, update=True):
+        """One micro-step: forward, loss, backward (gradients accumulate into flat_grad); with `update`, also the
+        gradient exchange and the optimizer pass, which leaves flat_grad cleared for the next backward."""
+        self.inner.engine().invalidate_weights()     # flat_grad is clean or holds the earlier micro-steps' sum
         pred, teacher, mse = self.model([frames, meta])
         loss, _, _ = PF.pretrain_loss(pred, teacher, mse, topk=self.topk)
         loss.backward()
+        if not update:
+            return loss.detach()
         if self.world > 1:
             if self._ar_ranges is None:
                 torch.distributed.all_reduce(self.flat_grad, op=torch.distributed.ReduceOp.AVG, group=self.pg)
@@ -101,7 +115,10 @@ class PretrainStep:
         return loss.detach()
 
     def capture(self, frames, meta, warmup=3):
-        """Warm up on a side stream, then record one step into a CUDA graph with `frames` / `meta` as static inputs."""
+        """Warm up on a side stream, then record one step into a CUDA graph with `frames` / `meta` as static inputs
+        (with accumulation: a second graph of the update-free micro-step)."""
+        assert not (self.accum_steps > 1 and self._ar_ranges is not None), \
+            "bucketed exchange during the backward and gradient accumulation are not combined"
         self.static = (frames, meta)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -113,14 +130,27 @@ class PretrainStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.static_loss = self._eager(frames, meta)
+        self.micro_graph = None
+        if self.accum_steps > 1:
+            self.micro_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.micro_graph, pool=self.graph.pool()):
+                self.static_micro_loss = self._eager(frames, meta, update=False)
         return self
 
     def __call__(self, frames=None, meta=None):
-        """Run one step.  With a captured graph, `frames` (if given) is copied into the static input buffer."""
+        """Run one (micro-)step; every `accum_steps`-th call exchanges the gradients and updates the parameters.  With a
+        captured graph, `frames` (if given) is copied into the static input buffer."""
+        self._micro += 1
+        update = self._micro % self.accum_steps == 0
         if self.graph is None:
-            return self._eager(frames, meta)
+            if update:
+                self.opt.sync_hyper()
+            return self._eager(frames, meta, update)
         if frames is not None and frames.data_ptr() != self.static[0].data_ptr():
             self.static[0].copy_(frames, non_blocking=True)
+        if not update:
+            self.micro_graph.replay()
+            return self.static_micro_loss
         self.opt.sync_hyper()                       # learning-rate changes reach the graph through a device scalar
         self.graph.replay()
         return self.static_loss
