@@ -209,10 +209,11 @@ int pvrl_softmax_rows(const float* x, float* y, int32_t M, int32_t K, void* stre
 
 /* y[M,N] = (resid ? resid : 0) + prologue(x)[M,K] W[N,K]^T + bias.  x_mode 0: x; 1: LayerNorm(x) with ln_w/ln_b/eps
  * (also writes xhat[M,K] and rstd[M] when non-NULL, for pvrl_ot_ln_bwd / pvrl_ot_linear_dw); 2: QuickGELU(x)
- * (tfm_model.py:27-29).  K % 128 == 0, K <= 2048. */
+ * (tfm_model.py:27-29).  act_out (NULL or [M,N]) also receives QuickGELU(y): the input of the next Linear and of its dW,
+ * computed once.  K % 128 == 0, K <= 2048. */
 int pvrl_ot_linear_fwd(const float* x, int32_t x_mode, const float* ln_w, const float* ln_b, float eps, float* xhat_out,
-                       float* rstd_out, const float* W, const float* bias, const float* resid, float* y, int32_t M,
-                       int32_t N, int32_t K, void* stream);
+                       float* rstd_out, const float* W, const float* bias, const float* resid, float* y, float* act_out,
+                       int32_t M, int32_t N, int32_t K, void* stream);
 /* dA[M,K] = dY[M,N] W[N,K], times QuickGELU'(pre[M,K]) when pre != NULL. */
 int pvrl_ot_linear_dx(const float* dY, const float* W, const float* pre, float* dA, int32_t M, int32_t N, int32_t K,
                       void* stream);

@@ -160,15 +160,16 @@ struct LnEmit {
 
 // emit dx row `xr` (values v, this lane's columns) to every row of em.map that addresses it
 // Column-sum accumulation of the LayerNorm backward.  SMEM = false: per-lane registers (folded through shared memory at the
-// end of the kernel); SMEM = true: straight into the block's shared accumulators, laid out [component j][float4 index q]
-// (column 4q + j) so that a warp's 32 adds hit 32 different banks -- 72 fewer live registers at D = 768, which is what
-// lets two blocks (16 warps) share an SM.
+// end of the kernel).  SMEM = true: a warp-private slice of shared memory, read-modify-written as whole float4s (lane-
+// contiguous: conflict-free, no atomics) -- 72 fewer live registers at D = 768, which lets two blocks (16 warps) share an
+// SM.  (Shared-memory fp32 atomics into one block-wide copy were measured first: 83 us against 71 us with registers.)
 template <bool SMEM, int NVEC>
 __device__ __forceinline__ void ln_acc(float4 (&reg)[NVEC], float* sm, int i, int lane, float a, float b, float c, float d) {
   if constexpr (SMEM) {
-    constexpr int Q = NVEC * 32;
-    float* p = sm + i * 32 + lane;
-    atomicAdd(p, a), atomicAdd(p + Q, b), atomicAdd(p + 2 * Q, c), atomicAdd(p + 3 * Q, d);
+    float4* p = reinterpret_cast<float4*>(sm) + i * 32 + lane;
+    float4 v = *p;
+    v.x += a, v.y += b, v.z += c, v.w += d;
+    *p = v;
   } else {
     reg[i].x += a, reg[i].y += b, reg[i].z += c, reg[i].w += d;
   }
@@ -217,10 +218,19 @@ layernorm_bwd_kernel(const InT* __restrict__ dy, const float* __restrict__ x, co
   if (PDL_EARLY_TRIGGER) pdl_launch_dependents();
   pdl_wait();
   constexpr int D = NVEC * 128;
-  __shared__ float sacc[(EMIT ? 3 : 2) * D];
-  for (int i = threadIdx.x; i < (EMIT ? 3 : 2) * D; i += blockDim.x) sacc[i] = 0.f;
-  __syncthreads();
+  constexpr int NACC = EMIT ? 3 : 2;
+  // SMEM: [LN_WARPS][NACC][D] warp-private accumulators (dynamic); otherwise one [NACC][D] block-wide copy for the final fold
+  extern __shared__ __align__(16) float sdyn[];
+  __shared__ float sstat[SMEM ? 1 : NACC * D];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* sacc = SMEM ? sdyn + warp * NACC * D : sstat;
+  if constexpr (SMEM) {
+    for (int i = lane; i < NACC * D / 4; i += 32) reinterpret_cast<float4*>(sacc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+  } else {
+    for (int i = threadIdx.x; i < NACC * D; i += blockDim.x) sstat[i] = 0.f;
+    __syncthreads();
+  }
   float4 aw[NVEC], ab[NVEC], ec[NVEC];   // ec: column sums of the emitted rows (dead code without EMIT)
 #pragma unroll
   for (int i = 0; i < NVEC; ++i) aw[i] = make_float4(0.f, 0.f, 0.f, 0.f), ab[i] = aw[i];
@@ -302,20 +312,45 @@ layernorm_bwd_kernel(const InT* __restrict__ dy, const float* __restrict__ x, co
   }
   __syncthreads();
   for (int i = threadIdx.x; i < D; i += blockDim.x) {
-    const int at = SMEM ? (i & 3) * (D / 4) + (i >> 2) : i;      // where column i's sum sits (see ln_acc)
-    if (dw != nullptr) atomicAdd(dw + i, sacc[at]);
-    if (db != nullptr) atomicAdd(db + i, sacc[D + at]);
-    if (EMIT && em.colsum != nullptr) atomicAdd(em.colsum + i, sacc[2 * D + at]);
+    float s[3] = {0.f, 0.f, 0.f};
+    if constexpr (SMEM) {
+      for (int wv = 0; wv < LN_WARPS; ++wv)
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) s[k] += sdyn[(wv * NACC + k) * D + i];
+    } else {
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) s[k] = sstat[k * D + i];
+    }
+    if (dw != nullptr) atomicAdd(dw + i, s[0]);
+    if (db != nullptr) atomicAdd(db + i, s[1]);
+    if (EMIT && em.colsum != nullptr) atomicAdd(em.colsum + i, s[2]);
   }
 }
 
-// PVRL_LN_SMEM_ACC=0 selects the register-accumulator variant (one 8-warp block per SM at D = 768)
+// Default: column sums in warp-private shared memory (128 registers, two 8-warp blocks per SM: 53.7 us per launch at the
+// bench shape); PVRL_LN_SMEM_ACC=0 keeps them in registers (254 registers, one block per SM: 71.3 us)
 inline bool ln_smem_acc() {
   static const bool on = [] {
     const char* e = getenv("PVRL_LN_SMEM_ACC");
     return e == nullptr || atoi(e) != 0;
   }();
   return on;
+}
+
+template <typename InT, int NVEC, bool EMIT, bool SMEM>
+int layernorm_bwd_launch3(const InT* d, const float* x, const float* x_cls, const float* w, const float* stats, float* dx,
+                          float* dw, float* db, int M, int map, Geom gg, LnEmit em, int grid, cudaStream_t stream) {
+  const size_t smem = SMEM ? sizeof(float) * LN_WARPS * (EMIT ? 3 : 2) * NVEC * 128 : 0;
+  auto kern = layernorm_bwd_kernel<InT, NVEC, EMIT, SMEM>;
+  if (smem > 48 * 1024) {
+    static bool configured = false;      // one flag per instantiation
+    if (!configured) {
+      PVRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      configured = true;
+    }
+  }
+  PVRL_CUDA(launch_pdl(kern, dim3(grid), dim3(LN_WARPS * 32), smem, stream, d, x, x_cls, w, stats, dx, dw, db, M, map, gg, em));
+  return launched("layernorm_bwd_kernel");
 }
 
 template <typename InT, bool EMIT, bool SMEM>
@@ -325,13 +360,12 @@ int layernorm_bwd_launch2(const void* dy, const float* x, const float* x_cls, co
   if (grid > 148 * 2) grid = 148 * 2;   // persistent row loop; 1-2 blocks are resident per SM (register-bound)
   const InT* d = static_cast<const InT*>(dy);
   switch (D / 128) {
-    case 2: launch_pdl(layernorm_bwd_kernel<InT, 2, EMIT, SMEM>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, d, x, x_cls, w, stats, dx, dw, db, M, map, gg, em); break;
-    case 4: launch_pdl(layernorm_bwd_kernel<InT, 4, EMIT, SMEM>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, d, x, x_cls, w, stats, dx, dw, db, M, map, gg, em); break;
-    case 6: launch_pdl(layernorm_bwd_kernel<InT, 6, EMIT, SMEM>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, d, x, x_cls, w, stats, dx, dw, db, M, map, gg, em); break;
-    case 8: launch_pdl(layernorm_bwd_kernel<InT, 8, EMIT, SMEM>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, d, x, x_cls, w, stats, dx, dw, db, M, map, gg, em); break;
+    case 2: return layernorm_bwd_launch3<InT, 2, EMIT, SMEM>(d, x, x_cls, w, stats, dx, dw, db, M, map, gg, em, grid, stream);
+    case 4: return layernorm_bwd_launch3<InT, 4, EMIT, SMEM>(d, x, x_cls, w, stats, dx, dw, db, M, map, gg, em, grid, stream);
+    case 6: return layernorm_bwd_launch3<InT, 6, EMIT, SMEM>(d, x, x_cls, w, stats, dx, dw, db, M, map, gg, em, grid, stream);
+    case 8: return layernorm_bwd_launch3<InT, 8, EMIT, SMEM>(d, x, x_cls, w, stats, dx, dw, db, M, map, gg, em, grid, stream);
     default: return fail(-1, "pvrl_layernorm_bwd: D=%d not in {256, 512, 768, 1024}", D);
   }
-  return launched("layernorm_bwd_kernel");
 }
 
 template <typename InT, bool EMIT>

@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(OT_THREADS, KJ <= 4 ? 2 : 1)
 ot_linear_fwd_kernel(const float* __restrict__ x, int x_mode, const float* __restrict__ ln_w,
                      const float* __restrict__ ln_b, float eps, float* __restrict__ xhat_out,
                      float* __restrict__ rstd_out, const float* __restrict__ W, const float* __restrict__ bias,
-                     const float* __restrict__ resid, float* __restrict__ y, int M, int N, int K, int mt) {
+                     const float* __restrict__ resid, float* __restrict__ y, float* __restrict__ act_out, int M, int N,
+                     int K, int mt) {
   extern __shared__ __align__(16) float xs[];   // [mt][K]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * mt;
@@ -119,6 +120,9 @@ ot_linear_fwd_kernel(const float* __restrict__ x, int x_mode, const float* __res
     float v = acc[0] + (bias != nullptr ? __ldg(bias + n) : 0.f);
     if (resid != nullptr) v += resid[o];
     y[o] = v;
+    // QuickGELU(y) once, here, for the Linear that consumes it and for that Linear's dW -- not once per output column of
+    // the consumer (x_mode 2) and once per weight row of its dW (a_mode 2), where the exponentials dominated the kernels
+    if (act_out != nullptr) act_out[o] = quick_gelu(v);
   }
 }
 
@@ -402,7 +406,8 @@ using namespace pvrl;
 
 extern "C" int pvrl_ot_linear_fwd(const float* x, int32_t x_mode, const float* ln_w, const float* ln_b, float eps,
                                   float* xhat_out, float* rstd_out, const float* W, const float* bias,
-                                  const float* resid, float* y, int32_t M, int32_t N, int32_t K, void* stream) {
+                                  const float* resid, float* y, float* act_out, int32_t M, int32_t N, int32_t K,
+                                  void* stream) {
   PVRL_CHECK_ARG(x && W && y && M > 0 && N > 0 && K > 0, "pvrl_ot_linear_fwd: bad arguments");
   PVRL_CHECK_ARG(K % 128 == 0 && K <= OT_KMAX, "pvrl_ot_linear_fwd: K=%d must be a multiple of 128, <= 2048", K);
   PVRL_CHECK_ARG(x_mode >= 0 && x_mode <= 2, "pvrl_ot_linear_fwd: bad x_mode %d", x_mode);
@@ -421,10 +426,10 @@ extern "C" int pvrl_ot_linear_fwd(const float* x, int32_t x_mode, const float* l
   dim3 grid((N + 7) / 8, (M + mt - 1) / mt);
   if (K <= 512)
     ot_linear_fwd_kernel<4><<<grid, OT_THREADS, smem, STREAM>>>(x, x_mode, ln_w, ln_b, eps, xhat_out, rstd_out, W, bias,
-                                                                resid, y, M, N, K, mt);
+                                                                resid, y, act_out, M, N, K, mt);
   else
     ot_linear_fwd_kernel<16><<<grid, OT_THREADS, smem, STREAM>>>(x, x_mode, ln_w, ln_b, eps, xhat_out, rstd_out, W, bias,
-                                                                 resid, y, M, N, K, mt);
+                                                                 resid, y, act_out, M, N, K, mt);
   return launched("ot_linear_fwd_kernel");
 }
 

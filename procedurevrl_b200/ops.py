@@ -72,7 +72,7 @@ _SIGS = {
                           _c_void_p],
     "pvrl_softmax_rows": [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p],
     "pvrl_ot_linear_fwd": [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_float, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
-                           _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
+                           _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
     "pvrl_ot_linear_dx": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
     "pvrl_ot_linear_dw": [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int,
                           _c_void_p],
@@ -359,12 +359,13 @@ def _f32c(*ts):
         assert t is None or (t.dtype == torch.float32 and t.is_contiguous()), "order-transformer ops take contiguous fp32"
 
 
-def ot_linear_fwd(x, W, bias, y, x_mode=OT_X_PLAIN, ln_w=None, ln_b=None, eps=1e-5, xhat=None, rstd=None, resid=None):
+def ot_linear_fwd(x, W, bias, y, x_mode=OT_X_PLAIN, ln_w=None, ln_b=None, eps=1e-5, xhat=None, rstd=None, resid=None,
+                  act_out=None):
     M, K = x.shape
     N = W.shape[0]
-    _f32c(x, W, bias, y, ln_w, ln_b, xhat, rstd, resid)
+    _f32c(x, W, bias, y, ln_w, ln_b, xhat, rstd, resid, act_out)
     _check(lib().pvrl_ot_linear_fwd(_p(x), x_mode, _p(ln_w), _p(ln_b), eps, _p(xhat), _p(rstd), _p(W), _p(bias), _p(resid),
-                                    _p(y), M, N, K, _stream()), "pvrl_ot_linear_fwd")
+                                    _p(y), _p(act_out), M, N, K, _stream()), "pvrl_ot_linear_fwd")
     return y
 
 

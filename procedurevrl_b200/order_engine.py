@@ -3,7 +3,7 @@ kernels (include/pvrl.h) -- the B200-native replacement for the ~1500 eager kern
 DiffusionTransformer.diffusion_signal_training (reference lib/models/tfm_model.py:165-204) and its autograd.
 
 Per denoising level: one level-input kernel, then per ResidualAttentionBlock (tfm_model.py:32-53) five launches
-(LN+in_proj, attention, out_proj+residual, LN+c_fc, QuickGELU+c_proj+residual).  Levels are independent in the
+(LN+in_proj, attention, out_proj+residual, LN+c_fc (+QuickGELU of its output), c_proj+residual).  Levels are independent in the
 backward because each level's noisy input is built from the *detached* output of the previous level
 (tfm_model.py:183-186) and they share the block weights, so the backward stacks the levels along the row axis and runs
 once: eleven launches per block over L*B*S rows.  torch supplies memory and the autograd hook-up only."""
@@ -40,7 +40,8 @@ class OrderLevels(torch.autograd.Function):
         saved = [dict(xhat1=torch.empty(L * M, C, **f32), rstd1=torch.empty(L * M, **f32),
                       qkv=torch.empty(L * M, 3 * C, **f32), probs=torch.empty(L * B, H, S, S, **f32),
                       o=torch.empty(L * M, C, **f32), xhat2=torch.empty(L * M, C, **f32),
-                      rstd2=torch.empty(L * M, **f32), u=torch.empty(L * M, Hd, **f32)) for _ in range(nblk)]
+                      rstd2=torch.empty(L * M, **f32), u=torch.empty(L * M, Hd, **f32),
+                      act=torch.empty(L * M, Hd, **f32)) for _ in range(nblk)]
         outs = []
         src = x0.contiguous()
         for lvl in range(L):
@@ -52,14 +53,15 @@ class OrderLevels(torch.autograd.Function):
             for i in range(nblk):
                 (ln1w, ln1b, win, bin_, wout, bout, ln2w, ln2b, wfc, bfc, wproj, bproj) = P[12 * i:12 * i + 12]
                 sv = saved[i]
-                qkv, o, u = sv["qkv"][r0:r1], sv["o"][r0:r1], sv["u"][r0:r1]
+                qkv, o, u, act = sv["qkv"][r0:r1], sv["o"][r0:r1], sv["u"][r0:r1], sv["act"][r0:r1]
                 ops.ot_linear_fwd(h, win, bin_, qkv, ops.OT_X_LN, ln1w, ln1b, eps, sv["xhat1"][r0:r1], sv["rstd1"][r0:r1])
                 ops.ot_attn_fwd(qkv, pad_start, sv["probs"][lvl * B:(lvl + 1) * B], o, B, S, H)
                 h_mid = torch.empty(M, C, **f32)
                 ops.ot_linear_fwd(o, wout, bout, h_mid, resid=h)
-                ops.ot_linear_fwd(h_mid, wfc, bfc, u, ops.OT_X_LN, ln2w, ln2b, eps, sv["xhat2"][r0:r1], sv["rstd2"][r0:r1])
+                ops.ot_linear_fwd(h_mid, wfc, bfc, u, ops.OT_X_LN, ln2w, ln2b, eps, sv["xhat2"][r0:r1], sv["rstd2"][r0:r1],
+                                  act_out=act)                 # u for QuickGELU' in the backward, act = QuickGELU(u)
                 h = torch.empty(M, C, **f32)
-                ops.ot_linear_fwd(u, wproj, bproj, h, ops.OT_X_QGELU, resid=h_mid)
+                ops.ot_linear_fwd(act, wproj, bproj, h, resid=h_mid)
             den = h.index_select(0, mask_rows)          # tokens at the mask positions (tfm_model.py:194)
             outs.append(den)
             src = den
@@ -98,7 +100,7 @@ class OrderLevels(torch.autograd.Function):
             sv = saved[i]
             u = sv["u"]
             # h_out = h_mid + c_proj(QuickGELU(u)),  u = c_fc(LN2(h_mid))
-            ops.ot_linear_dw(dh, u, g_wproj, g_bproj, ops.OT_X_QGELU)
+            ops.ot_linear_dw(dh, sv["act"], g_wproj, g_bproj)
             dU = torch.empty_like(u)
             ops.ot_linear_dx(dh, wproj, dU, pre=u)
             ops.ot_linear_dw(dU, sv["xhat2"], g_wfc, g_bfc, ops.OT_X_LN, ln2w, ln2b)

@@ -341,7 +341,7 @@ def _qgelu(u):
     return u * torch.sigmoid(1.702 * u)
 
 
-def ot_linear_fwd(x, W, bias, y, x_mode=0, ln_w=None, ln_b=None, eps=1e-5, xhat=None, rstd=None, resid=None):
+def ot_linear_fwd(x, W, bias, y, x_mode=0, ln_w=None, ln_b=None, eps=1e-5, xhat=None, rstd=None, resid=None, act_out=None):
     _launches[0] += 1
     a = x
     if x_mode == 1:
@@ -361,6 +361,8 @@ def ot_linear_fwd(x, W, bias, y, x_mode=0, ln_w=None, ln_b=None, eps=1e-5, xhat=
     if resid is not None:
         out = out + resid
     y.copy_(out)
+    if act_out is not None:
+        act_out.copy_(_qgelu(out))
     return y
 
 

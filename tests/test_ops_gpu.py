@@ -386,9 +386,11 @@ def test_ot_linear(ops, M, N, K):
         y, yr = torch.empty(M, N, device="cuda"), torch.empty(M, N, device="cuda")
         xh, rs = torch.empty(M, K, device="cuda"), torch.empty(M, device="cuda")
         xhr, rsr = torch.empty_like(xh), torch.empty_like(rs)
-        ops.ot_linear_fwd(x, W, b, y, mode, lw, lb, 1e-5, xh, rs, resid=res)
-        S.ot_linear_fwd(x, W, b, yr, mode, lw, lb, 1e-5, xhr, rsr, resid=res)
+        act, actr = torch.empty_like(y), torch.empty_like(yr)
+        ops.ot_linear_fwd(x, W, b, y, mode, lw, lb, 1e-5, xh, rs, resid=res, act_out=act)
+        S.ot_linear_fwd(x, W, b, yr, mode, lw, lb, 1e-5, xhr, rsr, resid=res, act_out=actr)
         _close(f"ot_linear_fwd mode{mode}", y, yr)
+        _close(f"ot_linear_fwd mode{mode} QuickGELU(y)", act, actr)
         if mode == 1:
             _close("ot xhat", xh, xhr), _close("ot rstd", rs, rsr)
     dY = _rand(M, N, seed=7)
