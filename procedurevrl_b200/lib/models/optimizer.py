@@ -195,19 +195,36 @@ class FlatOptimizer:
             self._lr_host = lrs
 
     # -- torch.optim surface --------------------------------------------------------------------------------
+    def _grad_view(self, i):
+        a, b = self.offsets[i]
+        return self.flat_grad[a:b].view_as(self._params[i])
+
     def zero_grad(self, set_to_none=False):
         """Gradients stay views of the flat buffer (the engine's dW kernels accumulate into them), so they are cleared,
-        never dropped."""
+        never dropped.  A `.grad` that something else re-pointed (DistributedDataParallel's bucket views) is cleared
+        where it lives; a `.grad` that was set to None gets its view back."""
         self.flat_grad.zero_()
+        base = self.flat_grad.data_ptr()
+        for i, (p, (a, _)) in enumerate(zip(self._params, self.offsets)):
+            if p.grad is None:
+                p.grad = self._grad_view(i)
+            elif p.grad.data_ptr() != base + 4 * a:
+                p.grad.zero_()
 
     def _adopt_foreign_grads(self):
-        """A wrapper (e.g. DistributedDataParallel with gradient_as_bucket_view) may have re-pointed `.grad`: copy
-        such gradients into the flat buffer.  Returns the parameters without any gradient (torch skips those)."""
+        """Called by the eager `step()`.  Checks that every parameter still IS its slice of the flat buffer (a later
+        `model.to(...)` / `.cuda()` would silently detach them), copies gradients that a wrapper re-pointed (e.g.
+        DistributedDataParallel with gradient_as_bucket_view) into the flat buffer, and returns the parameters
+        without any gradient (torch skips those)."""
         missing = []
+        pbase, gbase = self.flat_param.data_ptr(), self.flat_grad.data_ptr()
         for i, (p, (a, b)) in enumerate(zip(self._params, self.offsets)):
+            if p.data_ptr() != pbase + 4 * a:
+                raise RuntimeError("FlatOptimizer: a parameter no longer lives in the flat buffer (was the model moved or "
+                                   "re-cast after the optimizer was built?) -- construct the optimizer last")
             if p.grad is None:
                 missing.append(i)
-            elif p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * a:
+            elif p.grad.data_ptr() != gbase + 4 * a:
                 self.flat_grad[a:b].view_as(p).copy_(p.grad)
         return missing
 

@@ -172,3 +172,42 @@ def test_flat_optimizer_in_cuda_graph(ops):
         tw.grad = g.clone()
         t.step()
         torch.testing.assert_close(w.detach(), tw.detach(), rtol=2e-6, atol=1e-7)
+
+
+def test_flat_optimizer_foreign_and_missing_grads(ops):
+    """`.grad`s that a wrapper re-pointed (DistributedDataParallel's bucket views) are adopted by step() and cleared by
+    zero_grad(); a `.grad` set to None skips that parameter for the step (torch semantics) and gets its view back; a
+    parameter moved out of the flat buffer is reported instead of silently ignored."""
+    from procedurevrl_b200.lib.models.optimizer import FlatOptimizer
+    torch.manual_seed(1)
+    ws = [torch.nn.Parameter(torch.randn(40, 3, device="cuda")), torch.nn.Parameter(torch.randn(17, device="cuda"))]
+    tw = [torch.nn.Parameter(w.detach().clone()) for w in ws]
+    o = FlatOptimizer(ws, "adamw", lr=1e-2, weight_decay=0.1)
+    t = torch.optim.AdamW(tw, lr=1e-2, weight_decay=0.1)
+    bucket = torch.zeros(40 * 3, device="cuda")
+    ws[0].grad = bucket.view(40, 3)                      # what gradient_as_bucket_view does
+    for it in range(3):
+        g0, g1 = torch.randn(40, 3, device="cuda"), torch.randn(17, device="cuda")
+        o.zero_grad()
+        t.zero_grad()
+        assert (bucket == 0).all()
+        ws[0].grad.add_(g0)
+        tw[0].grad = g0.clone()
+        if it == 1:
+            ws[1].grad = None                            # no gradient this step: torch leaves the parameter alone
+            tw[1].grad = None
+        else:
+            ws[1].grad.add_(g1)
+            tw[1].grad = g1.clone()
+        before = ws[1].detach().clone()
+        o.step()
+        t.step()
+        if it == 1:
+            assert torch.equal(ws[1].detach(), before)
+        torch.testing.assert_close(ws[0].detach(), tw[0].detach(), rtol=2e-6, atol=1e-7)
+    # parameter 1 took 2 steps in torch (its own counter) but the flat optimizer counts 3: compare parameter 0 only above
+    o.zero_grad()
+    assert ws[1].grad is not None and ws[1].grad.data_ptr() == o.flat_grad.data_ptr() + 4 * 120
+    ws[0].data = ws[0].data.clone()
+    with pytest.raises(RuntimeError, match="no longer lives in the flat buffer"):
+        o.step()
