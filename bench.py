@@ -222,6 +222,11 @@ def run_b200(args):
         ops.gemm = timed_gemm
         launches0 = ops.launch_count()
         te0, te1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # The eager step is host-bound (one Python / ctypes call per launch): on an idle GPU the event recorded BEFORE a
+        # launch is stamped ~10 us before the kernel starts, and that host gap would be billed to the kernel.  Park the
+        # GPU on a spin kernel first, long enough for the host to enqueue the whole step, so that events and kernels are
+        # consumed back to back and an event pair brackets the kernel's execution only.
+        torch.cuda._sleep(int(0.12 * 1.9e9))
         te0.record()
         trainer._eager(frames, meta)
         te1.record()
@@ -302,7 +307,8 @@ def run_b200(args):
                          "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic,
                          "peak_source": f"bf16_tflops_sustained, {peak_src}",
                          "launches": n_gemm, "gemm_share_of_step": round(gemm_ms / ms_step, 4),
-                         "timed_in": ("CUDA events around every GEMM launch of one eager step run after the graph-replayed timed "
+                         "timed_in": ("CUDA events around every GEMM launch of one eager step (GPU parked on a spin kernel while the "
+                                      "host enqueues it, so no host gap is billed to a kernel) run after the graph-replayed timed "
                                       "region (events cannot time nodes inside a graph); share = that GEMM time / ms_per_step")
                          if graphed else "timed region",
                          "step_mfu": round(step_flops / (ms_step / 1e3) / 1e12 / peak, 4)},
