@@ -262,6 +262,69 @@ int pvrl_sgd_flat(float* p, float* g, float* buf, int64_t n, const float* lr_dev
                   float momentum, float dampening, int32_t nesterov, float weight_decay, float grad_scale,
                   int32_t zero_grad, void* stream);
 
+/* ---- MViTv2 video encoder (BASELINE config 5; reference lib/models/slowfast_mvit/) --------------
+ * Tokens of a clip are [1 + T*H*W, width] rows, cls first, grid order (t h w) with w fastest (mvit.py:338-360).
+ * The encoder's Linear layers (qkv, proj, skip proj, MLP, Conv3d stem as im2col) go through pvrl_gemm_bf16. */
+
+/* nn.LayerNorm over the last axis of [M, D], any D <= 1024 (attention.py:239-280 norm_q/k/v over 96; :530,:556 norm1 /
+ * norm2 over 96 .. 768; mvit.py:401 final norm).  x, y: bf16 or fp32; stats [M, 2] = (mean, rstd) for the backward.
+ * Backward: dx (dtype of x) is written; dw / db (fp32, may be NULL) are ACCUMULATED (+=, atomics). */
+int pvrl_ln_any_fwd(const void* x, int32_t x_dtype, const float* w, const float* b, void* y, int32_t y_dtype, float* stats,
+                    int32_t M, int32_t D, float eps, void* stream);
+int pvrl_ln_any_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* w, const float* stats,
+                    void* dx, float* dw, float* db, int32_t M, int32_t D, void* stream);
+
+/* Geometry of a 3-D pooling window over a clip's token grid. out[d] = floor((in[d] + 2 pad[d] - kernel[d]) / stride[d]) + 1. */
+typedef struct pvrl_pool3d {
+  int32_t B;         /* clips                                                                         */
+  int32_t heads;     /* heads sharing the pooling weights (1 for the skip max-pool / the stem)        */
+  int32_t C;         /* channels per head (pool3d: <= 128), token width (maxpool3d)                   */
+  int32_t T, H, W;   /* input grid                                                                    */
+  int32_t kernel[3], stride[3], pad[3], out[3];
+  int64_t ld;        /* pool3d: row pitch (elements) of the token-major input [B, 1 + T*H*W, ld]      */
+} pvrl_pool3d_t;
+
+/* attention_pool (attention.py:14-48) for one of Q / K / V: `in` points at that tensor's first column inside the qkv
+ * GEMM output [B, 1 + T*H*W, ld = 3 * heads * C] (head h = columns [h*C, h*C + C)); depth-wise Conv3d(C, C, kernel,
+ * stride, pad, groups = C, bias = False) with weights w [C, kt*kh*kw] shared by all heads, the cls row bypasses the
+ * convolution.  out [B, heads, 1 + To*Ho*Wo, C] (same dtype).  w == NULL: no pooling, only the head-major re-layout.
+ * Backward: din gets the same strided layout as `in` (every element of the slice is written); dw [C, 27] (may be
+ * NULL) is ACCUMULATED and needs the forward input `in` and a 3 x 3 x 3 kernel. */
+int pvrl_pool3d_fwd(const void* in, const float* w, void* out, int32_t dtype, const pvrl_pool3d_t* p, void* stream);
+int pvrl_pool3d_bwd(const void* dout, const void* in, const float* w, void* din, float* dw, int32_t dtype,
+                    const pvrl_pool3d_t* p, void* stream);
+
+/* MaxPool3d of the skip path (attention.py:521-543): x [B, 1 + T*H*W, C] -> y [B, 1 + To*Ho*Wo, C], cls row copied;
+ * arg [B, To*Ho*Wo, C] = winning input token of every window (first maximum in scan order, as ATen).
+ * Backward: dx fp32, ZERO-INITIALISED by the caller, receives dy through arg (windows overlap: atomics). */
+int pvrl_maxpool3d_fwd(const void* x, void* y, int32_t* arg, int32_t dtype, const pvrl_pool3d_t* p, void* stream);
+int pvrl_maxpool3d_bwd(const void* dy, const int32_t* arg, float* dx, int32_t dtype, const pvrl_pool3d_t* p, void* stream);
+
+/* Rows of the Conv3d patch stem (stem_helper.py:290-322) for the GEMM: frames fp32 [B, Cin, T, H, W] ->
+ * out [B * To*Ho*Wo, Kpad], column ((c*kt + dt)*kh + dh)*kw + dw, zero-padded to Kpad and outside the clip. */
+int pvrl_im2col3d(const float* frames, void* out, int32_t out_dtype, int32_t Cin, int32_t Kpad, const pvrl_pool3d_t* p,
+                  void* stream);
+
+/* Pooled attention with decomposed relative-position bias and residual pooling (attention.py:51-159, :360-411).
+ * q [B, heads, Nq, C], k / v [B, heads, Nk, C] (row 0 = cls; C = 96), bq [B, heads, Nq - 1, Kt + Kh + Kw] fp32 = each non-cls
+ * query's dot products with the rows of the relative-position tables that its position selects:
+ *   score(i, j) = scale * q_i . k_j + [i > 0 and j > 0] (bq[i-1, kt] + bq[i-1, Kt + kh] + bq[i-1, Kt + Kh + kw]),
+ *   j - 1 = (kt * Kh + kh) * Kw + kw;    out[b, i, h*C ..] = softmax_j(score) v + [i > 0 and residual_pooling] q_i.
+ * out [B, Nq, heads * C] (what the projection Linear reads), lse [B, heads, Nq] fp32.
+ * Backward: dq (layout / dtype of q), dbq (layout of bq) and delta [B, heads, Nq] are written; dk / dv are fp32
+ * [B, heads, Nk, C], ZERO-INITIALISED by the caller (atomics over query slices). */
+typedef struct pvrl_pooled_attn {
+  int32_t B, heads, Nq, Nk, C;
+  int32_t Kt, Kh, Kw;          /* key grid: Nk = 1 + Kt*Kh*Kw */
+  float scale;
+  int32_t residual_pooling;
+} pvrl_pooled_attn_t;
+int pvrl_pooled_attn_fwd(const void* q, const void* k, const void* v, const float* bq, void* out, float* lse, int32_t dtype,
+                         const pvrl_pooled_attn_t* a, void* stream);
+int pvrl_pooled_attn_bwd(const void* q, const void* k, const void* v, const float* bq, const void* out, const void* dout,
+                         const float* lse, void* dq, float* dk, float* dv, float* dbq, float* delta, int32_t dtype,
+                         const pvrl_pooled_attn_t* a, void* stream);
+
 /* ---- misc ----------------------------------------------------------------------------------------------- */
 const char* pvrl_last_error(void);
 int pvrl_abi_version(void);

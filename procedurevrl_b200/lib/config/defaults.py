@@ -1,5 +1,5 @@
 """Config tree with the reference's keys and defaults for everything the hot path reads
-(reference lib/config/defaults.py:40-65 DEV.*, :73-106 TRAIN.*, :383-440 MODEL.*, :463-466 TIMESFORMER.*,
+(reference lib/config/defaults.py:40-65 DEV.*, :73-106 TRAIN.*, :383-440 MODEL.*, :463-466 TIMESFORMER.*, :169-280 MVIT.*,
 :504-525 DATA.*, :14-23 BN.*, :576-627 SOLVER.*, :634-659 NUM_GPUS/NUM_SHARDS/RNG_SEED/DIST_BACKEND/GLOBAL_BATCH_SIZE).
 
 The reference uses fvcore/yacs `CfgNode`; neither is a dependency here, so `CfgNode` below is a small
@@ -96,6 +96,15 @@ _DEFAULTS = {
               "DROPOUT_RATE": 0.5, "PRETRAINED": True, "MLP": 0, "TEXT_MODEL": "", "TEXT_LP": False, "NUM_SEG": 0,
               "EXTRA_TR": "", "DROP_E": 0.0, "PRE_CLASSES": 0, "DROP_PATH": 0.1},
     "TIMESFORMER": {"ATTENTION_TYPE": "divided_space_time", "PRETRAINED_MODEL": "", "DEPTH": 12},
+    # reference lib/config/defaults.py:169-280 (MViTv2 encoder, MODEL.MODEL_NAME: MViT)
+    "MVIT": {"MODE": "conv", "POOL_FIRST": False, "CLS_EMBED_ON": True, "PATCH_KERNEL": [3, 7, 7], "PATCH_STRIDE": [2, 4, 4],
+             "PATCH_PADDING": [2, 4, 4], "PATCH_2D": False, "EMBED_DIM": 96, "NUM_HEADS": 1, "MLP_RATIO": 4.0,
+             "QKV_BIAS": True, "DROPPATH_RATE": 0.1, "LAYER_SCALE_INIT_VALUE": 0.0, "DEPTH": 16, "NORM": "layernorm",
+             "DIM_MUL": [], "HEAD_MUL": [], "POOL_KV_STRIDE": [], "POOL_KV_STRIDE_ADAPTIVE": None, "POOL_Q_STRIDE": [],
+             "POOL_KVQ_KERNEL": None, "ZERO_DECAY_POS_CLS": True, "NORM_STEM": False, "SEP_POS_EMBED": False,
+             "DROPOUT_RATE": 0.0, "USE_ABS_POS": True, "REL_POS_SPATIAL": False, "REL_POS_TEMPORAL": False,
+             "REL_POS_ZERO_INIT": False, "RESIDUAL_POOLING": False, "DIM_MUL_IN_ATT": False, "SEPARATE_QKV": False,
+             "HEAD_INIT_SCALE": 1.0, "USE_MEAN_POOLING": False, "USE_FIXED_SINCOS_POS": False},
     "DATA": {"NUM_FRAMES": 8, "MEAN": [0.45, 0.45, 0.45], "STD": [0.225, 0.225, 0.225], "INPUT_CHANNEL_NUM": [3, 3],
              "TRAIN_CROP_SIZE": 224, "TEST_CROP_SIZE": 256},
     # extension node of this implementation (not in the reference): arithmetic mode of the sm_100a path

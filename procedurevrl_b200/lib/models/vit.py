@@ -123,6 +123,24 @@ class VisionTransformer(nn.Module):
                                            attention_type) for i in range(depth)])
         self.norm = norm_layer(embed_dim)
 
+        self._build_heads(cfg, embed_dim, num_classes, label_emb, mlp, text_model, num_seg)
+
+        trunc_normal_(self.pos_embed, std=0.02)
+        trunc_normal_(self.cls_token, std=0.02)
+        # vit.py:273-281 zero-initialises temporal_fc in *every* block (the `i > 0` guard sees the ModuleList first)
+        if attention_type == "divided_space_time":
+            for blk in self.blocks:
+                nn.init.constant_(blk.temporal_fc.weight, 0)
+                nn.init.constant_(blk.temporal_fc.bias, 0)
+
+        self._engine = None
+        self._label_dev = None
+        self.fixed_rand_inds = None           # tests replay the reference's randperm (vit.py:345)
+        self.fixed_drop_scales = None         # tests replay DropPath draws
+
+    def _build_heads(self, cfg, embed_dim, num_classes, label_emb, mlp, text_model, num_seg):
+        """Matching head, order transformer, fine-tune heads and the text tower (vit.py:229-266; lib/models/mvit.py:72-108
+        builds exactly the same set around the MViT encoder)."""
         self.mlp, self.label = mlp, label_emb
         if label_emb != "":                                                            # pre-training (vit.py:231-236)
             self.label_emb = torch.load(label_emb)
@@ -164,19 +182,6 @@ class VisionTransformer(nn.Module):
             self.num_seg = num_seg
             self.order_tfm = OrderTransformer(num_seg=num_seg, tfm_layers=self.order_tfm_layers, dropout=cfg.MODEL.DROP_E,
                                               hidden_size=self.head.weight.shape[0], cfg=cfg)
-
-        trunc_normal_(self.pos_embed, std=0.02)
-        trunc_normal_(self.cls_token, std=0.02)
-        # vit.py:273-281 zero-initialises temporal_fc in *every* block (the `i > 0` guard sees the ModuleList first)
-        if attention_type == "divided_space_time":
-            for blk in self.blocks:
-                nn.init.constant_(blk.temporal_fc.weight, 0)
-                nn.init.constant_(blk.temporal_fc.bias, 0)
-
-        self._engine = None
-        self._label_dev = None
-        self.fixed_rand_inds = None           # tests replay the reference's randperm (vit.py:345)
-        self.fixed_drop_scales = None         # tests replay DropPath draws
 
     def _init_weights(self, m):
         """vit.py:442-449."""

@@ -34,6 +34,16 @@ class GemmDesc(ctypes.Structure):
     ]
 
 
+class Pool3dDesc(ctypes.Structure):
+    _fields_ = [("B", _c_int), ("heads", _c_int), ("C", _c_int), ("T", _c_int), ("H", _c_int), ("W", _c_int),
+                ("kernel", _c_int * 3), ("stride", _c_int * 3), ("pad", _c_int * 3), ("out", _c_int * 3), ("ld", _c_i64)]
+
+
+class PooledAttnDesc(ctypes.Structure):
+    _fields_ = [("B", _c_int), ("heads", _c_int), ("Nq", _c_int), ("Nk", _c_int), ("C", _c_int),
+                ("Kt", _c_int), ("Kh", _c_int), ("Kw", _c_int), ("scale", _c_float), ("residual_pooling", _c_int)]
+
+
 _SIGS = {
     "pvrl_gemm_bf16": [ctypes.POINTER(GemmDesc), _c_void_p],
     "pvrl_patchify": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
@@ -84,6 +94,19 @@ _SIGS = {
                           _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
     "pvrl_ot_embed_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int,
                           _c_int, _c_int, _c_void_p],
+    "pvrl_ln_any_fwd": [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_float,
+                        _c_void_p],
+    "pvrl_ln_any_bwd": [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int,
+                        _c_int, _c_void_p],
+    "pvrl_pool3d_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_int, ctypes.POINTER(Pool3dDesc), _c_void_p],
+    "pvrl_pool3d_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, ctypes.POINTER(Pool3dDesc), _c_void_p],
+    "pvrl_maxpool3d_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_int, ctypes.POINTER(Pool3dDesc), _c_void_p],
+    "pvrl_maxpool3d_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_int, ctypes.POINTER(Pool3dDesc), _c_void_p],
+    "pvrl_im2col3d": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, ctypes.POINTER(Pool3dDesc), _c_void_p],
+    "pvrl_pooled_attn_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int,
+                             ctypes.POINTER(PooledAttnDesc), _c_void_p],
+    "pvrl_pooled_attn_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                             _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, ctypes.POINTER(PooledAttnDesc), _c_void_p],
     "pvrl_optim_tick": [_c_void_p, _c_void_p],
     "pvrl_adam_flat": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_i64, _c_void_p, _c_void_p, _c_float,
                        ctypes.c_double, ctypes.c_double, _c_float, _c_float, _c_int, _c_float, _c_int, _c_void_p],
@@ -356,7 +379,7 @@ OT_X_PLAIN, OT_X_LN, OT_X_QGELU = 0, 1, 2
 
 def _f32c(*ts):
     for t in ts:
-        assert t is None or (t.dtype == torch.float32 and t.is_contiguous()), "order-transformer ops take contiguous fp32"
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous()), "this argument must be a contiguous fp32 tensor"
 
 
 def ot_linear_fwd(x, W, bias, y, x_mode=OT_X_PLAIN, ln_w=None, ln_b=None, eps=1e-5, xhat=None, rstd=None, resid=None,
@@ -443,3 +466,123 @@ def sgd_flat(p, g, buf, lr, step, *, lr_mult=1.0, momentum=0.0, dampening=0.0, n
     assert p.numel() == g.numel() == buf.numel()
     _check(lib().pvrl_sgd_flat(_p(p), _p(g), _p(buf), p.numel(), _p(lr), _p(step), lr_mult, momentum, dampening,
                                int(nesterov), weight_decay, grad_scale, int(zero_grad), _stream()), "pvrl_sgd_flat")
+
+
+# ---------------------------------------------------------------------------------------------- MViTv2 encoder ops
+def pool_out_grid(grid, kernel, stride, pad):
+    """floor((in + 2 pad - kernel) / stride) + 1 per axis (nn.Conv3d / nn.MaxPool3d without ceil_mode)."""
+    return [(g + 2 * p - k) // s + 1 for g, k, s, p in zip(grid, kernel, stride, pad)]
+
+
+def _pool_desc(B, heads, C, grid, kernel, stride, pad, ld):
+    d = Pool3dDesc()
+    d.B, d.heads, d.C = int(B), int(heads), int(C)
+    d.T, d.H, d.W = (int(g) for g in grid)
+    d.kernel, d.stride, d.pad = (_c_int * 3)(*kernel), (_c_int * 3)(*stride), (_c_int * 3)(*pad)
+    d.out = (_c_int * 3)(*pool_out_grid(grid, kernel, stride, pad))
+    d.ld = int(ld)
+    return d
+
+
+def _col_ptr(t, col0):
+    """address of column `col0` of the first row of a contiguous [.., ld] CUDA tensor"""
+    assert t.is_cuda and t.is_contiguous(), "pvrl ops take contiguous CUDA tensors only (no CPU fallback)"
+    return t.data_ptr() + int(col0) * t.element_size()
+
+
+def ln_any_fwd(x, w, b, y, stats, M, D, eps):
+    """y = LayerNorm(x) over the last axis of [M, D], any D <= 1024; stats [M, 2] = (mean, rstd)."""
+    _f32c(w, b, stats)
+    assert x.is_contiguous() and y.is_contiguous()
+    _check(lib().pvrl_ln_any_fwd(_p(x), _dt(x), _p(w), _p(b), _p(y), _dt(y), _p(stats), M, D, eps, _stream()),
+           "pvrl_ln_any_fwd")
+    return y
+
+
+def ln_any_bwd(dy, x, w, stats, dx, dw, db, M, D):
+    """dx (dtype of x) written; dw / db (fp32) accumulated."""
+    _f32c(w, stats, dw, db)
+    assert dy.is_contiguous() and x.is_contiguous() and dx.is_contiguous() and dx.dtype == x.dtype
+    _check(lib().pvrl_ln_any_bwd(_p(dy), _dt(dy), _p(x), _dt(x), _p(w), _p(stats), _p(dx), _p(dw), _p(db), M, D, _stream()),
+           "pvrl_ln_any_bwd")
+
+
+def pool3d_fwd(src, col0, w, out, heads, C, grid, kernel, stride, pad):
+    """attention_pool of one of Q / K / V: src [B, 1 + T*H*W, ld] (columns [col0, col0 + heads*C) are this tensor),
+    w [C, kt*kh*kw] fp32 or None (re-layout only) -> out [B, heads, 1 + To*Ho*Wo, C]."""
+    B, _, ld = src.shape
+    assert out.dtype == src.dtype and out.is_contiguous()
+    if w is not None:
+        _f32c(w)
+    d = _pool_desc(B, heads, C, grid, kernel, stride, pad, ld)
+    _check(lib().pvrl_pool3d_fwd(_col_ptr(src, col0), _p(w), _p(out), _dt(src), ctypes.byref(d), _stream()), "pvrl_pool3d_fwd")
+    return out
+
+
+def pool3d_bwd(dout, src, col0, w, din, dw, heads, C, grid, kernel, stride, pad):
+    """din [B, 1 + T*H*W, ld]: columns [col0, col0 + heads*C) are written; dw [C, 27] (or None) accumulated."""
+    B, _, ld = din.shape
+    assert dout.dtype == din.dtype and dout.is_contiguous() and (src is None or src.shape == din.shape)
+    if w is not None:
+        _f32c(w, dw)
+    d = _pool_desc(B, heads, C, grid, kernel, stride, pad, ld)
+    _check(lib().pvrl_pool3d_bwd(_p(dout), None if src is None else _col_ptr(src, col0), _p(w), _col_ptr(din, col0), _p(dw),
+                                 _dt(din), ctypes.byref(d), _stream()), "pvrl_pool3d_bwd")
+
+
+def maxpool3d_fwd(x, y, arg, grid, kernel, stride, pad):
+    """x [B, 1 + T*H*W, D] -> y [B, 1 + To*Ho*Wo, D], arg int32 [B, To*Ho*Wo, D] (winning input token)."""
+    B, _, D = x.shape
+    assert x.is_contiguous() and y.is_contiguous() and y.dtype == x.dtype and arg.dtype == torch.int32
+    d = _pool_desc(B, 1, D, grid, kernel, stride, pad, D)
+    _check(lib().pvrl_maxpool3d_fwd(_p(x), _p(y), _p(arg), _dt(x), ctypes.byref(d), _stream()), "pvrl_maxpool3d_fwd")
+    return y
+
+
+def maxpool3d_bwd(dy, arg, dx, grid, kernel, stride, pad):
+    """dx fp32 [B, 1 + T*H*W, D], zero-initialised by the caller, += dy scattered through arg."""
+    B, _, D = dx.shape
+    _f32c(dx)
+    assert dy.is_contiguous() and arg.dtype == torch.int32
+    d = _pool_desc(B, 1, D, grid, kernel, stride, pad, D)
+    _check(lib().pvrl_maxpool3d_bwd(_p(dy), _p(arg), _p(dx), _dt(dy), ctypes.byref(d), _stream()), "pvrl_maxpool3d_bwd")
+
+
+def im2col3d(frames, out, kernel, stride, pad):
+    """frames fp32 [B, Cin, T, H, W] -> out [B * To*Ho*Wo, Kpad] rows of the Conv3d stem (zero-padded columns)."""
+    B, Cin, T, H, W = frames.shape
+    _f32c(frames)
+    assert out.is_contiguous()
+    d = _pool_desc(B, 1, Cin, (T, H, W), kernel, stride, pad, 0)
+    _check(lib().pvrl_im2col3d(_p(frames), _p(out), _dt(out), Cin, out.shape[1], ctypes.byref(d), _stream()), "pvrl_im2col3d")
+    return out
+
+
+def _attn_desc(q, k, kgrid, scale, resid):
+    B, heads, Nq, C = q.shape
+    d = PooledAttnDesc()
+    d.B, d.heads, d.Nq, d.Nk, d.C = B, heads, Nq, k.shape[2], C
+    d.Kt, d.Kh, d.Kw = (int(g) for g in kgrid)
+    d.scale, d.residual_pooling = float(scale), int(bool(resid))
+    return d
+
+
+def pooled_attn_fwd(q, k, v, bq, out, lse, kgrid, scale, resid):
+    """q [B, heads, Nq, 96], k / v [B, heads, Nk, 96], bq fp32 [B, heads, Nq - 1, Kt + Kh + Kw] -> out [B, Nq, heads * 96],
+    lse fp32 [B, heads, Nq] (see pvrl_pooled_attn_fwd in include/pvrl.h)."""
+    _f32c(bq, lse)
+    assert q.is_contiguous() and k.is_contiguous() and v.is_contiguous() and out.is_contiguous()
+    assert q.dtype == k.dtype == v.dtype == out.dtype
+    d = _attn_desc(q, k, kgrid, scale, resid)
+    _check(lib().pvrl_pooled_attn_fwd(_p(q), _p(k), _p(v), _p(bq), _p(out), _p(lse), _dt(q), ctypes.byref(d), _stream()),
+           "pvrl_pooled_attn_fwd")
+    return out
+
+
+def pooled_attn_bwd(q, k, v, bq, out, dout, lse, dq, dk, dv, dbq, delta, kgrid, scale, resid):
+    """dq (like q), dbq (like bq), delta written; dk / dv fp32, zero-initialised by the caller, accumulated."""
+    _f32c(bq, lse, dk, dv, dbq, delta)
+    assert dout.is_contiguous() and dout.dtype == q.dtype and dq.dtype == q.dtype and dq.is_contiguous()
+    d = _attn_desc(q, k, kgrid, scale, resid)
+    _check(lib().pvrl_pooled_attn_bwd(_p(q), _p(k), _p(v), _p(bq), _p(out), _p(dout), _p(lse), _p(dq), _p(dk), _p(dv),
+                                      _p(dbq), _p(delta), _dt(q), ctypes.byref(d), _stream()), "pvrl_pooled_attn_bwd")

@@ -450,4 +450,133 @@ def ot_embed_bwd(dh, mask_inds, pad_start, dvideo, dtype, dpos, dpad, dtvec, B, 
     dvideo += (g * (~is_mask & ~is_pad)).reshape(B * S, C)
 
 
+# ---------------------------------------------------------------------------------------------- MViTv2 encoder ops
+def pool_out_grid(grid, kernel, stride, pad):
+    return [(g + 2 * p - k) // s + 1 for g, k, s, p in zip(grid, kernel, stride, pad)]
+
+
+def ln_any_fwd(x, w, b, y, stats, M, D, eps):
+    _launches[0] += 1
+    xf = x.reshape(M, D).float()
+    mean, var = xf.mean(1), xf.var(1, unbiased=False)
+    rstd = 1.0 / torch.sqrt(var + eps)
+    y.reshape(M, D).copy_((xf - mean[:, None]) * rstd[:, None] * w + b)
+    stats[:, 0], stats[:, 1] = mean, rstd
+    return y
+
+
+def ln_any_bwd(dy, x, w, stats, dx, dw, db, M, D):
+    _launches[0] += 1
+    d, xf = dy.reshape(M, D).float(), x.reshape(M, D).float()
+    mean, rstd = stats[:, :1], stats[:, 1:]
+    xh = (xf - mean) * rstd
+    g = d * w
+    dx.reshape(M, D).copy_(rstd * (g - g.mean(1, keepdim=True) - xh * (g * xh).mean(1, keepdim=True)))
+    if dw is not None:
+        dw += (d * xh).sum(0)
+    if db is not None:
+        db += d.sum(0)
+
+
+def _pool_conv(t, w, grid, kernel, stride, pad):
+    """t [B, heads, 1 + L, C] fp32 -> depth-wise Conv3d over the grid of every head, cls row bypasses."""
+    if w is None:
+        return t
+    B, Hh, _, C = t.shape
+    T, H, W = grid
+    vol = t[:, :, 1:].reshape(B * Hh, T, H, W, C).permute(0, 4, 1, 2, 3)
+    vol = F.conv3d(vol, w.reshape(C, 1, *kernel), None, stride=list(stride), padding=list(pad), groups=C)
+    return torch.cat((t[:, :, :1], vol.reshape(B, Hh, C, -1).transpose(2, 3)), dim=2)
+
+
+def pool3d_fwd(src, col0, w, out, heads, C, grid, kernel, stride, pad):
+    _launches[0] += 1
+    B, N, _ = src.shape
+    t = src[:, :, col0:col0 + heads * C].float().reshape(B, N, heads, C).permute(0, 2, 1, 3)
+    out.copy_(_pool_conv(t, w, grid, kernel, stride, pad))
+    return out
+
+
+def pool3d_bwd(dout, src, col0, w, din, dw, heads, C, grid, kernel, stride, pad):
+    _launches[0] += 1
+    B, N, _ = din.shape
+    if w is None:
+        din[:, :, col0:col0 + heads * C] = dout.permute(0, 2, 1, 3).reshape(B, N, heads * C)
+        return
+    with torch.enable_grad():
+        t = src[:, :, col0:col0 + heads * C].float().reshape(B, N, heads, C).permute(0, 2, 1, 3).detach().requires_grad_(True)
+        wv = w.detach().clone().requires_grad_(True)
+        gt, gw = torch.autograd.grad(_pool_conv(t, wv, grid, kernel, stride, pad), (t, wv), dout.float())
+    din[:, :, col0:col0 + heads * C] = gt.permute(0, 2, 1, 3).reshape(B, N, heads * C)
+    if dw is not None:
+        dw += gw.reshape(dw.shape)
+
+
+def maxpool3d_fwd(x, y, arg, grid, kernel, stride, pad):
+    _launches[0] += 1
+    B, _, D = x.shape
+    T, H, W = grid
+    vol = x[:, 1:].float().reshape(B, T, H, W, D).permute(0, 4, 1, 2, 3)
+    o, idx = F.max_pool3d(vol, list(kernel), list(stride), list(pad), return_indices=True)
+    y[:, 0] = x[:, 0]
+    y[:, 1:] = o.reshape(B, D, -1).transpose(1, 2)
+    arg.copy_(idx.reshape(B, D, -1).transpose(1, 2))
+    return y
+
+
+def maxpool3d_bwd(dy, arg, dx, grid, kernel, stride, pad):
+    _launches[0] += 1
+    dx[:, 0] = dy[:, 0].float()
+    dx[:, 1:].scatter_add_(1, arg.long(), dy[:, 1:].float())
+
+
+def im2col3d(frames, out, kernel, stride, pad):
+    _launches[0] += 1
+    B, Cin = frames.shape[:2]
+    xp = F.pad(frames, (pad[2], pad[2], pad[1], pad[1], pad[0], pad[0]))
+    cols = xp.unfold(2, kernel[0], stride[0]).unfold(3, kernel[1], stride[1]).unfold(4, kernel[2], stride[2])
+    cols = cols.permute(0, 2, 3, 4, 1, 5, 6, 7).reshape(out.shape[0], Cin * kernel[0] * kernel[1] * kernel[2])
+    out.zero_()
+    out[:, :cols.shape[1]] = cols
+    return out
+
+
+def _pooled_attn(q, k, v, bq, kgrid, scale, resid):
+    B, Hh, Nq, C = q.shape
+    Kt, Kh, Kw = kgrid
+    s = (q * scale) @ k.transpose(-1, -2)
+    bt, bh, bw = bq[..., :Kt], bq[..., Kt:Kt + Kh], bq[..., Kt + Kh:]
+    bias = (bt[..., :, None, None] + bh[..., None, :, None] + bw[..., None, None, :]).reshape(B, Hh, Nq - 1, -1)
+    s = torch.cat((s[:, :, :1], torch.cat((s[:, :, 1:, :1], s[:, :, 1:, 1:] + bias), dim=3)), dim=2)
+    o = s.softmax(-1) @ v
+    if resid:
+        o = torch.cat((o[:, :, :1], o[:, :, 1:] + q[:, :, 1:]), dim=2)
+    return o.transpose(1, 2).reshape(B, Nq, Hh * C), torch.logsumexp(s, dim=-1)
+
+
+def pooled_attn_fwd(q, k, v, bq, out, lse, kgrid, scale, resid):
+    _launches[0] += 1
+    o, l = _pooled_attn(q.float(), k.float(), v.float(), bq, kgrid, scale, resid)
+    out.copy_(o)
+    lse.copy_(l)
+    return out
+
+
+def pooled_attn_bwd(q, k, v, bq, out, dout, lse, dq, dk, dv, dbq, delta, kgrid, scale, resid):
+    _launches[0] += 2
+    with torch.enable_grad():
+        ins = [t.detach().float().clone().requires_grad_(True) for t in (q, k, v, bq)]
+        o, _ = _pooled_attn(*ins, kgrid, scale, resid)
+        gq, gk, gv, gb = torch.autograd.grad(o, ins, dout.float())
+    dq.copy_(gq)
+    dk += gk
+    dv += gv
+    dbq.copy_(gb)
+    B, Hh, Nq, C = q.shape
+    o_attn = out.float().reshape(B, Nq, Hh, C).transpose(1, 2).clone()
+    if resid:
+        o_attn[:, :, 1:] -= q.float()[:, :, 1:]
+    delta.copy_((dout.float().reshape(B, Nq, Hh, C).transpose(1, 2) * o_attn).sum(-1))
+
+
 ALL = [n for n, v in list(globals().items()) if callable(v) and not n.startswith("_") and n not in ("F", "math", "torch")]
