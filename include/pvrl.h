@@ -311,7 +311,8 @@ int pvrl_im2col3d(const float* frames, void* out, int32_t out_dtype, int32_t Cin
  *   score(i, j) = scale * q_i . k_j + [i > 0 and j > 0] (bq[i-1, kt] + bq[i-1, Kt + kh] + bq[i-1, Kt + Kh + kw]),
  *   j - 1 = (kt * Kh + kh) * Kw + kw;    out[b, i, h*C ..] = softmax_j(score) v + [i > 0 and residual_pooling] q_i.
  * out [B, Nq, heads * C] (what the projection Linear reads), lse [B, heads, Nq] fp32.
- * Backward: dq (layout / dtype of q), dbq (layout of bq) and delta [B, heads, Nq] are written; dk / dv are fp32
+ * Backward (recomputes the probabilities from q, k, bq and lse; the forward output is not needed): dq (layout / dtype of
+ * q), dbq (layout of bq) and delta [B, heads, Nq] = sum_j p_ij dP_ij are written; dk / dv are fp32
  * [B, heads, Nk, C], ZERO-INITIALISED by the caller (atomics over query slices). */
 typedef struct pvrl_pooled_attn {
   int32_t B, heads, Nq, Nk, C;
@@ -321,8 +322,8 @@ typedef struct pvrl_pooled_attn {
 } pvrl_pooled_attn_t;
 int pvrl_pooled_attn_fwd(const void* q, const void* k, const void* v, const float* bq, void* out, float* lse, int32_t dtype,
                          const pvrl_pooled_attn_t* a, void* stream);
-int pvrl_pooled_attn_bwd(const void* q, const void* k, const void* v, const float* bq, const void* out, const void* dout,
-                         const float* lse, void* dq, float* dk, float* dv, float* dbq, float* delta, int32_t dtype,
+int pvrl_pooled_attn_bwd(const void* q, const void* k, const void* v, const float* bq, const void* dout, const float* lse,
+                         void* dq, float* dk, float* dv, float* dbq, float* delta, int32_t dtype,
                          const pvrl_pooled_attn_t* a, void* stream);
 
 /* ---- misc ----------------------------------------------------------------------------------------------- */

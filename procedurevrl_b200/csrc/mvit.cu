@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(AT_WARPS * 32) pooled_attn_fwd_kernel(const T*
                                                                         const T* __restrict__ v,
                                                                         const float* __restrict__ bq, T* __restrict__ out,
                                                                         float* __restrict__ lse, AttnGeom g) {
-  __shared__ float qs[AT_WARPS][AT_QPW][AT_C];
+  __shared__ __align__(16) float qs[AT_WARPS][AT_QPW][AT_C];
   __shared__ float ps[AT_WARPS][AT_QPW][32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int bh = blockIdx.y, KB = g.Kt + g.Kh + g.Kw;
@@ -498,18 +498,23 @@ __global__ void __launch_bounds__(AT_WARPS * 32) pooled_attn_fwd_kernel(const T*
   }
 }
 
-// dQ pass (a warp owns AT_QPW queries and walks the keys):  p = exp(s - lse), dP = dO . v, dS = p (dP - delta),
-// dq = scale * sum_j dS k_j (+ dO for the residual pooling), dbq[i, component(j)] += dS;  delta = dO . (O - q[i>0]) is
-// written for the dKV pass.  dq has the layout of q; dbq the layout of bq (every row written once, no atomics in HBM).
+// dQ pass (a warp owns AT_QPW queries and walks the keys ONCE):  p = exp(s - lse), dP = dO . v, dS = p (dP - delta) with
+// delta = sum_j p dP (= dO . O_attn) -- not known until the walk ends, so the pass accumulates the two halves of
+//   dq  = scale * (sum_j p dP k_j  -  delta * sum_j p k_j)  (+ dO for the residual pooling)
+//   dbq[i, component(j)] = sum_j p dP - delta * sum_j p      (per component group)
+// separately and combines them at the end, all in fp32 (nothing is derived from the rounded forward output).
+// delta [BH, Nq] is written for the dKV pass; dq has the layout of q; dbq the layout of bq (every row written once).
 template <typename T>
 __global__ void __launch_bounds__(AT_WARPS * 32) pooled_attn_bwd_q_kernel(
     const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const float* __restrict__ bq,
-    const T* __restrict__ out, const T* __restrict__ dout, const float* __restrict__ lse, T* __restrict__ dq,
-    float* __restrict__ dbq, float* __restrict__ delta, AttnGeom g) {
-  __shared__ float qs[AT_WARPS][AT_QPW][AT_C];
-  __shared__ float dos[AT_WARPS][AT_QPW][AT_C];
-  __shared__ float dss[AT_WARPS][AT_QPW][32];
-  __shared__ float dbs[AT_WARPS][AT_QPW][AT_KBMAX];
+    const T* __restrict__ dout, const float* __restrict__ lse, T* __restrict__ dq, float* __restrict__ dbq,
+    float* __restrict__ delta, AttnGeom g) {
+  __shared__ __align__(16) float qs[AT_WARPS][AT_QPW][AT_C];
+  __shared__ __align__(16) float dos[AT_WARPS][AT_QPW][AT_C];
+  __shared__ float pss[AT_WARPS][AT_QPW][32];
+  __shared__ float pds[AT_WARPS][AT_QPW][32];
+  __shared__ float dbp[AT_WARPS][AT_QPW][AT_KBMAX];    // sum of p per bias component
+  __shared__ float dbd[AT_WARPS][AT_QPW][AT_KBMAX];    // sum of p * dP per bias component
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int bh = blockIdx.y, KB = g.Kt + g.Kh + g.Kw;
   const int b = bh / g.heads, h = bh % g.heads;
@@ -519,33 +524,30 @@ __global__ void __launch_bounds__(AT_WARPS * 32) pooled_attn_bwd_q_kernel(
   const T* kb = k + (size_t)bh * g.Nk * AT_C;
   const T* vb = v + (size_t)bh * g.Nk * AT_C;
   const size_t orow_pitch = (size_t)g.heads * AT_C;
-  float dl[AT_QPW], ls[AT_QPW];
+  float ls[AT_QPW], dpart[AT_QPW];
 #pragma unroll
   for (int a = 0; a < AT_QPW; ++a) {
     const int i = i0 + a;
-    float part = 0.f;
 #pragma unroll
     for (int d = 0; d < AT_V; ++d) {
       const int c = lane + 32 * d;
-      float qv = 0.f, dv_ = 0.f, ov = 0.f;
+      float qv = 0.f, dv_ = 0.f;
       if (i < g.Nq) {
-        const size_t off = ((size_t)b * g.Nq + i) * orow_pitch + (size_t)h * AT_C + c;
-        qv = ldf(qb + (size_t)i * AT_C + c), dv_ = ldf(dout + off), ov = ldf(out + off);
+        qv = ldf(qb + (size_t)i * AT_C + c);
+        dv_ = ldf(dout + ((size_t)b * g.Nq + i) * orow_pitch + (size_t)h * AT_C + c);
       }
       qs[wid][a][c] = qv * g.scale, dos[wid][a][c] = dv_;
-      part += dv_ * (ov - ((g.resid && i > 0) ? qv : 0.f));
     }
-    dl[a] = wsum(part);
     ls[a] = (i < g.Nq) ? lse[(size_t)bh * g.Nq + i] : 0.f;
-    if (lane == 0 && i < g.Nq) delta[(size_t)bh * g.Nq + i] = dl[a];
-    for (int e = lane; e < AT_KBMAX; e += 32) dbs[wid][a][e] = 0.f;
+    dpart[a] = 0.f;
+    for (int e = lane; e < AT_KBMAX; e += 32) dbp[wid][a][e] = 0.f, dbd[wid][a][e] = 0.f;
   }
   __syncwarp();
-  float acc[AT_QPW][AT_V];
+  float acd[AT_QPW][AT_V], acp[AT_QPW][AT_V];
 #pragma unroll
   for (int a = 0; a < AT_QPW; ++a)
 #pragma unroll
-    for (int d = 0; d < AT_V; ++d) acc[a][d] = 0.f;
+    for (int d = 0; d < AT_V; ++d) acd[a][d] = 0.f, acp[a][d] = 0.f;
   for (int j0 = 0; j0 < g.Nk; j0 += 32) {
     const int j = j0 + lane;
     const bool valid = j < g.Nk;
@@ -581,20 +583,21 @@ __global__ void __launch_bounds__(AT_WARPS * 32) pooled_attn_bwd_q_kernel(
 #pragma unroll
     for (int a = 0; a < AT_QPW; ++a) {
       const int i = i0 + a;
-      float ds = 0.f;
+      float p = 0.f, pd = 0.f;
       if (valid && i < g.Nq) {
         float sc = s[a];
         const bool biased = j > 0 && i > 0;
         if (biased) sc += attn_bias(bq + ((size_t)bh * (g.Nq - 1) + (i - 1)) * KB, j, g);
-        const float p = expf(sc - ls[a]);
-        ds = p * (dp[a] - dl[a]);
+        p = expf(sc - ls[a]);
+        pd = p * dp[a];
         if (biased) {
-          atomicAdd(&dbs[wid][a][kt], ds);
-          atomicAdd(&dbs[wid][a][g.Kt + kh], ds);
-          atomicAdd(&dbs[wid][a][g.Kt + g.Kh + kw], ds);
+          atomicAdd(&dbp[wid][a][kt], p), atomicAdd(&dbd[wid][a][kt], pd);
+          atomicAdd(&dbp[wid][a][g.Kt + kh], p), atomicAdd(&dbd[wid][a][g.Kt + kh], pd);
+          atomicAdd(&dbp[wid][a][g.Kt + g.Kh + kw], p), atomicAdd(&dbd[wid][a][g.Kt + g.Kh + kw], pd);
         }
       }
-      dss[wid][a][lane] = ds;
+      dpart[a] += pd;
+      pss[wid][a][lane] = p, pds[wid][a][lane] = pd;
     }
     __syncwarp();
     const int nj = min(32, g.Nk - j0);
@@ -605,9 +608,9 @@ __global__ void __launch_bounds__(AT_WARPS * 32) pooled_attn_bwd_q_kernel(
       for (int d = 0; d < AT_V; ++d) kf[d] = ldf(kr + lane + 32 * d);
 #pragma unroll
       for (int a = 0; a < AT_QPW; ++a) {
-        const float ds = dss[wid][a][jj];
+        const float p = pss[wid][a][jj], pd = pds[wid][a][jj];
 #pragma unroll
-        for (int d = 0; d < AT_V; ++d) acc[a][d] += ds * kf[d];
+        for (int d = 0; d < AT_V; ++d) acp[a][d] += p * kf[d], acd[a][d] += pd * kf[d];
       }
     }
     __syncwarp();
@@ -616,15 +619,18 @@ __global__ void __launch_bounds__(AT_WARPS * 32) pooled_attn_bwd_q_kernel(
   for (int a = 0; a < AT_QPW; ++a) {
     const int i = i0 + a;
     if (i >= g.Nq) break;
+    const float dl = wsum(dpart[a]);
+    if (lane == 0) delta[(size_t)bh * g.Nq + i] = dl;
 #pragma unroll
     for (int d = 0; d < AT_V; ++d) {
       const int c = lane + 32 * d;
-      float r = acc[a][d] * g.scale;
+      float r = (acd[a][d] - dl * acp[a][d]) * g.scale;
       if (g.resid && i > 0) r += dos[wid][a][c];
       stf(dq + ((size_t)bh * g.Nq + i) * AT_C + c, r);
     }
     if (i > 0)
-      for (int e = lane; e < KB; e += 32) dbq[((size_t)bh * (g.Nq - 1) + (i - 1)) * KB + e] = dbs[wid][a][e];
+      for (int e = lane; e < KB; e += 32)
+        dbq[((size_t)bh * (g.Nq - 1) + (i - 1)) * KB + e] = dbd[wid][a][e] - dl * dbp[wid][a][e];
   }
 }
 
@@ -635,8 +641,8 @@ __global__ void __launch_bounds__(AT_WARPS * 32) pooled_attn_bwd_kv_kernel(
     const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const float* __restrict__ bq,
     const T* __restrict__ dout, const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dk,
     float* __restrict__ dv, AttnGeom g) {
-  __shared__ float ks[AT_WARPS][AT_QPW][AT_C];
-  __shared__ float vs[AT_WARPS][AT_QPW][AT_C];
+  __shared__ __align__(16) float ks[AT_WARPS][AT_QPW][AT_C];
+  __shared__ __align__(16) float vs[AT_WARPS][AT_QPW][AT_C];
   __shared__ float ps[AT_WARPS][AT_QPW][32];
   __shared__ float dss[AT_WARPS][AT_QPW][32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -951,22 +957,20 @@ extern "C" int pvrl_pooled_attn_fwd(const void* q, const void* k, const void* v,
   return launched("pooled_attn_fwd_kernel");
 }
 
-extern "C" int pvrl_pooled_attn_bwd(const void* q, const void* k, const void* v, const float* bq, const void* out,
-                                    const void* dout, const float* lse, void* dq, float* dk, float* dv, float* dbq,
-                                    float* delta, int32_t dtype, const pvrl_pooled_attn_t* a, void* stream) {
+extern "C" int pvrl_pooled_attn_bwd(const void* q, const void* k, const void* v, const float* bq, const void* dout,
+                                    const float* lse, void* dq, float* dk, float* dv, float* dbq, float* delta,
+                                    int32_t dtype, const pvrl_pooled_attn_t* a, void* stream) {
   int rc = check_attn(a, "pvrl_pooled_attn_bwd");
   if (rc) return rc;
-  PVRL_CHECK_ARG(q && k && v && bq && out && dout && lse && dq && dk && dv && dbq && delta, "pvrl_pooled_attn_bwd: null buffer");
+  PVRL_CHECK_ARG(q && k && v && bq && dout && lse && dq && dk && dv && dbq && delta, "pvrl_pooled_attn_bwd: null buffer");
   AttnGeom g = to_attn(a);
   const dim3 gq((g.Nq + AT_WARPS * AT_QPW - 1) / (AT_WARPS * AT_QPW), g.BH);
   if (dtype == PVRL_F32)
     pooled_attn_bwd_q_kernel<float><<<gq, AT_WARPS * 32, 0, STREAM>>>((const float*)q, (const float*)k, (const float*)v, bq,
-                                                                      (const float*)out, (const float*)dout, lse, (float*)dq,
-                                                                      dbq, delta, g);
+                                                                      (const float*)dout, lse, (float*)dq, dbq, delta, g);
   else
     pooled_attn_bwd_q_kernel<bf16><<<gq, AT_WARPS * 32, 0, STREAM>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, bq,
-                                                                     (const bf16*)out, (const bf16*)dout, lse, (bf16*)dq, dbq,
-                                                                     delta, g);
+                                                                     (const bf16*)dout, lse, (bf16*)dq, dbq, delta, g);
   rc = launched("pooled_attn_bwd_q_kernel");
   if (rc) return rc;
   // dK / dV: cut the query range so that the grid fills the chip (few keys, many queries), >= 256 queries per slice

@@ -137,20 +137,20 @@ class _PooledAttention(torch.autograd.Function):
         out = torch.empty(B, Nq, Hh * C, device=q.device, dtype=q.dtype)
         lse = torch.empty(B, Hh, Nq, device=q.device, dtype=torch.float32)
         ops.pooled_attn_fwd(q, k, v, bq, out, lse, k_grid, scale, residual_pooling)
-        ctx.save_for_backward(q, k, v, bq, out, lse)
+        ctx.save_for_backward(q, k, v, bq, lse)
         ctx.cfg = (tuple(k_grid), scale, residual_pooling)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        q, k, v, bq, out, lse = ctx.saved_tensors
+        q, k, v, bq, lse = ctx.saved_tensors
         k_grid, scale, resid = ctx.cfg
         dq = torch.empty_like(q)
         dk = torch.zeros(k.shape, device=k.device, dtype=torch.float32)
         dv = torch.zeros(v.shape, device=v.device, dtype=torch.float32)
         dbq = torch.empty_like(bq)
         delta = torch.empty_like(lse)
-        ops.pooled_attn_bwd(q, k, v, bq, out, _act(dout, q.dtype).contiguous(), lse, dq, dk, dv, dbq, delta, k_grid, scale, resid)
+        ops.pooled_attn_bwd(q, k, v, bq, _act(dout, q.dtype).contiguous(), lse, dq, dk, dv, dbq, delta, k_grid, scale, resid)
         return dq, _act(dk, k.dtype), _act(dv, v.dtype), dbq, None, None, None
 
 

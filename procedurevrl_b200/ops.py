@@ -106,7 +106,7 @@ _SIGS = {
     "pvrl_pooled_attn_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int,
                              ctypes.POINTER(PooledAttnDesc), _c_void_p],
     "pvrl_pooled_attn_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
-                             _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, ctypes.POINTER(PooledAttnDesc), _c_void_p],
+                             _c_void_p, _c_void_p, _c_void_p, _c_int, ctypes.POINTER(PooledAttnDesc), _c_void_p],
     "pvrl_optim_tick": [_c_void_p, _c_void_p],
     "pvrl_adam_flat": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_i64, _c_void_p, _c_void_p, _c_float,
                        ctypes.c_double, ctypes.c_double, _c_float, _c_float, _c_int, _c_float, _c_int, _c_void_p],
@@ -579,10 +579,10 @@ def pooled_attn_fwd(q, k, v, bq, out, lse, kgrid, scale, resid):
     return out
 
 
-def pooled_attn_bwd(q, k, v, bq, out, dout, lse, dq, dk, dv, dbq, delta, kgrid, scale, resid):
+def pooled_attn_bwd(q, k, v, bq, dout, lse, dq, dk, dv, dbq, delta, kgrid, scale, resid):
     """dq (like q), dbq (like bq), delta written; dk / dv fp32, zero-initialised by the caller, accumulated."""
     _f32c(bq, lse, dk, dv, dbq, delta)
     assert dout.is_contiguous() and dout.dtype == q.dtype and dq.dtype == q.dtype and dq.is_contiguous()
     d = _attn_desc(q, k, kgrid, scale, resid)
-    _check(lib().pvrl_pooled_attn_bwd(_p(q), _p(k), _p(v), _p(bq), _p(out), _p(dout), _p(lse), _p(dq), _p(dk), _p(dv),
+    _check(lib().pvrl_pooled_attn_bwd(_p(q), _p(k), _p(v), _p(bq), _p(dout), _p(lse), _p(dq), _p(dk), _p(dv),
                                       _p(dbq), _p(delta), _dt(q), ctypes.byref(d), _stream()), "pvrl_pooled_attn_bwd")

@@ -562,7 +562,7 @@ def pooled_attn_fwd(q, k, v, bq, out, lse, kgrid, scale, resid):
     return out
 
 
-def pooled_attn_bwd(q, k, v, bq, out, dout, lse, dq, dk, dv, dbq, delta, kgrid, scale, resid):
+def pooled_attn_bwd(q, k, v, bq, dout, lse, dq, dk, dv, dbq, delta, kgrid, scale, resid):
     _launches[0] += 2
     with torch.enable_grad():
         ins = [t.detach().float().clone().requires_grad_(True) for t in (q, k, v, bq)]
@@ -573,10 +573,8 @@ def pooled_attn_bwd(q, k, v, bq, out, dout, lse, dq, dk, dv, dbq, delta, kgrid, 
     dv += gv
     dbq.copy_(gb)
     B, Hh, Nq, C = q.shape
-    o_attn = out.float().reshape(B, Nq, Hh, C).transpose(1, 2).clone()
-    if resid:
-        o_attn[:, :, 1:] -= q.float()[:, :, 1:]
-    delta.copy_((dout.float().reshape(B, Nq, Hh, C).transpose(1, 2) * o_attn).sum(-1))
+    o_attn, _ = _pooled_attn(q.float(), k.float(), v.float(), bq, kgrid, scale, False)      # delta = dO . (P V)
+    delta.copy_((dout.float() * o_attn).reshape(B, Nq, Hh, C).sum(-1).transpose(1, 2))
 
 
 ALL = [n for n, v in list(globals().items()) if callable(v) and not n.startswith("_") and n not in ("F", "math", "torch")]

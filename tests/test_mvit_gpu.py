@@ -1,0 +1,267 @@
+"""MViTv2 path (BASELINE config 5) on the GPU: every kernel of csrc/mvit.cu through the C ABI against its torch
+restatement (tests/shadow_ops.py, evaluated on the same device in fp32), then the whole model mirror against the golden
+vectors of the unmodified reference (tests/golden/mvit_*.pt) and a full-size MViTv2-S 16 x 224 training step.
+Tolerances: fp32 kernels 2e-5 .. 2e-4 of the output range (summation order), bf16 I/O 2e-2; model logits rtol 1e-3 /
+atol 5e-3 with bit-equal argmax in the parity mode (the north star's tolerance)."""
+import json
+import os
+
+import pytest
+import torch
+
+import mvit_oracle as MO
+import shadow_ops as S
+from procedurevrl_b200 import mvit_functional as MF
+from procedurevrl_b200 import ops
+from test_mvit_cpu import build, mvit_cfg
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+# the restatements must be fp32 references: cuDNN's conv3d / cuBLAS would otherwise run TF32 (first GPU run: conv weight
+# gradients of the restatement were 3e-4 off the fp32 kernels)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+
+
+def rel(a, b):
+    return (a.float() - b.float()).abs().max().item() / (b.float().abs().max().item() + 1e-12)
+
+
+def rnd(*shape, seed=0, dtype=torch.float32, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (scale * torch.randn(*shape, generator=g)).to(DEV).to(dtype)
+
+
+@pytest.mark.parametrize("D", [96, 192, 384, 768, 100])
+@pytest.mark.parametrize("xdt,ydt", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
+                                     (torch.bfloat16, torch.bfloat16)])
+def test_ln_any(D, xdt, ydt):
+    need_gpu()
+    M = 1111
+    x, w, b = rnd(M, D, seed=1, dtype=xdt), 1 + 0.1 * rnd(D, seed=2), 0.1 * rnd(D, seed=3)
+    dy = rnd(M, D, seed=4, dtype=ydt)
+    tol = 3e-5 if ydt == torch.float32 else 1.5e-2
+    out = []
+    for o in (ops, S):
+        y, st = torch.empty(M, D, device=DEV, dtype=ydt), torch.empty(M, 2, device=DEV)
+        o.ln_any_fwd(x, w, b, y, st, M, D, 1e-6)
+        dx, dw, db = torch.empty_like(x), torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
+        o.ln_any_bwd(dy, x, w, st, dx, dw, db, M, D)
+        out.append((y, st, dx, dw, db))
+    for name, a, r in zip(("y", "stats", "dx", "dw", "db"), *out):
+        assert rel(a, r) < (tol if name in ("y", "dx") else 2e-4), (name, D, rel(a, r))
+
+
+POOLS = [  # B, heads, grid, stride, pooled?
+    (2, 2, (4, 8, 8), (1, 2, 2), True), (1, 4, (2, 7, 7), (1, 1, 1), True), (2, 1, (2, 16, 16), (1, 4, 4), True),
+    (1, 2, (3, 5, 6), (1, 1, 1), False), (1, 1, (8, 6, 6), (2, 2, 2), True)]
+
+
+@pytest.mark.parametrize("B,heads,grid,stride,pooled", POOLS)
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_pool3d(B, heads, grid, stride, pooled, dt):
+    need_gpu()
+    C, L = 96, grid[0] * grid[1] * grid[2]
+    ld = 3 * heads * C
+    src = rnd(B, 1 + L, ld, seed=5, dtype=dt)
+    w = 0.3 * rnd(C, 27, seed=6) if pooled else None
+    kern, pad = ((3, 3, 3), (1, 1, 1)) if pooled else ((1, 1, 1), (0, 0, 0))
+    st = stride if pooled else (1, 1, 1)
+    og = ops.pool_out_grid(grid, kern, st, pad)
+    Lo = og[0] * og[1] * og[2]
+    tol = 2e-5 if dt == torch.float32 else 1.5e-2
+    for which in (0, 2):
+        col0 = which * heads * C
+        dout = rnd(B, heads, 1 + Lo, C, seed=7 + which, dtype=dt)
+        res = []
+        for o in (ops, S):
+            out = torch.empty(B, heads, 1 + Lo, C, device=DEV, dtype=dt)
+            o.pool3d_fwd(src, col0, w, out, heads, C, grid, kern, st, pad)
+            din = torch.full((B, 1 + L, ld), 7.0, device=DEV, dtype=dt)
+            dw = None if w is None else torch.zeros(C, 27, device=DEV)
+            o.pool3d_bwd(dout, src, col0, w, din, dw, heads, C, grid, kern, st, pad)
+            res.append((out, din, dw))
+        (o1, d1, w1), (o2, d2, w2) = res
+        assert rel(o1, o2) < tol, ("out", rel(o1, o2))
+        assert rel(d1[:, :, col0:col0 + heads * C], d2[:, :, col0:col0 + heads * C]) < tol, "din"
+        other = torch.ones(ld, dtype=torch.bool)
+        other[col0:col0 + heads * C] = False
+        assert (d1[:, :, other.to(DEV)] == 7.0).all(), "pool3d_bwd wrote outside its column slice"
+        if w is not None:
+            assert rel(w1, w2) < (2e-4 if dt == torch.float32 else 2e-2), ("dw", rel(w1, w2))
+
+
+@pytest.mark.parametrize("B,D,grid,stride", [(2, 192, (2, 8, 8), (1, 2, 2)), (1, 96, (4, 7, 9), (1, 2, 2)), (1, 384, (4, 6, 6), (2, 2, 2))])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_maxpool3d(B, D, grid, stride, dt):
+    need_gpu()
+    L = grid[0] * grid[1] * grid[2]
+    kern = tuple(s + 1 if s > 1 else s for s in stride)
+    pad = tuple(k // 2 for k in kern)
+    og = ops.pool_out_grid(grid, kern, stride, pad)
+    Lo = og[0] * og[1] * og[2]
+    x = rnd(B, 1 + L, D, seed=11, dtype=dt)
+    dy = rnd(B, 1 + Lo, D, seed=12, dtype=dt)
+    res = []
+    for o in (ops, S):
+        y, arg = torch.empty(B, 1 + Lo, D, device=DEV, dtype=dt), torch.empty(B, Lo, D, device=DEV, dtype=torch.int32)
+        o.maxpool3d_fwd(x, y, arg, grid, kern, stride, pad)
+        dx = torch.zeros(B, 1 + L, D, device=DEV)
+        o.maxpool3d_bwd(dy, arg, dx, grid, kern, stride, pad)
+        res.append((y, arg, dx))
+    (y1, a1, d1), (y2, a2, d2) = res
+    assert torch.equal(y1, y2)
+    if dt == torch.float32:                       # bf16 inputs tie; ATen's tie order is checked through the values instead
+        assert torch.equal(a1, a2)
+        assert rel(d1, d2) < 1e-6
+    else:
+        picked = torch.gather(x[:, 1:].float(), 1, a1.long())
+        assert torch.equal(picked, y1[:, 1:].float())
+        assert abs(d1.sum().item() - dy.float().sum().item()) < 1e-2 * dy.float().abs().sum().item()
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_im2col3d(dt):
+    need_gpu()
+    frames = rnd(2, 3, 4, 32, 36, seed=13)
+    kern, stride, pad = (3, 7, 7), (2, 4, 4), (1, 3, 3)
+    og = ops.pool_out_grid((4, 32, 36), kern, stride, pad)
+    rows = 2 * og[0] * og[1] * og[2]
+    a = ops.im2col3d(frames, torch.full((rows, 448), 5.0, device=DEV, dtype=dt), kern, stride, pad)
+    b = S.im2col3d(frames, torch.empty(rows, 448, device=DEV, dtype=dt), kern, stride, pad)
+    assert torch.equal(a, b)
+    r2, g2 = MF.conv3d_stem_rows(frames, kern, stride, pad, dt)
+    assert list(g2) == og and torch.equal(r2, b)
+
+
+ATTN = [  # B, heads, q grid, k grid
+    (2, 2, (2, 8, 8), (2, 4, 4)), (1, 1, (1, 5, 5), (1, 3, 3)), (1, 3, (4, 14, 14), (4, 7, 7)), (2, 1, (2, 4, 4), (2, 8, 8)),
+    (1, 2, (8, 7, 7), (8, 7, 7))]
+
+
+@pytest.mark.parametrize("B,heads,qg,kg", ATTN)
+@pytest.mark.parametrize("dt,resid", [(torch.float32, True), (torch.float32, False), (torch.bfloat16, True)])
+def test_pooled_attention(B, heads, qg, kg, dt, resid):
+    need_gpu()
+    C = 96
+    Nq, Nk = 1 + qg[0] * qg[1] * qg[2], 1 + kg[0] * kg[1] * kg[2]
+    KB = kg[0] + kg[1] + kg[2]
+    q, k, v = (rnd(B, heads, n, C, seed=20 + i, dtype=dt) for i, n in enumerate((Nq, Nk, Nk)))
+    bq = rnd(B, heads, Nq - 1, KB, seed=24, scale=0.5)
+    dout = rnd(B, Nq, heads * C, seed=25, dtype=dt)
+    scale = C ** -0.5
+    res = []
+    for o in (ops, S):
+        out, lse = torch.empty(B, Nq, heads * C, device=DEV, dtype=dt), torch.empty(B, heads, Nq, device=DEV)
+        o.pooled_attn_fwd(q, k, v, bq, out, lse, kg, scale, resid)
+        dq = torch.empty_like(q)
+        dk, dv = torch.zeros(B, heads, Nk, C, device=DEV), torch.zeros(B, heads, Nk, C, device=DEV)
+        dbq, delta = torch.empty_like(bq), torch.empty_like(lse)
+        o.pooled_attn_bwd(q, k, v, bq, dout, lse, dq, dk, dv, dbq, delta, kg, scale, resid)
+        res.append((out, lse, dq, dk, dv, dbq, delta))
+    tol = 5e-5 if dt == torch.float32 else 2.5e-2
+    for name, a, r in zip(("out", "lse", "dq", "dk", "dv", "dbq", "delta"), *res):
+        assert torch.isfinite(a.float()).all(), name
+        assert rel(a, r) < tol, (name, rel(a, r))
+
+
+def test_autograd_functions_match_torch():
+    """The Functions of mvit_functional end to end (save-for-backward, dtype routing) against autograd of the restatement."""
+    need_gpu()
+    B, heads, C, grid = 2, 2, 96, (2, 8, 8)
+    L = grid[0] * grid[1] * grid[2]
+    qkv = rnd(B, 1 + L, 3 * heads * C, seed=30).requires_grad_(True)
+    wq, wk, wv = (0.3 * rnd(C, 1, 3, 3, 3, seed=31 + i) for i in range(3))
+    for w in (wq, wk, wv):
+        w.requires_grad_(True)
+    rel_h, rel_w, rel_t = (0.2 * rnd(n, C, seed=35 + i) for i, n in enumerate((15, 15, 3)))
+    for t in (rel_h, rel_w, rel_t):
+        t.requires_grad_(True)
+
+    def run(mod_ops):
+        saved = {n: getattr(ops, n) for n in S.ALL if hasattr(ops, n)}
+        try:
+            if mod_ops is S:
+                for n in saved:
+                    setattr(ops, n, getattr(S, n))
+            q, k, v = MF.pool_qkv(qkv, wq, wk, wv, heads, C, grid, (3, 3, 3), (1, 1, 1), (1, 2, 2))
+            lnw, lnb = torch.ones(C, device=DEV, requires_grad=True), torch.zeros(C, device=DEV, requires_grad=True)
+            q = MF.layer_norm(q, lnw, lnb, 1e-6, torch.float32)
+            bq = MF.rel_pos_projections(q, grid, (2, 4, 4), rel_h, rel_w, rel_t)
+            o = MF.pooled_attention(q, k, v, bq, (2, 4, 4), C ** -0.5, True)
+            y = MF.max_pool_skip(o, grid, (1, 2, 2))
+            g = torch.autograd.grad((y * y).sum(), (qkv, wq, wk, wv, rel_h, rel_w, rel_t, lnw, lnb))
+            return (y,) + g
+        finally:
+            for n, f in saved.items():
+                setattr(ops, n, f)
+
+    for i, (a, r) in enumerate(zip(run(ops), run(S))):
+        assert rel(a, r) < 3e-4, (i, rel(a, r))
+
+
+@pytest.mark.parametrize("case", ["d4_t4_c64", "d3_t8_c96"])
+def test_model_matches_reference_goldens(gold_dir, case):
+    need_gpu()
+    g = torch.load(os.path.join(gold_dir, f"mvit_{case}.pt"))
+    c = g["cfg"]
+    m = build(gold_dir, g, "bf16x3").to(DEV)
+    x = MO.synthetic_clips(c["B"], c["frames"], c["crop"], c["seed"] + 1).to(DEV)
+    taps = []
+    enc = m.model.video_encoder
+    orig = enc.forward
+    enc.forward = lambda clips: orig(clips, taps=taps)
+    n0 = ops.launch_count()
+    logits = m(x)
+    assert ops.launch_count() > n0, "no kernel of libpvrl_sm100.so was launched"
+    torch.testing.assert_close(logits.detach().cpu(), g["logits"], rtol=1e-3, atol=5e-3)
+    assert torch.equal(logits.argmax(1).cpu(), g["logits"].argmax(1))
+    for t, ref in zip(taps, g["taps"]):
+        torch.testing.assert_close(t[:, 0].detach().cpu(), ref["cls"], rtol=1e-3, atol=1e-4)
+    loss = torch.nn.functional.cross_entropy(logits, g["labels"].to(DEV))
+    assert abs(loss.item() - g["loss"]) <= 1e-3 * abs(g["loss"])
+    loss.backward()
+    got = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+    assert set(got) == set(g["grads"])
+    for k, ref in g["grads"].items():
+        assert abs(got[k].norm().item() - ref["norm"]) <= 1e-2 * ref["norm"] + 1e-7, k
+        torch.testing.assert_close(got[k].flatten()[:32].cpu(), ref["head"], rtol=1e-2, atol=1e-6 + 1e-3 * ref["norm"],
+                                   msg=lambda s, k=k: f"{k}: {s}")
+    # throughput mode on the same weights: bf16 operands / activations
+    os.environ["PVRL_PRECISION"] = "bf16"
+    try:
+        lb = m(x)
+    finally:
+        del os.environ["PVRL_PRECISION"]
+    assert (lb.detach().cpu() - g["logits"]).abs().max().item() < 1.0
+
+
+def test_full_size_training_step(gold_dir):
+    """MViTv2-S 16 x 224 as shipped (25 089 -> 393 tokens, 393 / 1 569 pooled keys): one clip forward + backward in the
+    throughput mode: finite, deterministic forward, every encoder parameter receives a gradient."""
+    need_gpu()
+    with open(os.path.join(gold_dir, "mvit_full_geometry.json")) as f:
+        fg = json.load(f)
+    torch.manual_seed(0)
+    from procedurevrl_b200.lib.models import MODEL_REGISTRY
+    m = MODEL_REGISTRY.get("MViT")(mvit_cfg(gold_dir, fg["mvit"], 16, 224, "bf16")).to(DEV).train()
+    for p in m.parameters():
+        p.requires_grad_(True)
+    x = MO.synthetic_clips(1, 16, 224, 5).to(DEV)
+    torch.cuda.synchronize()
+    t0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0[0].record()
+    a = m(x)
+    a.logsumexp(1).sum().backward()
+    t0[1].record()
+    torch.cuda.synchronize()
+    print(f"MViTv2-S 16x224, 1 clip fwd+bwd: {t0[0].elapsed_time(t0[1]):.1f} ms (first call, includes operand casts)")
+    b = m(x)
+    assert a.shape == (1, 778) and torch.isfinite(a).all() and torch.equal(a, b)
+    missing = [k for k, p in m.model.video_encoder.named_parameters() if p.grad is None or not torch.isfinite(p.grad).all()]
+    assert not missing, missing
