@@ -104,6 +104,81 @@ def one_case(name, frames, crop, B, seed, ov):
     print(name, "logits", tuple(logits.shape), "loss", round(loss.item(), 5), "grads", len(grads), os.path.getsize(path), "bytes")
 
 
+def pretrain_case(name="pretrain_d4_t4_c64", case="d4_t4_c64", Bv=1, seed=303):
+    """BASELINE config 5 as the driver runs it (tools/train_net.py:146-162 on procedurevrl_mvitv2_adamw.yaml): one video of
+    9 clips through the MViT encoder, head, order transformer, teacher and the KL(top-k) + MSE loss, and its backward --
+    reduced geometry, COIN step bank as LABEL_EMB, the CLIP text tower replaced by pre-extracted embeddings (north star).
+    Records the reference's random draws so that the mirror can replay them."""
+    import make_golden as MG
+    import timesformer_oracle as TO
+    import torch.nn.functional as F
+    c = CASES[case]
+    frames, crop, max_len = c["frames"], c["crop"], 9
+    ref_shims.install()
+    cwd = os.getcwd()
+    os.chdir(ref_shims.REFERENCE_ROOT)
+    try:
+        cfg = ref_shims.reference_cfg(YAML, [
+            "DATA.NUM_FRAMES", frames, "DATA.TRAIN_CROP_SIZE", crop, "DATA.TEST_CROP_SIZE", crop,
+            "TRAIN.LABEL_EMB", "./data/clip_step_emb_coin.pth", "MODEL.NUM_CLASSES", 778, "TRAIN.TEXT", "preextracted"] + c["ov"])
+        mv = importlib.import_module("lib.models.mvit")
+        m = mv.MViT(cfg)
+    finally:
+        os.chdir(cwd)
+    own = m.state_dict()
+    shapes = {k: tuple(v.shape) for k, v in own.items() if k.startswith(MO.PRE) or k.startswith("model.head.")}
+    state = MO.seeded_state(shapes, seed)
+    order = {k: v for k, v in TO.seeded_state(depth=1, frames=8, seed=seed + 1, with_order=True).items()
+             if k.startswith("model.order_tfm.")}
+    assert {k: tuple(v.shape) for k, v in order.items()} == {k: tuple(v.shape) for k, v in own.items() if k.startswith("model.order_tfm.")}
+    state.update(order)
+    for k in own:
+        if k.startswith("model.text_model."):
+            state[k] = own[k]
+    m.load_state_dict(state, strict=True)
+    m.model.label_emb = m.model.label_emb / m.model.label_emb.norm(dim=1, keepdim=True)
+    g = torch.Generator().manual_seed(seed + 2)
+    text_emb = 0.4 * torch.randn(Bv * max_len, 512, generator=g)
+    vis_emb = 0.4 * torch.randn(Bv * max_len, 512, generator=g)
+    m.model.text_model.encode_text = lambda ids: text_emb
+    x = MO.synthetic_clips(Bv * max_len, frames, crop, seed + 3).reshape(Bv, max_len, 3, frames, crop, crop)
+    meta = {"clip_text_ids": torch.zeros(Bv * max_len, 77, dtype=torch.long), "clip_vis_feat": vis_emb}
+    m.train()
+    m.model.text_model.eval()
+    torch.manual_seed(11)
+    log = []
+    with MG.record_rng(log):
+        pred, teacher, mse = m([x, meta])
+    ints = [t for n, t in log if n == "randint"]
+    mask_inds = ints[0]
+    pad_start = torch.full((Bv,), max_len, dtype=torch.long)
+    j = 1
+    for i in range(Bv):
+        if int(mask_inds[i]) + 1 != max_len:
+            pad_start[i] = int(ints[j])
+            j += 1
+    noise = torch.stack([t for n, t in log if n == "randn_like"])
+    rand_inds = [t for n, t in log if n == "randperm"][0]
+    with torch.no_grad():                                       # tools/train_net.py:152-162
+        tp = F.softmax(teacher, 1)
+        tp = (tp.unsqueeze(1) * (tp.unsqueeze(1) == tp.topk(k=cfg.TRAIN.TOPK, dim=1)[0].unsqueeze(2)).float()).sum(1)
+        tp = tp / tp.sum(1, keepdim=True)
+    loss1 = torch.nn.KLDivLoss(reduction="batchmean")(F.log_softmax(pred, dim=1), tp)
+    loss2 = torch.nn.MSELoss(reduction="mean")(mse[0], mse[1])
+    (loss1 + loss2).backward()
+    grads = {k: {"norm": p.grad.norm().item(), "sum": p.grad.double().sum().item(), "head": p.grad.flatten()[:32].clone()}
+             for k, p in m.named_parameters() if p.grad is not None}
+    out = {"cfg": {"case": case, "frames": frames, "crop": crop, "Bv": Bv, "seed": seed, "mvit": mvit_keys(cfg), "topk": cfg.TRAIN.TOPK},
+           "shapes": {k: tuple(v.shape) for k, v in own.items() if not k.startswith("model.text_model.")},
+           "draws": {"mask_inds": mask_inds, "pad_start": pad_start, "noise": noise, "rand_inds": rand_inds},
+           "pred": pred.detach().clone(), "teacher": teacher.detach().clone(), "mse0": mse[0].detach().clone(),
+           "mse1": mse[1].detach().clone(), "loss1": loss1.item(), "loss2": loss2.item(), "grads": grads, "n_grads": len(grads)}
+    path = os.path.join(GOLD, f"mvit_{name}.pt")
+    torch.save(out, path)
+    print(name, "pred", tuple(pred.shape), "loss", round(loss1.item(), 5), round(loss2.item(), 5), "grads", len(grads),
+          os.path.getsize(path), "bytes")
+
+
 def full_geometry():
     """The shipped 16 x 224 model: only its construction is needed (no forward)."""
     m, cfg = build_reference(16, 224, [])
@@ -128,6 +203,7 @@ def main():
     torch.manual_seed(0)
     for name, c in CASES.items():
         one_case(name, **c)
+    pretrain_case()
     full_geometry()
 
 

@@ -101,6 +101,57 @@ def test_forward_backward_match_reference(shadow, gold_dir, case):
                                    msg=lambda s, k=k: f"{k}: {s}")
 
 
+def pretrain_model(gold_dir, g, precision):
+    """The config-5 pre-training model (TRAIN.LABEL_EMB set, order transformer, text side pre-extracted) with the golden's state."""
+    import timesformer_oracle as TO
+    c = g["cfg"]
+    cfg = mvit_cfg(gold_dir, c["mvit"], c["frames"], c["crop"], precision)
+    cfg.merge_from_list(["DEV.ORDER_PRETRAIN_ENABLED", True, "DEV.ORDER_TFM_LAYERS", 4, "TRAIN.LABEL_EMB",
+                         os.path.join(gold_dir, "clip_step_emb_coin.pt"), "TRAIN.TOPK", c["topk"], "MODEL.LOSS_FUNC", "kldiv",
+                         "MODEL.TEXT_MODEL", "clip_vit_b_16"])
+    m = MODEL_REGISTRY.get("MViT")(cfg)
+    shapes = {k: v for k, v in g["shapes"].items() if k.startswith(MO.PRE) or k.startswith("model.head.")}
+    state = MO.seeded_state(shapes, c["seed"])
+    state.update({k: v for k, v in TO.seeded_state(depth=1, frames=8, seed=c["seed"] + 1, with_order=True).items()
+                  if k.startswith("model.order_tfm.")})
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v) for k, v in g["shapes"].items()}
+    m.load_state_dict(state, strict=True)
+    gen = torch.Generator().manual_seed(c["seed"] + 2)
+    text_emb = 0.4 * torch.randn(c["Bv"] * 9, 512, generator=gen)
+    vis_emb = 0.4 * torch.randn(c["Bv"] * 9, 512, generator=gen)
+    x = MO.synthetic_clips(c["Bv"] * 9, c["frames"], c["crop"], c["seed"] + 3).reshape(c["Bv"], 9, 3, c["frames"], c["crop"], c["crop"])
+    d = g["draws"]
+    m.model.order_tfm.fixed_draws = (d["mask_inds"], d["pad_start"], d["noise"])
+    m.model.fixed_rand_inds = d["rand_inds"]
+    return m.train(), x, {"clip_text_emb": text_emb, "clip_vis_feat": vis_emb}
+
+
+def check_pretrain_step(m, x, meta, g, dev="cpu"):
+    from procedurevrl_b200 import functional as PF
+    pred, teacher, mse = m([x.to(dev), {k: v.to(dev) for k, v in meta.items()}])
+    torch.testing.assert_close(pred.detach().cpu(), g["pred"], rtol=1e-3, atol=5e-3)
+    torch.testing.assert_close(teacher.cpu(), g["teacher"], rtol=1e-4, atol=5e-4)
+    torch.testing.assert_close(mse[0].detach().cpu(), g["mse0"], rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(mse[1].detach().cpu(), g["mse1"], rtol=1e-3, atol=1e-3)
+    loss, l1, l2 = PF.pretrain_loss(pred, teacher, mse, topk=g["cfg"]["topk"])
+    assert abs(l1.item() - g["loss1"]) < 2e-3 and abs(l2.item() - g["loss2"]) < 2e-3
+    loss.backward()
+    got = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+    assert set(got) == set(g["grads"]) and len(got) == g["n_grads"]
+    for k, ref in g["grads"].items():
+        assert abs(got[k].norm().item() - ref["norm"]) <= 1e-2 * ref["norm"] + 1e-7, k
+        torch.testing.assert_close(got[k].flatten()[:32].cpu(), ref["head"], rtol=1e-2, atol=1e-6 + 1e-3 * ref["norm"],
+                                   msg=lambda s, k=k: f"{k}: {s}")
+
+
+def test_pretrain_step_matches_reference(shadow, gold_dir):
+    """BASELINE config 5's step as tools/train_net.py:146-162 runs it: model([frames, meta]) -> (pred, teacher, mse) ->
+    KL(top-k) + MSE -> backward, against the unmodified reference (its random draws replayed)."""
+    g = torch.load(os.path.join(gold_dir, "mvit_pretrain_d4_t4_c64.pt"))
+    m, x, meta = pretrain_model(gold_dir, g, "bf16x3")
+    check_pretrain_step(m, x, meta, g)
+
+
 def test_throughput_mode_and_droppath(shadow, gold_dir):
     """bf16 activations / operands: logits stay within the bf16 budget of the reference's, DropPath rows scale whole clips."""
     g = torch.load(os.path.join(gold_dir, "mvit_d4_t4_c64.pt"))

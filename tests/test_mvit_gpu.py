@@ -13,7 +13,7 @@ import mvit_oracle as MO
 import shadow_ops as S
 from procedurevrl_b200 import mvit_functional as MF
 from procedurevrl_b200 import ops
-from test_mvit_cpu import build, mvit_cfg
+from test_mvit_cpu import build, check_pretrain_step, mvit_cfg, pretrain_model
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -239,6 +239,15 @@ def test_model_matches_reference_goldens(gold_dir, case):
     finally:
         del os.environ["PVRL_PRECISION"]
     assert (lb.detach().cpu() - g["logits"]).abs().max().item() < 1.0
+
+
+def test_pretrain_step_matches_reference(gold_dir):
+    """Config 5's pre-training step (encoder, head, order transformer on the pvrl_ot_* kernels, teacher, fused KL top-k loss,
+    backward) on the GPU against the golden of the unmodified reference."""
+    need_gpu()
+    g = torch.load(os.path.join(gold_dir, "mvit_pretrain_d4_t4_c64.pt"))
+    m, x, meta = pretrain_model(gold_dir, g, "bf16x3")
+    check_pretrain_step(m.to(DEV), x, meta, g, dev=DEV)
 
 
 def test_full_size_training_step(gold_dir):
