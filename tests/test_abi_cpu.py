@@ -53,6 +53,34 @@ def test_bad_arguments_return_errors_not_crashes(lib):
     assert lib.pvrl_kl_topk_loss(16, 16, None, None, None, 2, 100, 9, 1.0, None) == -1  # topk > 8
 
 
+def test_mvit_entry_points_validate_arguments(lib):
+    """The MViTv2 entry points (include/pvrl.h, csrc/mvit.cu) reject inconsistent geometry with a message, before any launch."""
+    import ctypes as C
+    from procedurevrl_b200 import ops
+    assert lib.pvrl_ln_any_fwd(16, 1, 16, 16, 16, 1, 16, 8, 2048, 1e-6, None) == -1            # width > 1024
+    assert b"1 .. 1024" in lib.pvrl_last_error()
+    d = ops._pool_desc(2, 2, 96, (4, 8, 8), (3, 3, 3), (1, 2, 2), (1, 1, 1), 576)
+    assert list(d.out) == [4, 4, 4]
+    d.out[1] = 5                                                                               # wrong output grid
+    assert lib.pvrl_pool3d_fwd(16, 16, 16, 1, C.byref(d), None) == -1
+    assert b"output grid" in lib.pvrl_last_error()
+    d = ops._pool_desc(2, 2, 256, (4, 8, 8), (3, 3, 3), (1, 2, 2), (1, 1, 1), 3 * 2 * 256)       # more than 128 channels per head
+    assert lib.pvrl_pool3d_fwd(16, 16, 16, 1, C.byref(d), None) == -1
+    d = ops._pool_desc(2, 2, 96, (4, 8, 8), (3, 3, 3), (1, 2, 2), (1, 1, 1), 576)
+    assert lib.pvrl_pool3d_fwd(16, None, 16, 1, C.byref(d), None) == -1                        # no weights but a pooled grid
+    assert b"re-layout only" in lib.pvrl_last_error()
+    d = ops._pool_desc(1, 2, 96, (2, 8, 8), (1, 3, 3), (1, 2, 2), (0, 1, 1), 96)
+    assert lib.pvrl_maxpool3d_fwd(16, 16, 16, 1, C.byref(d), None) == -1                       # heads must be 1
+    a = ops.PooledAttnDesc(1, 2, 129, 33, 64, 2, 4, 4, 0.125, 1)
+    assert lib.pvrl_pooled_attn_fwd(16, 16, 16, 16, 16, 16, 1, C.byref(a), None) == -1         # head width 64
+    assert b"96-wide heads" in lib.pvrl_last_error()
+    a = ops.PooledAttnDesc(1, 2, 129, 34, 96, 2, 4, 4, 0.1, 1)
+    assert lib.pvrl_pooled_attn_bwd(16, 16, 16, 16, 16, 16, 16, 16, 16, 16, 16, 1, C.byref(a), None) == -1   # key grid != Nk - 1
+    assert b"key grid" in lib.pvrl_last_error()
+    d = ops._pool_desc(1, 1, 3, (4, 32, 32), (3, 7, 7), (2, 4, 4), (1, 3, 3), 0)
+    assert lib.pvrl_im2col3d(16, 16, 0, 3, 440, C.byref(d), None) == -1                        # Kpad shorter than a window (441)
+
+
 def test_no_cpu_fallback(monkeypatch):
     from procedurevrl_b200 import build, ops
     x = torch.zeros(4, 8)
