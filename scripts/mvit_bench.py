@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--clips", type=int, default=9)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
+    ap.add_argument("--optimizer", action="store_true", help="include the flat AdamW step (construct_optimizer) in the timed step")
     a = ap.parse_args()
     with open(os.path.join(ROOT, "tests", "golden", "mvit_full_geometry.json")) as f:
         fg = json.load(f)
@@ -47,11 +48,22 @@ def main():
     x = ((u8.float() / 255.0 - 0.45) / 0.225).cuda()
     labels = torch.arange(a.clips, device="cuda") % 778
 
+    opt = None
+    if a.optimizer:
+        from procedurevrl_b200.lib.models import optimizer as optim
+        c.merge_from_list(["SOLVER.OPTIMIZING_METHOD", "adamw", "SOLVER.BASE_LR", 5e-5, "SOLVER.WEIGHT_DECAY", 0.05])
+        opt = optim.construct_optimizer(m, c)
+
     def step():
-        for p in m.parameters():
-            p.grad = None
+        if opt is None:
+            for p in m.parameters():
+                p.grad = None
+        else:
+            opt.zero_grad()
         loss = torch.nn.functional.cross_entropy(m(x), labels)
         loss.backward()
+        if opt is not None:
+            opt.step()
         return loss
 
     for _ in range(a.warmup):
@@ -72,7 +84,7 @@ def main():
     except OSError:
         pass
     cps = a.clips / ms * 1e3
-    print(json.dumps({"metric": "clips/sec MViTv2-S 16x224 forward+backward (no optimizer step), 1 GPU", "value": round(cps, 2),
+    print(json.dumps({"metric": "clips/sec MViTv2-S 16x224 forward+backward" + (" + flat AdamW step" if opt is not None else " (no optimizer step)") + ", 1 GPU", "value": round(cps, 2),
                       "unit": "clips/s", "ms_per_step": round(ms, 2), "steps": a.steps, "warmup": a.warmup, "n_gpus": 1,
                       "dtype": a.precision, "data": "synthetic", "loss": round(loss.item(), 4),
                       "gpu_launches_per_step": (ops.launch_count() - n0) // a.steps,

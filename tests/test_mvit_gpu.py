@@ -250,6 +250,44 @@ def test_pretrain_step_matches_reference(gold_dir):
     check_pretrain_step(m.to(DEV), x, meta, g, dev=DEV)
 
 
+def test_reference_style_loop_with_construct_optimizer(gold_dir):
+    """The driver loop of tools/train_net.py:146-192 on the MViT drop-in pieces: model([frames, meta]), PF.pretrain_loss,
+    construct_optimizer (flat AdamW: the parameters become views of its buffer and are updated through raw pointers -- the
+    operand caches of tc_linear must notice every step), zero_grad / backward / step, against the same loop with
+    torch.optim.AdamW on a second copy: same losses over 3 iterations (parity mode, as the TimeSformer loop test)."""
+    need_gpu()
+    from procedurevrl_b200 import functional as PF
+    from procedurevrl_b200.lib.models import optimizer as optim
+    g = torch.load(os.path.join(gold_dir, "mvit_pretrain_d4_t4_c64.pt"))
+    losses = {}
+    for kind in ("torch", "flat"):
+        m, x, meta = pretrain_model(gold_dir, g, "bf16x3")
+        m = m.to(DEV)
+        cfg = m.model.cfg
+        cfg.merge_from_list(["SOLVER.OPTIMIZING_METHOD", "adamw", "SOLVER.BASE_LR", 2e-5, "SOLVER.WEIGHT_DECAY", 1e-2,
+                             "SOLVER.MAX_EPOCH", 4, "SOLVER.LR_POLICY", "cosine"])
+        x, meta = x.to(DEV), {k: v.to(DEV) for k, v in meta.items()}
+        if kind == "flat":
+            opt_ = optim.construct_optimizer(m, cfg)
+        else:
+            opt_ = torch.optim.AdamW([{"params": [p for p in m.parameters() if p.requires_grad], "lr_mult": 1.0}], lr=2e-5,
+                                     weight_decay=1e-2)
+        out = []
+        for it in range(3):
+            optim.set_lr(opt_, optim.get_epoch_lr(it * 0.5, cfg))
+            pred, teacher, mse = m([x, meta])
+            loss, _, _ = PF.pretrain_loss(pred, teacher, mse, topk=g["cfg"]["topk"])
+            opt_.zero_grad()
+            loss.backward()
+            opt_.step()
+            out.append(loss.item())
+        losses[kind] = out
+    print("[MViT reference-style loop]", losses)
+    assert losses["torch"][0] != losses["torch"][2]
+    for a, b in zip(losses["flat"], losses["torch"]):
+        assert abs(a - b) <= 2e-3 * abs(b) + 1e-5
+
+
 def test_full_size_training_step(gold_dir):
     """MViTv2-S 16 x 224 as shipped (25 089 -> 393 tokens, 393 / 1 569 pooled keys): one clip forward + backward in the
     throughput mode: finite, deterministic forward, every encoder parameter receives a gradient."""
