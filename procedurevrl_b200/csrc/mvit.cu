@@ -390,6 +390,9 @@ constexpr int AT_V = AT_C / 32;
 constexpr int AT_QPW = 4;     // queries (dQ) / keys (dKV) per warp
 constexpr int AT_WARPS = 4;
 constexpr int AT_KBMAX = 64;
+#ifndef PVRL_MVIT_ATTN_MMA_DEFAULT
+#define PVRL_MVIT_ATTN_MMA_DEFAULT 0   // the mma.sync forward is opt-in until it has a measured GPU run behind it
+#endif
 
 __device__ __forceinline__ float attn_bias(const float* __restrict__ bqrow, int j, const AttnGeom& g) {
   const int jj = j - 1;
@@ -794,8 +797,22 @@ PoolGeom to_geom(const pvrl_pool3d_t* p) {
 }  // namespace
 }  // namespace pvrl
 
+namespace pvrl {
+// mvit_attn_mma.cu: the forward on mma.sync (bf16 only)
+int pooled_attn_fwd_mma_launch(const void* q, const void* k, const void* v, const float* bq, void* out, float* lse, int B,
+                               int heads, int Nq, int Nk, int Kt, int Kh, int Kw, float scale, int resid,
+                               cudaStream_t stream);
+}  // namespace pvrl
+
 using namespace pvrl;
 #define STREAM static_cast<cudaStream_t>(stream)
+
+// PVRL_MVIT_ATTN_MMA = 1 / 0 selects the mma.sync forward (mvit_attn_mma.cu) or the CUDA-core forward for bf16 problems;
+// read on every call so that tests can compare the two in one process.
+static bool mvit_attn_mma_enabled() {
+  const char* e = getenv("PVRL_MVIT_ATTN_MMA");
+  return e != nullptr ? atoi(e) != 0 : PVRL_MVIT_ATTN_MMA_DEFAULT != 0;
+}
 
 extern "C" int pvrl_ln_any_fwd(const void* x, int32_t x_dtype, const float* w, const float* b, void* y, int32_t y_dtype,
                                float* stats, int32_t M, int32_t D, float eps, void* stream) {
@@ -956,6 +973,9 @@ extern "C" int pvrl_pooled_attn_fwd(const void* q, const void* k, const void* v,
   int rc = check_attn(a, "pvrl_pooled_attn_fwd");
   if (rc) return rc;
   PVRL_CHECK_ARG(q && k && v && bq && out && lse, "pvrl_pooled_attn_fwd: null buffer");
+  if (dtype == PVRL_BF16 && mvit_attn_mma_enabled())
+    return pooled_attn_fwd_mma_launch(q, k, v, bq, out, lse, a->B, a->heads, a->Nq, a->Nk, a->Kt, a->Kh, a->Kw, a->scale,
+                                      a->residual_pooling, STREAM);
   const AttnGeom g = to_attn(a);
   const dim3 grid((g.Nq + AT_WARPS * AT_QPW - 1) / (AT_WARPS * AT_QPW), g.BH);
   if (dtype == PVRL_F32)

@@ -170,6 +170,44 @@ def test_pooled_attention(B, heads, qg, kg, dt, resid):
         assert rel(a, r) < tol, (name, rel(a, r))
 
 
+@pytest.mark.parametrize("B,heads,qg,kg", ATTN + [(1, 2, (1, 5, 5), (1, 3, 3)), (1, 1, (2, 6, 6), (2, 7, 7)), (1, 1, (8, 56, 56), (8, 7, 7)),
+                                                 (9, 4, (8, 14, 14), (8, 7, 7))])
+def test_pooled_attention_mma_forward(B, heads, qg, kg):
+    """The mma.sync forward (csrc/mvit_attn_mma.cu, opt-in: PVRL_MVIT_ATTN_MMA=1) against the restatement and against the
+    CUDA-core forward it will replace: same outputs within bf16 rounding of P, same lse."""
+    need_gpu()
+    C = 96
+    Nq, Nk = 1 + qg[0] * qg[1] * qg[2], 1 + kg[0] * kg[1] * kg[2]
+    q, k, v = (rnd(B, heads, n, C, seed=40 + i, dtype=torch.bfloat16) for i, n in enumerate((Nq, Nk, Nk)))
+    bq = rnd(B, heads, Nq - 1, sum(kg), seed=44, scale=0.5)
+    scale = C ** -0.5
+    res = {}
+    for name, o, env in (("mma", ops, "1"), ("simt", ops, "0"), ("ref", S, "0")):
+        out, lse = torch.full((B, Nq, heads * C), float("nan"), device=DEV, dtype=torch.bfloat16), torch.empty(B, heads, Nq, device=DEV)
+        os.environ["PVRL_MVIT_ATTN_MMA"] = env
+        try:
+            o.pooled_attn_fwd(q, k, v, bq, out, lse, kg, scale, True)
+        finally:
+            del os.environ["PVRL_MVIT_ATTN_MMA"]
+        res[name] = (out.float(), lse)
+    torch.cuda.synchronize()
+    if B == 9:                     # the shape of blocks 4 .. 13 of MViTv2-S at 9 clips: per-launch times of the two forwards
+        for env in ("1", "0"):
+            os.environ["PVRL_MVIT_ATTN_MMA"] = env
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ev[0].record()
+            for _ in range(5):
+                ops.pooled_attn_fwd(q, k, v, bq, out, lse, kg, scale, True)
+            ev[1].record()
+            torch.cuda.synchronize()
+            del os.environ["PVRL_MVIT_ATTN_MMA"]
+            print(f"[mma fwd] 9 clips x 4 heads, 1569 x 393: PVRL_MVIT_ATTN_MMA={env}: {ev[0].elapsed_time(ev[1]) / 5 * 1e3:.0f} us per launch")
+    e_out, e_lse = rel(res["mma"][0], res["ref"][0]), (res["mma"][1] - res["ref"][1]).abs().max().item()
+    print(f"[mma fwd] Nq={Nq} Nk={Nk} heads={heads}: out vs ref {e_out:.2e}, vs simt {rel(res['mma'][0], res['simt'][0]):.2e}, lse {e_lse:.2e}")
+    assert torch.isfinite(res["mma"][0]).all()
+    assert e_out < 2e-2 and e_lse < 2e-3
+
+
 def test_autograd_functions_match_torch():
     """The Functions of mvit_functional end to end (save-for-backward, dtype routing) against autograd of the restatement."""
     need_gpu()
