@@ -173,8 +173,8 @@ def test_pooled_attention(B, heads, qg, kg, dt, resid):
 @pytest.mark.parametrize("B,heads,qg,kg", ATTN + [(1, 2, (1, 5, 5), (1, 3, 3)), (1, 1, (2, 6, 6), (2, 7, 7)), (1, 1, (8, 56, 56), (8, 7, 7)),
                                                  (9, 4, (8, 14, 14), (8, 7, 7))])
 def test_pooled_attention_mma_forward(B, heads, qg, kg):
-    """The mma.sync forward (csrc/mvit_attn_mma.cu, opt-in: PVRL_MVIT_ATTN_MMA=1) against the restatement and against the
-    CUDA-core forward it will replace: same outputs within bf16 rounding of P, same lse."""
+    """The mma.sync forward (csrc/mvit_attn_mma.cu, the default for bf16; PVRL_MVIT_ATTN_MMA=0 selects the CUDA-core one)
+    against the restatement and against the CUDA-core forward: same outputs within bf16 rounding of P, same lse."""
     need_gpu()
     C = 96
     Nq, Nk = 1 + qg[0] * qg[1] * qg[2], 1 + kg[0] * kg[1] * kg[2]
