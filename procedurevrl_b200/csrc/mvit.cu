@@ -802,6 +802,9 @@ namespace pvrl {
 int pooled_attn_fwd_mma_launch(const void* q, const void* k, const void* v, const float* bq, void* out, float* lse, int B,
                                int heads, int Nq, int Nk, int Kt, int Kh, int Kw, float scale, int resid,
                                cudaStream_t stream);
+int pooled_attn_bwd_mma_launch(const void* q, const void* k, const void* v, const float* bq, const void* dout, const float* lse,
+                               void* dq, float* dk, float* dv, float* dbq, float* delta, int B, int heads, int Nq, int Nk,
+                               int Kt, int Kh, int Kw, float scale, int resid, cudaStream_t stream);
 }  // namespace pvrl
 
 using namespace pvrl;
@@ -994,6 +997,14 @@ extern "C" int pvrl_pooled_attn_bwd(const void* q, const void* k, const void* v,
   int rc = check_attn(a, "pvrl_pooled_attn_bwd");
   if (rc) return rc;
   PVRL_CHECK_ARG(q && k && v && bq && dout && lse && dq && dk && dv && dbq && delta, "pvrl_pooled_attn_bwd: null buffer");
+  // PVRL_MVIT_ATTN_MMA_BWD = 1: the mma.sync dQ and dK/dV passes (mvit_attn_mma.cu) for bf16 problems.  Opt-in: their
+  // fragment algebra is checked by the CPU emulation (tests/test_mvit_mma_emulation.py), they have not run on a GPU yet.
+  if (dtype == PVRL_BF16) {
+    const char* e = getenv("PVRL_MVIT_ATTN_MMA_BWD");
+    if (e != nullptr && atoi(e) != 0)
+      return pooled_attn_bwd_mma_launch(q, k, v, bq, dout, lse, dq, dk, dv, dbq, delta, a->B, a->heads, a->Nq, a->Nk, a->Kt,
+                                        a->Kh, a->Kw, a->scale, a->residual_pooling, STREAM);
+  }
   AttnGeom g = to_attn(a);
   const dim3 gq((g.Nq + AT_WARPS * AT_QPW - 1) / (AT_WARPS * AT_QPW), g.BH);
   if (dtype == PVRL_F32)

@@ -166,3 +166,244 @@ def test_mma_forward_index_algebra(B, heads, qg, kg, resid):
     err = np.abs(out - ref.numpy()).max() / np.abs(ref.numpy()).max()
     assert err < 1.5e-2, err                                   # P and the output are rounded to bf16
     assert np.abs(lse.reshape(B, heads, Nq) - ref_lse.numpy()).max() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ backward kernels
+BC = 32      # MB_C: keys (dQ pass) / queries (dK/dV pass) per chunk
+
+
+def afrag(rows0, rows1, t, valid0, valid1):
+    """load_afrag: [C // 16][32 lanes][4 regs][2] from the two rows each lane owns (zeros where the row does not exist)."""
+    a = np.zeros((C // 16, 32, 4, 2), np.float32)
+    for kk in range(C // 16):
+        for lane in range(32):
+            d = kk * 16 + 2 * t[lane]
+            if valid0[lane]:
+                a[kk, lane, 0], a[kk, lane, 2] = rows0[lane][d:d + 2], rows0[lane][d + 8:d + 10]
+            if valid1[lane]:
+                a[kk, lane, 1], a[kk, lane, 3] = rows1[lane][d:d + 2], rows1[lane][d + 8:d + 10]
+    return a
+
+
+def bfrag(smem, n, kk, gq, t):
+    b0 = np.stack([smem[n * 8 + gq[l], kk * 16 + 2 * t[l]:kk * 16 + 2 * t[l] + 2] for l in range(32)])
+    b1 = np.stack([smem[n * 8 + gq[l], kk * 16 + 8 + 2 * t[l]:kk * 16 + 10 + 2 * t[l]] for l in range(32)])
+    return b0, b1
+
+
+def pack_a(x, kk):
+    pa = np.zeros((32, 4, 2), np.float32)
+    pa[:, 0], pa[:, 1] = bf16(x[2 * kk][:, 0:2]), bf16(x[2 * kk][:, 2:4])
+    pa[:, 2], pa[:, 3] = bf16(x[2 * kk + 1][:, 0:2]), bf16(x[2 * kk + 1][:, 2:4])
+    return pa
+
+
+def ldsm_addr(kk, npair):
+    return lambda l: (kk * 16 + ((l >> 3) & 1) * 8 + (l & 7), npair * 16 + ((l >> 3) >> 1) * 8)
+
+
+def emulate_bwd_q_warp(q, k, v, bq, do, lse, bh, block_x, wid, kg, scale, resid, dq, dbq, delta):
+    """One warp of pooled_attn_bwd_q_mma_kernel.  do [BH, Nq, C] is the (clip, head) slice of dout."""
+    Nq, Nk = q.shape[1], k.shape[1]
+    Kt, Kh, Kw = kg
+    KB = Kt + Kh + Kw
+    lanes = np.arange(32)
+    gq, t = lanes >> 2, lanes & 3
+    r0 = block_x * 64 + wid * 16 + gq
+    r1 = r0 + 8
+    rows = lambda x, r: [x[bh, min(ri, Nq - 1)] for ri in r]
+    qa = afrag(rows(q, r0), rows(q, r1), t, r0 < Nq, r1 < Nq)
+    da = afrag(rows(do, r0), rows(do, r1), t, r0 < Nq, r1 < Nq)
+    ls0 = np.array([lse[bh, r] if r < Nq else 0.0 for r in r0], np.float32)
+    ls1 = np.array([lse[bh, r] if r < Nq else 0.0 for r in r1], np.float32)
+    nbt = (KB + 7) // 8
+    dl0, dl1 = np.zeros(32, np.float32), np.zeros(32, np.float32)
+    dqa, dba = np.zeros((C // 8, 32, 4), np.float32), np.zeros((8, 32, 4), np.float32)
+    for pas in range(2):
+        for j0 in range(0, Nk, BC):
+            ks, vs, sel = np.zeros((BC, 104), np.float32), np.zeros((BC, 104), np.float32), np.zeros((BC, 72), np.float32)
+            kcomp = np.full(BC, -1, np.int64)
+            for row in range(BC):
+                j = j0 + row
+                if j < Nk:
+                    ks[row, :C], vs[row, :C] = k[bh, j], v[bh, j]
+                if 0 < j < Nk:
+                    jj = j - 1
+                    cols = (jj // (Kw * Kh), Kt + (jj // Kw) % Kh, Kt + Kh + jj % Kw)
+                    kcomp[row] = cols[0] | (cols[1] << 8) | (cols[2] << 16)
+                    if pas == 1:
+                        sel[row, list(cols)] = 1.0
+            s, dp = np.zeros((BC // 8, 32, 4), np.float32), np.zeros((BC // 8, 32, 4), np.float32)
+            for n in range(BC // 8):
+                for kk in range(C // 16):
+                    mma16816(s[n], qa[kk], *bfrag(ks, n, kk, gq, t))
+                    mma16816(dp[n], da[kk], *bfrag(vs, n, kk, gq, t))
+            for n in range(BC // 8):
+                for e in range(2):
+                    for lane in range(32):
+                        jl = n * 8 + 2 * t[lane] + e
+                        cc = kcomp[jl]
+                        a0, a1 = s[n, lane, e] * scale, s[n, lane, 2 + e] * scale
+                        if cc >= 0:
+                            cols = [cc & 0xff, (cc >> 8) & 0xff, (cc >> 16) & 0xff]
+                            if 0 < r0[lane] < Nq:
+                                a0 += bq[bh, r0[lane] - 1, cols].sum()
+                            if 0 < r1[lane] < Nq:
+                                a1 += bq[bh, r1[lane] - 1, cols].sum()
+                        live = j0 + jl < Nk
+                        p0 = np.exp(a0 - ls0[lane]) if live and r0[lane] < Nq else 0.0
+                        p1 = np.exp(a1 - ls1[lane]) if live and r1[lane] < Nq else 0.0
+                        if pas == 0:
+                            dl0[lane] += p0 * dp[n, lane, e]
+                            dl1[lane] += p1 * dp[n, lane, 2 + e]
+                        else:
+                            s[n, lane, e] = p0 * (dp[n, lane, e] - dl0[lane])
+                            s[n, lane, 2 + e] = p1 * (dp[n, lane, 2 + e] - dl1[lane])
+            if pas == 1:
+                for kk in range(BC // 16):
+                    pa = pack_a(s, kk)
+                    for npair in range(C // 16):
+                        regs = ldsm_x4_trans(ks, ldsm_addr(kk, npair))
+                        mma16816(dqa[2 * npair], pa, regs[0], regs[1])
+                        mma16816(dqa[2 * npair + 1], pa, regs[2], regs[3])
+                    for nb in range(4):
+                        if 2 * nb < nbt:
+                            regs = ldsm_x4_trans(sel, ldsm_addr(kk, nb))
+                            mma16816(dba[2 * nb], pa, regs[0], regs[1])
+                            mma16816(dba[2 * nb + 1], pa, regs[2], regs[3])
+        if pas == 0:
+            dl0, dl1 = quad(dl0, np.add), quad(dl1, np.add)
+            for lane in range(0, 32, 4):
+                if r0[lane] < Nq:
+                    delta[bh, r0[lane]] = dl0[lane]
+                if r1[lane] < Nq:
+                    delta[bh, r1[lane]] = dl1[lane]
+    for n in range(C // 8):
+        for lane in range(32):
+            d = n * 8 + 2 * t[lane]
+            for r, lo in ((r0[lane], 0), (r1[lane], 2)):
+                if r < Nq:
+                    val = dqa[n, lane, lo:lo + 2] * scale
+                    if resid and r > 0:
+                        val = val + do[bh, r, d:d + 2]
+                    dq[bh, r, d:d + 2] = bf16(val)
+    for n in range(8):
+        for e in range(2):
+            for lane in range(32):
+                col = n * 8 + 2 * t[lane] + e
+                if col < KB:
+                    if 0 < r0[lane] < Nq:
+                        dbq[bh, r0[lane] - 1, col] = dba[n, lane, e]
+                    if 0 < r1[lane] < Nq:
+                        dbq[bh, r1[lane] - 1, col] = dba[n, lane, 2 + e]
+
+
+def emulate_bwd_kv_warp(q, k, v, bq, do, lse, delta, bh, block_x, wid, zslice, qsplit, kg, scale, dk, dv):
+    """One warp of pooled_attn_bwd_kv_mma_kernel for query slice `zslice` of `qsplit`; dk / dv accumulate (the atomics)."""
+    Nq, Nk = q.shape[1], k.shape[1]
+    Kt, Kh, Kw = kg
+    lanes = np.arange(32)
+    gq, t = lanes >> 2, lanes & 3
+    j_0 = block_x * 64 + wid * 16 + gq
+    j_1 = j_0 + 8
+    rows = lambda x, r: [x[bh, min(ri, Nk - 1)] for ri in r]
+    ka = afrag(rows(k, j_0), rows(k, j_1), t, j_0 < Nk, j_1 < Nk)
+    va = afrag(rows(v, j_0), rows(v, j_1), t, j_0 < Nk, j_1 < Nk)
+
+    def comps(j):
+        if not 0 < j < Nk:
+            return None
+        jj = j - 1
+        return [jj // (Kw * Kh), Kt + (jj // Kw) % Kh, Kt + Kh + jj % Kw]
+    c0, c1 = [comps(j) for j in j_0], [comps(j) for j in j_1]
+    dka, dva = np.zeros((C // 8, 32, 4), np.float32), np.zeros((C // 8, 32, 4), np.float32)
+    per = (((Nq + qsplit - 1) // qsplit) + BC - 1) // BC * BC
+    ibeg, iend = zslice * per, min(Nq, zslice * per + per)
+    for i0 in range(ibeg, iend, BC):
+        qs, dos = np.zeros((BC, 104), np.float32), np.zeros((BC, 104), np.float32)
+        lss, dls = np.zeros(BC, np.float32), np.zeros(BC, np.float32)
+        for row in range(BC):
+            if i0 + row < iend:
+                qs[row, :C], dos[row, :C] = q[bh, i0 + row], do[bh, i0 + row]
+                lss[row], dls[row] = lse[bh, i0 + row], delta[bh, i0 + row]
+        st, dpt = np.zeros((BC // 8, 32, 4), np.float32), np.zeros((BC // 8, 32, 4), np.float32)
+        for n in range(BC // 8):
+            for kk in range(C // 16):
+                mma16816(st[n], ka[kk], *bfrag(qs, n, kk, gq, t))
+                mma16816(dpt[n], va[kk], *bfrag(dos, n, kk, gq, t))
+        for n in range(BC // 8):
+            for e in range(2):
+                for lane in range(32):
+                    il = n * 8 + 2 * t[lane] + e
+                    i = i0 + il
+                    a0, a1 = st[n, lane, e] * scale, st[n, lane, 2 + e] * scale
+                    if 0 < i < iend:
+                        if c0[lane] is not None:
+                            a0 += bq[bh, i - 1, c0[lane]].sum()
+                        if c1[lane] is not None:
+                            a1 += bq[bh, i - 1, c1[lane]].sum()
+                    p0 = np.exp(a0 - lss[il]) if i < iend and j_0[lane] < Nk else 0.0
+                    p1 = np.exp(a1 - lss[il]) if i < iend and j_1[lane] < Nk else 0.0
+                    d0, d1 = p0 * (dpt[n, lane, e] - dls[il]), p1 * (dpt[n, lane, 2 + e] - dls[il])
+                    st[n, lane, e], st[n, lane, 2 + e] = p0, p1
+                    dpt[n, lane, e], dpt[n, lane, 2 + e] = d0, d1
+        for kk in range(BC // 16):
+            pa, sa = pack_a(st, kk), pack_a(dpt, kk)
+            for npair in range(C // 16):
+                regs = ldsm_x4_trans(dos, ldsm_addr(kk, npair))
+                mma16816(dva[2 * npair], pa, regs[0], regs[1])
+                mma16816(dva[2 * npair + 1], pa, regs[2], regs[3])
+                regs = ldsm_x4_trans(qs, ldsm_addr(kk, npair))
+                mma16816(dka[2 * npair], sa, regs[0], regs[1])
+                mma16816(dka[2 * npair + 1], sa, regs[2], regs[3])
+    for n in range(C // 8):
+        for lane in range(32):
+            d = n * 8 + 2 * t[lane]
+            for j, lo in ((j_0[lane], 0), (j_1[lane], 2)):
+                if j < Nk:
+                    dk[bh, j, d:d + 2] += dka[n, lane, lo:lo + 2] * scale
+                    dv[bh, j, d:d + 2] += dva[n, lane, lo:lo + 2]
+
+
+@pytest.mark.parametrize("B,heads,qg,kg,resid", CASES)
+def test_mma_backward_index_algebra(B, heads, qg, kg, resid):
+    gen = torch.Generator().manual_seed(sum(qg) * 11 + sum(kg))
+    Nq, Nk, KB = 1 + qg[0] * qg[1] * qg[2], 1 + kg[0] * kg[1] * kg[2], sum(kg)
+    BH = B * heads
+    q, k, v = (torch.randn(B, heads, n, C, generator=gen).to(torch.bfloat16) for n in (Nq, Nk, Nk))
+    bq = 0.5 * torch.randn(B, heads, Nq - 1, KB, generator=gen)
+    dout = torch.randn(B, Nq, heads * C, generator=gen).to(torch.bfloat16)
+    scale = C ** -0.5
+    # reference: autograd of the plain attention (tests/shadow_ops.py)
+    lse_t = torch.empty(B, heads, Nq)
+    S.pooled_attn_fwd(q, k, v, bq, torch.empty(B, Nq, heads * C), lse_t, kg, scale, resid)
+    rdq = torch.empty(B, heads, Nq, C)
+    rdk, rdv = torch.zeros(B, heads, Nk, C), torch.zeros(B, heads, Nk, C)
+    rdbq, rdelta = torch.empty_like(bq), torch.empty(B, heads, Nq)
+    S.pooled_attn_bwd(q, k, v, bq, dout, lse_t, rdq, rdk, rdv, rdbq, rdelta, kg, scale, resid)
+
+    qn, kn, vn = (x.float().reshape(BH, -1, C).numpy() for x in (q, k, v))
+    bqn, lsn = bq.reshape(BH, Nq - 1, KB).numpy(), lse_t.reshape(BH, Nq).numpy()
+    don = dout.float().reshape(B, Nq, heads, C).permute(0, 2, 1, 3).reshape(BH, Nq, C).numpy()
+    dq = np.full((BH, Nq, C), np.nan, np.float32)
+    dbq = np.full((BH, Nq - 1, KB), np.nan, np.float32)
+    delta = np.full((BH, Nq), np.nan, np.float32)
+    dk, dv = np.zeros((BH, Nk, C), np.float32), np.zeros((BH, Nk, C), np.float32)
+    for bh in range(BH):
+        for bx in range((Nq + 63) // 64):
+            for wid in range(4):
+                emulate_bwd_q_warp(qn, kn, vn, bqn, don, lsn, bh, bx, wid, kg, scale, resid, dq, dbq, delta)
+    assert not (np.isnan(dq).any() or np.isnan(dbq).any() or np.isnan(delta).any()), "an output element was never written"
+    qsplit = 2                      # two query slices: their partial sums meet in dk / dv
+    for bh in range(BH):
+        for bx in range((Nk + 63) // 64):
+            for wid in range(4):
+                for z in range(qsplit):
+                    emulate_bwd_kv_warp(qn, kn, vn, bqn, don, lsn, delta, bh, bx, wid, z, qsplit, kg, scale, dk, dv)
+
+    def relerr(a, r):
+        r = r.reshape(a.shape).numpy()
+        return np.abs(a - r).max() / (np.abs(r).max() + 1e-12)
+    assert relerr(delta, rdelta) < 1e-4, relerr(delta, rdelta)           # fp32 end to end
+    for name, a, r in (("dq", dq, rdq), ("dbq", dbq, rdbq), ("dk", dk, rdk), ("dv", dv, rdv)):
+        assert relerr(a, r) < 2e-2, (name, relerr(a, r))                 # dS / P rounded to bf16 before their MMAs
