@@ -13,8 +13,8 @@ torch, what the reference's `MViT_encoder` computes (paths relative to the refer
 
 It is pinned by `oracle/make_golden_mvit.py`, which runs the UNMODIFIED reference (through `oracle/ref_shims.py`) on the
 same seeded parameters / clips and stores its outputs under tests/golden/mvit_*.pt; `tests/test_mvit_oracle_golden.py`
-checks this file against them.  The product (sm_100a) path for MViT is not built yet; this oracle
-and its goldens are what that build will be tested against.
+checks this file against them.  The product path (procedurevrl_b200/lib/models/mvit.py on csrc/mvit.cu)
+is tested against the same goldens (tests/test_mvit_cpu.py, tests/test_mvit_gpu.py); it never imports this file.
 
 Only what the shipped MViT YAMLs use is restated: MODE conv, POOL_FIRST False, SEPARATE_QKV False, CLS_EMBED_ON True,
 USE_ABS_POS False, REL_POS_SPATIAL / REL_POS_TEMPORAL True, RESIDUAL_POOLING True, DIM_MUL_IN_ATT True, NORM layernorm,

@@ -1,7 +1,7 @@
 """The MViTv2 oracle (oracle/mvit_oracle.py, BASELINE config 5) against golden vectors of the unmodified reference
 (tests/golden/mvit_*.pt, written by oracle/make_golden_mvit.py): geometry and parameter schema incl. the shipped
 16 x 224 model, logits / encoder feature / per-block cls rows, loss and every parameter gradient.  CPU only; this pins the
-oracle the sm_100a MViT path will be tested against (the product path for config 5 is not built yet -- DESIGN.md 8)."""
+oracle; the sm_100a MViT path itself is held to the same goldens in tests/test_mvit_cpu.py / tests/test_mvit_gpu.py."""
 import json
 import os
 
