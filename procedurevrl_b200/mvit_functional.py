@@ -105,15 +105,29 @@ def pool_qkv(qkv, wq, wk, wv, heads, C, grid, kernel, stride_q, stride_kv):
                           tuple(stride_kv or (1, 1, 1)))
 
 
+_REL_INDEX = {}     # (n_q, n_k, device) -> int64 [n_q, n_k] row indices into the relative-position table
+
+
+def _rel_index(n_q, n_k, device):
+    """table row of (query position i, key position j): i * rq - j * rk + (n_k - 1) * rk with rq = max(n_k / n_q, 1),
+    rk = max(n_q / n_k, 1) (attention.py:76-99,124-134).  Built once per geometry and device: no host-to-device copy (and no
+    host synchronisation) inside the step."""
+    key = (n_q, n_k, str(device))
+    idx = _REL_INDEX.get(key)
+    if idx is None:
+        rq, rk = max(n_k / n_q, 1.0), max(n_q / n_k, 1.0)
+        dist = torch.arange(n_q)[:, None] * rq - torch.arange(n_k)[None, :] * rk + (n_k - 1) * rk
+        idx = _REL_INDEX[key] = dist.long().to(device)
+    return idx
+
+
 def rel_table(table, n_q, n_k):
-    """R[i, j] = table[i * rq - j * rk + (n_k - 1) * rk], rq = max(n_k / n_q, 1), rk = max(n_q / n_k, 1); the table is
-    linearly resized first when its length is not 2 * max(n_q, n_k) - 1 (attention.py:51-64,76-99,124-134)."""
+    """R[i, j] = table[index(i, j)] (see _rel_index); the table is linearly resized first when its length is not
+    2 * max(n_q, n_k) - 1 (attention.py:51-64)."""
     d = 2 * max(n_q, n_k) - 1
     if table.shape[0] != d:
         table = torch.nn.functional.interpolate(table.t().unsqueeze(0), size=d, mode="linear").squeeze(0).t()
-    rq, rk = max(n_k / n_q, 1.0), max(n_q / n_k, 1.0)
-    dist = torch.arange(n_q)[:, None] * rq - torch.arange(n_k)[None, :] * rk + (n_k - 1) * rk
-    return table[dist.long().to(table.device)]
+    return table[_rel_index(n_q, n_k, table.device)]
 
 
 def rel_pos_projections(q, q_grid, k_grid, rel_h, rel_w, rel_t):

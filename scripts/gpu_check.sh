@@ -17,3 +17,11 @@ python scripts/summarize_launches.py gpurun_out/launches.csv | head -30
 python scripts/summarize_ncu_raw.py gpurun_out/prof_gemm_raw.csv | cut -c1-200
 python scripts/summarize_ncu_raw.py gpurun_out/prof_hbm_raw.csv | cut -c1-200
 python scripts/summarize_ncu_raw.py gpurun_out/prof_t32_raw.csv | cut -c1-200
+# MViTv2-S 16x224 (config 5): 9-clip forward + backward (+ flat AdamW), launch list of one step (give ncu ~3 min: ~1500 launches
+# per step incl. torch glue), and the mma.sync backward's first hardware run with its per-launch times
+timeout 120 python scripts/mvit_bench.py --steps 3 --warmup 2 > gpurun_out/mvit_bench.log 2>&1; tail -n 1 gpurun_out/mvit_bench.log
+timeout 120 python scripts/mvit_bench.py --steps 3 --warmup 2 --optimizer > gpurun_out/mvit_bench_opt.log 2>&1; tail -n 1 gpurun_out/mvit_bench_opt.log
+PVRL_MVIT_ATTN_MMA_BWD=1 timeout 120 python scripts/mvit_bench.py --steps 3 --warmup 2 > gpurun_out/mvit_bench_mma_bwd.log 2>&1; tail -n 1 gpurun_out/mvit_bench_mma_bwd.log
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_mvit.csv python scripts/mvit_bench.py --steps 1 --warmup 0 > gpurun_out/ncu_mvit.log 2>&1
+python scripts/summarize_launches.py gpurun_out/launches_mvit.csv | head -30
+timeout 300 python -m pytest tests/test_zz_mvit_mma_bwd_gpu.py -m gpu -q -s -rxX 2>&1 | grep "mma bwd\|passed\|failed\|xfail\|xpass"
