@@ -92,6 +92,9 @@ class _PoolQKV(torch.autograd.Function):
         dws = []
         for which, (dout, (w2, kern, st, pad)) in enumerate(zip((dq, dk, dv), ctx.args)):
             dw = None if w2 is None else torch.zeros_like(w2)
+            if dout is None:                        # an output nobody differentiated through: its slice of dqkv is zero
+                og = ops.pool_out_grid(ctx.grid, kern, st, pad)
+                dout = torch.zeros(qkv.shape[0], ctx.heads, 1 + og[0] * og[1] * og[2], ctx.C, device=qkv.device, dtype=qkv.dtype)
             ops.pool3d_bwd(_act(dout, qkv.dtype).contiguous(), qkv, which * ctx.heads * ctx.C, w2, dqkv, dw, ctx.heads, ctx.C,
                            ctx.grid, kern, st, pad)
             dws.append(None if dw is None else dw.reshape(ctx.wshapes[which]))
