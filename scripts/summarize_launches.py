@@ -7,7 +7,7 @@ import sys
 
 
 def kname(full):
-    s = re.sub(r"\(anonymous namespace\)::", "", full)
+    s = re.sub(r"(\(anonymous namespace\)|<unnamed>)::", "", full)
     m = re.search(r"([A-Za-z_][A-Za-z0-9_]*)\s*(<|\(|$)", s.replace("void ", "").split("::")[-1] if "<" not in s else
                   re.sub(r"<.*", "", s.replace("void ", "")).split("::")[-1] + "<")
     base = m.group(1) if m else s[:50]
