@@ -25,3 +25,4 @@ PVRL_MVIT_ATTN_MMA_BWD=1 timeout 120 python scripts/mvit_bench.py --steps 3 --wa
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_mvit.csv python scripts/mvit_bench.py --steps 1 --warmup 0 > gpurun_out/ncu_mvit.log 2>&1
 python scripts/summarize_launches.py gpurun_out/launches_mvit.csv | head -30
 timeout 300 python -m pytest tests/test_zz_mvit_mma_bwd_gpu.py -m gpu -q -s -rxX 2>&1 | grep "mma bwd\|passed\|failed\|xfail\|xpass"
+timeout 200 python scripts/mvit_attn_bench.py > gpurun_out/mvit_attn_bench.log 2>&1; cat gpurun_out/mvit_attn_bench.log
