@@ -51,7 +51,7 @@ def main():
         scale = C ** -0.5
         row = {"blocks": blocks, "heads": heads, "Nq": Nq, "Nk": Nk}
         flop = 4.0 * B * heads * Nq * Nk * C
-        for name, env in (("mma", "1"), ("simt", "0")):
+        for name, env in (("simt", "0"), ("mma", "1")):      # the proven variant first: a fault in an unproven one keeps its numbers
             os.environ["PVRL_MVIT_ATTN_MMA"] = env
             us = timed(lambda: ops.pooled_attn_fwd(q, k, v, bq, out, lse, kg, scale, True))
             row[f"fwd_{name}_us"], row[f"fwd_{name}_tflops"] = round(us, 1), round(flop / us / 1e6, 1)
