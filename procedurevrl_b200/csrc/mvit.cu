@@ -288,6 +288,58 @@ __global__ void __launch_bounds__(256) pool3d_bwd_w_kernel(const T* __restrict__
   for (int e = threadIdx.x; e < g.C * 27; e += blockDim.x) atomicAdd(dw + e, sacc[e]);
 }
 
+// Variant (opt-in, PVRL_POOL_DW = 2; not yet run on a GPU): the same sums with ONE channel per lane -- blockIdx.y picks the
+// 32-channel group -- so a lane carries 27 accumulators instead of 108 (254 registers, one block per SM, 310 us per launch
+// in the first launch list): ~5x the resident warps for the same loads.
+template <typename T>
+__global__ void __launch_bounds__(256) pool3d_bwd_w_cg_kernel(const T* __restrict__ dout, const T* __restrict__ in,
+                                                              float* __restrict__ dw, PoolGeom g) {
+  __shared__ float sacc[32 * 27];
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.y * 32 + lane;                      // this lane's channel
+  const bool live = c < g.C;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int L = g.T * g.H * g.W, Lo = g.OT * g.OH * g.OW;
+  for (int e = threadIdx.x; e < 32 * 27; e += blockDim.x) sacc[e] = 0.f;
+  __syncthreads();
+  float acc[27];
+#pragma unroll
+  for (int k = 0; k < 27; ++k) acc[k] = 0.f;
+  const long long total = (long long)g.B * g.heads * Lo;
+  for (long long idx = warp; idx < total; idx += nwarps) {
+    const int o = (int)(idx % Lo);
+    const int bh = (int)(idx / Lo), h = bh % g.heads, b = bh / g.heads;
+    const T* drow = dout + ((size_t)bh * (1 + Lo) + 1 + o) * g.C;
+    const T* src = in + (size_t)b * (1 + L) * g.ld + (size_t)h * g.C;
+    const int ow = o % g.OW, oh = (o / g.OW) % g.OH, ot = o / (g.OW * g.OH);
+    const float d = live ? ldf(drow + c) : 0.f;
+#pragma unroll
+    for (int dt = 0; dt < 3; ++dt) {
+      const int it = ot * g.ST - g.PT + dt;
+      if (it < 0 || it >= g.T) continue;
+#pragma unroll
+      for (int dh = 0; dh < 3; ++dh) {
+        const int ih = oh * g.SH - g.PH + dh;
+        if (ih < 0 || ih >= g.H) continue;
+#pragma unroll
+        for (int dw_ = 0; dw_ < 3; ++dw_) {
+          const int iw = ow * g.SW - g.PW + dw_;
+          if (iw < 0 || iw >= g.W) continue;
+          if (live) acc[(dt * 3 + dh) * 3 + dw_] += d * ldf(src + (size_t)(1 + (it * g.H + ih) * g.W + iw) * g.ld + c);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 27; ++k) atomicAdd(&sacc[lane * 27 + k], acc[k]);
+  __syncthreads();
+  for (int e = threadIdx.x; e < 32 * 27; e += blockDim.x) {
+    const int cc = blockIdx.y * 32 + e / 27;
+    if (cc < g.C) atomicAdd(dw + (size_t)cc * 27 + e % 27, sacc[e]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ MaxPool3d skip
 // x [B, 1 + L, D] -> y [B, 1 + Lo, D] (cls row copied), arg [B, Lo, D] = the input token (0 .. L-1) that won each window:
 // the first maximum in (t, h, w) scan order, as ATen's max_pool3d.
@@ -899,6 +951,15 @@ extern "C" int pvrl_pool3d_bwd(const void* dout, const void* in, const float* w,
   const long long orows = (long long)g.B * g.heads * g.OT * g.OH * g.OW;
   int gw = grid_for(orows, 8 * 16);
   if (gw > num_sms() * 2) gw = num_sms() * 2;
+  const char* variant = getenv("PVRL_POOL_DW");
+  if (variant != nullptr && atoi(variant) == 2) {
+    const dim3 grid2(grid_for(orows, 8 * 8), (g.C + 31) / 32);
+    if (dtype == PVRL_F32)
+      pool3d_bwd_w_cg_kernel<float><<<grid2, 256, 0, STREAM>>>((const float*)dout, (const float*)in, dw, g);
+    else
+      pool3d_bwd_w_cg_kernel<bf16><<<grid2, 256, 0, STREAM>>>((const bf16*)dout, (const bf16*)in, dw, g);
+    return launched("pool3d_bwd_w_cg_kernel");
+  }
   const size_t smem = (size_t)g.C * 27 * sizeof(float);
   if (dtype == PVRL_F32)
     pool3d_bwd_w_kernel<float><<<gw, 256, smem, STREAM>>>((const float*)dout, (const float*)in, dw, g);

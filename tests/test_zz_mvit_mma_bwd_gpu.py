@@ -1,5 +1,5 @@
 """First hardware run of the mma.sync dQ / dK/dV passes of the MViTv2 pooled attention (csrc/mvit_attn_mma.cu, opt-in:
-PVRL_MVIT_ATTN_MMA_BWD=1).  These two kernels were written after the round's GPU time was spent: their fragment algebra is
+PVRL_MVIT_ATTN_MMA_BWD=1) and of the one-channel-per-lane pooling weight-gradient kernel (csrc/mvit.cu, PVRL_POOL_DW=2).  These two kernels were written after the round's GPU time was spent: their fragment algebra is
 pinned by the lane-level CPU emulation (tests/test_mvit_mma_emulation.py, the procedure that the forward kernel passed
 before its first -- green -- GPU run), but they have not executed on a GPU.  So this file (a) sorts last, (b) runs the
 kernels in a CHILD process -- a fault in an unproven kernel must not poison the CUDA context of the rest of the suite --
@@ -23,7 +23,36 @@ import torch
 import shadow_ops as S
 from procedurevrl_b200 import ops
 torch.backends.cuda.matmul.allow_tf32 = False
-C, out = 96, []
+C = 96
+rel = lambda a, r: ((a - r).abs().max() / (r.abs().max() + 1e-12)).item()
+# the one-channel-per-lane weight-gradient kernel of the Q / K / V pooling (PVRL_POOL_DW=2, csrc/mvit.cu)
+pool = []
+for B, heads, grid, stride in [(2, 2, (4, 8, 8), (1, 2, 2)), (1, 4, (2, 7, 7), (1, 1, 1)), (9, 1, (8, 56, 56), (1, 1, 1))]:
+    L = grid[0] * grid[1] * grid[2]
+    g = torch.Generator().manual_seed(L)
+    src = torch.randn(B, 1 + L, 3 * heads * C, generator=g).cuda().bfloat16()
+    w = (0.3 * torch.randn(C, 27, generator=g)).cuda()
+    og = ops.pool_out_grid(grid, (3, 3, 3), stride, (1, 1, 1))
+    dout = torch.randn(B, heads, 1 + og[0] * og[1] * og[2], C, generator=g).cuda().bfloat16()
+    dws, times = {}, {}
+    for name, env in (("v1", "1"), ("cg", "2")):
+        os.environ["PVRL_POOL_DW"] = env
+        dw, din = torch.zeros(C, 27, device="cuda"), torch.empty_like(src)
+        ops.pool3d_bwd(dout, src, heads * C, w, din, dw, heads, C, grid, (3, 3, 3), stride, (1, 1, 1))
+        torch.cuda.synchronize()
+        dws[name] = dw
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            ops.pool3d_bwd(dout, src, heads * C, w, din, torch.zeros(C, 27, device="cuda"), heads, C, grid, (3, 3, 3), stride, (1, 1, 1))
+        e1.record()
+        torch.cuda.synchronize()
+        times[name] = e0.elapsed_time(e1) / 3 * 1e3
+    os.environ.pop("PVRL_POOL_DW")
+    pool.append({"shape": [B, heads, list(grid), list(stride)], "dw_cg_vs_v1": rel(dws["cg"], dws["v1"]),
+                 "us_both_kernels_v1": times["v1"], "us_both_kernels_cg": times["cg"]})
+print("RESULT_POOL " + json.dumps(pool), flush=True)
+out = []
 for B, heads, qg, kg in [(2, 2, (2, 8, 8), (2, 4, 4)), (1, 1, (1, 5, 5), (1, 3, 3)), (1, 3, (4, 14, 14), (4, 7, 7)),
                          (1, 1, (2, 6, 6), (2, 7, 7)), (9, 4, (8, 14, 14), (8, 7, 7))]:
     Nq, Nk = 1 + qg[0] * qg[1] * qg[2], 1 + kg[0] * kg[1] * kg[2]
@@ -43,7 +72,6 @@ for B, heads, qg, kg in [(2, 2, (2, 8, 8), (2, 4, 4)), (1, 1, (1, 5, 5), (1, 3, 
         o.pooled_attn_bwd(q, k, v, bq, dout, lse, dq, dk, dv, dbq, delta, kg, scale, True)
         torch.cuda.synchronize()
         res[name] = dict(dq=dq.float(), dk=dk, dv=dv, dbq=dbq, delta=delta)
-    rel = lambda a, r: ((a - r).abs().max() / (r.abs().max() + 1e-12)).item()
     row = {"shape": [B, heads, Nq, Nk]}
     for key in ("dq", "dk", "dv", "dbq", "delta"):
         row[key] = rel(res["mma"][key], res["ref"][key])
@@ -59,7 +87,7 @@ for B, heads, qg, kg in [(2, 2, (2, 8, 8), (2, 4, 4)), (1, 1, (1, 5, 5), (1, 3, 
             torch.cuda.synchronize()
             row["us_mma" if env == "1" else "us_simt"] = e0.elapsed_time(e1) / 3 * 1e3
     out.append(row)
-print("RESULT " + json.dumps(out))
+print("RESULT_ATTN " + json.dumps(out), flush=True)
 """
 
 
@@ -69,10 +97,14 @@ def test_mma_backward_first_hardware_run():
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
     r = subprocess.run([sys.executable, "-c", CHILD % {"root": ROOT, "here": HERE}], capture_output=True, text=True, timeout=300)
-    lines = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
+    got = {l.split(" ", 1)[0]: json.loads(l.split(" ", 1)[1]) for l in r.stdout.splitlines() if l.startswith("RESULT_")}
     print(r.stdout[-3000:], r.stderr[-2000:])
-    assert r.returncode == 0 and lines, "the child process failed"
-    for row in json.loads(lines[-1][7:]):
+    res = {"pool": got.get("RESULT_POOL", []), "attn": got.get("RESULT_ATTN", [])}
+    assert r.returncode == 0 and res["pool"] and res["attn"], "the child process failed (partial results are printed above)"
+    for row in res["pool"]:
+        print("[pool dw variant]", row)
+        assert row["dw_cg_vs_v1"] < 1e-3, row
+    for row in res["attn"]:
         print("[mma bwd]", row)
         for key in ("dq", "dk", "dv", "dbq"):
             assert row[key] < 3e-2, (row["shape"], key, row[key])
