@@ -432,8 +432,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   if (warp == 8) tmem_dealloc<512>(tmem);
 }
 
+}  // namespace
+
 // 3-D bf16 tensor map over a row-major [n_seq, seq, cols] view, box [1, box_rows, 64], 128B swizzle, zero OOB fill.
-int make_tmap_3d(CUtensorMap* out, const void* ptr, uint64_t cols, uint64_t seq, uint64_t n_seq, uint32_t box_rows) {
+int make_tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t cols, uint64_t seq, uint64_t n_seq, uint32_t box_rows) {
   EncodeTiledFn enc = get_encode_fn();
   if (enc == nullptr) return fail(-2, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || (cols * 2) % 16 != 0)
@@ -449,6 +451,21 @@ int make_tmap_3d(CUtensorMap* out, const void* ptr, uint64_t cols, uint64_t seq,
   return 0;
 }
 
+
+int attn_sp_fwd_launch(const void* qkv, void* out, float* lse, int n_seq, int seq, int H, float scale, cudaStream_t stream);
+
+namespace {
+inline int make_tmap_3d(CUtensorMap* out, const void* ptr, uint64_t cols, uint64_t seq, uint64_t n_seq, uint32_t box_rows) {
+  return make_tmap_3d_bf16(out, ptr, cols, seq, n_seq, box_rows);
+}
+// PVRL_ATTN_SP=0 selects the first-generation one-shot kernels (kept for A/B runs)
+inline bool use_sp() {
+  static const bool on = [] {
+    const char* e = getenv("PVRL_ATTN_SP");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  return on;
+}
 }  // namespace
 }  // namespace pvrl
 
@@ -458,6 +475,7 @@ extern "C" int pvrl_attn_tc_fwd(const void* qkv, void* out, float* lse, int32_t 
                                 float scale, void* stream) {
   PVRL_CHECK_ARG(qkv && out && n_seq > 0 && H > 0, "pvrl_attn_tc_fwd: bad arguments");
   PVRL_CHECK_ARG(seq > 0 && seq <= 256, "pvrl_attn_tc_fwd: seq=%d must be in [1, 256]", seq);
+  if (use_sp()) return attn_sp_fwd_launch(qkv, out, lse, n_seq, seq, H, scale, static_cast<cudaStream_t>(stream));
   const int npad = ((seq + 31) / 32) * 32;
   CUtensorMap tq, tkv;
   int rc;

@@ -128,8 +128,11 @@ class FlatOptimizer:
     """torch.optim-shaped (param_groups / step / zero_grad / state_dict) optimizer over flat buffers.
 
     Layout: trainable parameters of group 0, then group 1, ... in the order given; `offsets[i] = (start, end)` of
-    parameter i (torch.optim's numbering) inside `flat_param` / `flat_grad` / the state buffers.  Frozen parameters
-    (`requires_grad == False` at construction) are left alone, as torch leaves parameters without `.grad`.
+    TRAINABLE parameter i (`_params[i]`) inside `flat_param` / `flat_grad` / the state buffers.  Frozen parameters
+    (`requires_grad == False` at construction) stay in `param_groups` and in torch.optim's integer numbering
+    (`_ids[i]` = the torch id of trainable parameter i) exactly as torch.optim keeps them -- the reference's groups always
+    contain frozen parameters (`head.*` in every fine-tuning config, the CLIP text tower in pre-training), so an
+    `optimizer_state` saved by either side loads on the other -- but they get no slot in the flat buffers and no state.
     One deliberate difference: gradients are views that are cleared, never dropped, so a trainable parameter that the
     backward does not reach is updated with a zero gradient (it still sees weight decay and its moments decay) where
     torch would skip it; setting `p.grad = None` before `step()` restores torch's behaviour for that step."""
@@ -148,19 +151,24 @@ class FlatOptimizer:
         else:
             self.defaults.update(betas=tuple(betas), eps=eps)
         self.param_groups, self.offsets, self._ranges = [], [], []
-        total, dev = 0, None
+        self._params, self._ids = [], []
+        total, dev, next_id = 0, None, 0
         for g in groups:
             g = dict(g)
             for k, v in self.defaults.items():
                 g.setdefault(k, v)
-            ps = [p for p in g["params"] if p.requires_grad]
-            g["params"] = ps
+            g["params"] = list(g["params"])          # frozen parameters included, as torch.optim keeps them
             start = total
-            for p in ps:
-                assert p.is_cuda and p.dtype == torch.float32, "FlatOptimizer drives fp32 CUDA parameters (no CPU path)"
-                dev = p.device if dev is None else dev
-                self.offsets.append((total, total + p.numel()))
-                total += p.numel()
+            for p in g["params"]:
+                if p.requires_grad:
+                    assert p.is_cuda and p.dtype == torch.float32, \
+                        "FlatOptimizer drives fp32 CUDA parameters (no CPU path)"
+                    dev = p.device if dev is None else dev
+                    self.offsets.append((total, total + p.numel()))
+                    total += p.numel()
+                    self._params.append(p)
+                    self._ids.append(next_id)
+                next_id += 1
             self._ranges.append((start, total))
             self.param_groups.append(g)
         if total == 0:
@@ -169,7 +177,6 @@ class FlatOptimizer:
         self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
         n_state = 1 if method == "sgd" else 2
         self._state = [torch.zeros(total, device=dev, dtype=torch.float32) for _ in range(n_state)]
-        self._params = [p for g in self.param_groups for p in g["params"]]
         with torch.no_grad():
             for p, (a, b) in zip(self._params, self.offsets):
                 view = self.flat_param[a:b].view_as(p)
@@ -263,11 +270,11 @@ class FlatOptimizer:
         step = float(self._step_dev.item())
         state, keys = {}, self._STATE_KEYS[self.method]
         if step > 0:
-            for i, (p, (a, b)) in enumerate(zip(self._params, self.offsets)):
+            for pid, p, (a, b) in zip(self._ids, self._params, self.offsets):
                 st = {k: buf[a:b].view_as(p).clone() for k, buf in zip(keys, self._state)}
                 if self.method != "sgd":
                     st["step"] = torch.tensor(step)
-                state[i] = st
+                state[pid] = st
         groups, i = [], 0
         for g in self.param_groups:
             d = {k: v for k, v in g.items() if k != "params"}
@@ -282,14 +289,14 @@ class FlatOptimizer:
             raise ValueError("loaded state dict contains parameter groups that don't match the optimizer's")
         for mine, theirs in zip(self.param_groups, groups):
             mine.update({k: v for k, v in theirs.items() if k != "params"})
-        ids = [i for g in groups for i in g["params"]]
+        ids = [i for g in groups for i in g["params"]]      # their id of the parameter at torch position 0, 1, 2, ...
         keys, step = self._STATE_KEYS[self.method], 0.0
         for buf in self._state:
             buf.zero_()
-        for pos, pid in enumerate(ids):
-            st = sd["state"].get(pid)
+        for pos, tid in enumerate(self._ids):               # trainable parameter `pos` sits at torch position `tid`
+            st = sd["state"].get(ids[tid])
             if st is None:
-                continue
+                continue                                    # never stepped (or frozen on the saving side)
             a, b = self.offsets[pos]
             for k, buf in zip(keys, self._state):
                 if st.get(k) is not None:

@@ -334,7 +334,8 @@ def test_kl_topk_loss(ops, topk):
     assert _report("softmax", sm, pred.softmax(1))[0].max() < 1e-6
 
 
-@pytest.mark.parametrize("n_seq,seq,H", [(3, 197, 12), (2, 128, 4), (2, 50, 2), (1, 256, 2), (144, 197, 12)])
+@pytest.mark.parametrize("n_seq,seq,H", [(3, 197, 12), (2, 128, 4), (2, 50, 2), (1, 256, 2), (144, 197, 12),
+                                          (13, 197, 12), (30, 101, 12), (20, 145, 12), (37, 256, 5), (40, 17, 12)])
 def test_attn_tensor_core(ops, n_seq, seq, H):
     """tcgen05 spatial attention (bf16) against the fp32 torch restatement and the CUDA-core kernel."""
     C = H * 64

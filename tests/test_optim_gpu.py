@@ -92,8 +92,8 @@ def test_flat_optimizer_vs_reference_trajectories(ops, gold_dir):
         cfg = make_cfg(case["solver"], case["train"], case["bn_wd"])
         m = Skeleton(gold["names"], gold["shapes"], device="cuda")
         o = opt.construct_optimizer(m, cfg)
-        assert [len(g["params"]) for g in o.param_groups] == \
-            [len([n for n in g["names"] if n not in case["frozen"]]) for g in case["groups"]]
+        assert [len(g["params"]) for g in o.param_groups] == [len(g["names"]) for g in case["groups"]]   # frozen ones kept
+        assert len(o._params) == sum(len([n for n in g["names"] if n not in case["frozen"]]) for g in case["groups"])
         gg = torch.Generator().manual_seed(7)
         for it in range(4):
             opt.set_lr(o, cfg.SOLVER.BASE_LR * (1.0 - 0.2 * it))
