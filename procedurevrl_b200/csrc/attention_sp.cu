@@ -3,8 +3,9 @@
 //
 //   warp 8      TMA producer: Q (two 128-row tiles), K, V of problem i+1 land in the second smem stage while problem i
 //               computes.  K / V are fetched ONCE per (frame, head) and serve both query tiles.
-//   warp 9      tcgen05 issuer, event driven: for each query tile it issues S = Q K^T (128 x npad x 64) as soon as the
-//               tile's TMEM region is free and O = P V as soon as the tile's probabilities are in TMEM.
+//   warps 9,10  tcgen05 issuers, one per query tile (independent blocking waits, no polling loop): S = Q K^T
+//               (128 x npad x 64) as soon as the tile's TMEM region is free, O = P V as soon as its probabilities are
+//               in TMEM.
 //   warps 0-3   softmax + epilogue of query tile 0;  warps 4-7 the same for query tile 1.  One query row per thread:
 //               row max and exp2 on tcgen05.ld'ed scores (two passes over TMEM), the bf16 probabilities go back INTO
 //               TMEM over the dead scores (tcgen05.st) and feed the P V MMA as its A operand -- P never touches shared
@@ -20,12 +21,19 @@
 #include "pvrl_ptx.cuh"
 
 namespace pvrl {
+constexpr int TR_WARPS = 12, TR_ITERS = 16, TR_SLOTS = 8;
 namespace {
 
 constexpr int SP_TILE_BYTES = 128 * 128;   // [128 rows][64 bf16], SWIZZLE_128B
-constexpr int SP_THREADS = 320;
+constexpr int SP_THREADS = 352;
 constexpr int SP_STAGE_OUT = 4096;         // per-warp output staging: [32 rows][128 B]
 constexpr float SP_LOG2E = 1.4426950408889634f;
+
+// Development aid (PVRL_SP_TRACE=1): CTA 0 records clock64() at the phase boundaries of its first 16 problems into a
+// device buffer that pvrl_debug_sp_trace() copies out; a null pointer (the default) costs one predicate per phase.
+__device__ __forceinline__ void trace(long long* tr, int warp, int it, int slot) {
+  if (tr != nullptr && blockIdx.x == 0 && it < TR_ITERS) tr[(warp * TR_ITERS + it) * TR_SLOTS + slot] = clock64();
+}
 
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }   // one FMNMX3
 
@@ -73,7 +81,7 @@ __device__ __forceinline__ void chunk_exp(const uint32_t (&r)[W], int live, floa
 __global__ void __launch_bounds__(SP_THREADS, 1)
 attn_sp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                    const __grid_constant__ CUtensorMap tmO, float* __restrict__ lse, int seq, int H, float scale,
-                   int npad, int total) {
+                   int npad, int total, long long* __restrict__ tr) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -102,7 +110,7 @@ attn_sp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int rows = min(128, seq - i * 128);              // live query rows of tile i
       const int live_threads = rows > 0 ? ((rows + 31) >> 5) * 32 : 32;
       mbar_init(bar_full + 8 * i, 1);
-      mbar_init(bar_empty + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, n_tiles);
       mbar_init(bar_s + 8 * i, 1);
       mbar_init(bar_p + 8 * i, live_threads);
       mbar_init(bar_o + 8 * i, 1);
@@ -128,6 +136,7 @@ attn_sp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int s_idx = pair / H, h = pair - s_idx * H;
         const uint32_t sQ = base + s * stage_bytes, sK = sQ + 2 * SP_TILE_BYTES, sV = sK + kv_bytes;
         mbar_wait(bar_empty + 8 * s, ((it >> 1) & 1) ^ 1);
+        trace(tr, warp, it, 0);
         mbar_expect_tx(bar_full + 8 * s, tx);
         tma_load_3d(sQ, &tmQ, bar_full + 8 * s, h * 64, 0, s_idx);
         tma_load_3d(sK, &tmKV, bar_full + 8 * s, C + h * 64, 0, s_idx);
@@ -135,53 +144,32 @@ attn_sp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tma_load_3d(sV, &tmKV, bar_full + 8 * s, 2 * C + h * 64, 0, s_idx);
       }
     }
-  } else if (warp == 9) {
-    // ------------------------------------------------------------------------------- MMA issuer (event loop)
-    if (lane == 0) {
+  } else if (warp >= 9) {
+    // ------------------------------------------------------------------------------- MMA issuers: warp 9 -> tile 0, warp 10 -> tile 1
+    const int t = warp - 9;
+    if (lane == 0 && t < n_tiles) {
       const uint32_t idesc_s = make_idesc_bf16(128, npad, 0, 0);
       const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
-      int s_iss[2] = {0, 0}, pv_iss[2] = {0, 0};
-      int done = 0;
-      const int target = n_tiles * n_my;
-      long long t_last = clock64();
-      while (done < target) {
-        bool progress = false;
+      const uint32_t tcol = tmem + t * 256;
+      for (int it = 0; it < n_my; ++it) {
+        const int s = it & 1;
+        const uint32_t sQ = base + s * stage_bytes + t * SP_TILE_BYTES, sK = base + s * stage_bytes + 2 * SP_TILE_BYTES;
+        const uint32_t sV = sK + kv_bytes;
+        mbar_wait(bar_free + 8 * t, (it & 1) ^ 1);            // the tile's TMEM region has been drained (passes at it = 0)
+        mbar_wait(bar_full + 8 * s, (it >> 1) & 1);
+        tc_fence_after();
+        trace(tr, warp, it, 0);
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if (t >= n_tiles) continue;
-          const uint32_t tcol = tmem + t * 256;
-          if (pv_iss[t] < s_iss[t]) {
-            const int it = pv_iss[t], s = it & 1;
-            if (mbar_try_wait(bar_p + 8 * t, it & 1)) {
-              tc_fence_after();
-              const uint32_t sV = base + s * stage_bytes + 2 * SP_TILE_BYTES + kv_bytes;
-              for (int k = 0; k < npad / 16; ++k)
-                umma_bf16_ts(tcol + 128, tcol + k * 8, make_smem_desc(sV + k * 2048, 8192, 1024), idesc_o, k > 0);
-              umma_commit(bar_o + 8 * t);
-              pv_iss[t] = it + 1;
-              ++done;
-              if (n_tiles == 1 || pv_iss[t ^ 1] > it) umma_commit(bar_empty + 8 * s);   // both tiles are past this stage
-              progress = true;
-            }
-          } else if (s_iss[t] < n_my) {
-            const int it = s_iss[t], s = it & 1;
-            if (mbar_try_wait(bar_full + 8 * s, (it >> 1) & 1) && mbar_try_wait(bar_free + 8 * t, (it & 1) ^ 1)) {
-              tc_fence_after();
-              const uint32_t sQ = base + s * stage_bytes + t * SP_TILE_BYTES, sK = base + s * stage_bytes + 2 * SP_TILE_BYTES;
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(tcol, make_smem_desc(sQ + k * 32, 16, 1024), make_smem_desc(sK + k * 32, 16, 1024), idesc_s, k > 0);
-              umma_commit(bar_s + 8 * t);
-              s_iss[t] = it + 1;
-              progress = true;
-            }
-          }
-        }
-        if (progress) {
-          t_last = clock64();
-        } else if (clock64() - t_last > 4000000000LL) {
-          __trap();                                          // protocol bug: fail the launch instead of hanging the GPU
-        }
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tcol, make_smem_desc(sQ + k * 32, 16, 1024), make_smem_desc(sK + k * 32, 16, 1024), idesc_s, k > 0);
+        umma_commit(bar_s + 8 * t);
+        mbar_wait(bar_p + 8 * t, it & 1);
+        tc_fence_after();
+        trace(tr, warp, it, 1);
+        for (int k = 0; k < npad / 16; ++k)
+          umma_bf16_ts(tcol + 128, tcol + k * 8, make_smem_desc(sV + k * 2048, 8192, 1024), idesc_o, k > 0);
+        umma_commit(bar_o + 8 * t);
+        umma_commit(bar_empty + 8 * s);                       // this tile is done with the stage (count = n_tiles)
       }
     }
   } else {
@@ -199,8 +187,10 @@ attn_sp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int it = 0; it < n_my; ++it) {
         const int pair = total - 1 - (static_cast<int>(blockIdx.x) + it * G);
         const int s_idx = pair / H, h = pair - s_idx * H;
+        trace(tr, warp, it, 0);
         mbar_wait(bar_s + 8 * t, it & 1);
         tc_fence_after();
+        trace(tr, warp, it, 1);
         uint32_t ra[32], rb[32], rt[16];
         // ---- pass 1: row max (TMEM reads software-pipelined: chunk c + 1 is in flight while chunk c is reduced)
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -223,6 +213,7 @@ attn_sp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         const float mxs = mx * sl2;
+        trace(tr, warp, it, 2);
         // ---- pass 2: p = 2^(s * scale * log2e - max), bf16 pairs written back over the scores
         float sum4[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t pk[16];
@@ -251,15 +242,18 @@ attn_sp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(bar_p + 8 * t);
+        trace(tr, warp, it, 3);
         // ---- epilogue: O / sum -> bf16 -> staging tile -> TMA store
         mbar_wait(bar_o + 8 * t, it & 1);
         tc_fence_after();
+        trace(tr, warp, it, 4);
         tmem_ld32(tb + 128, ra);
         tmem_ld32(tb + 160, rb);
         tmem_ld_wait_on(ra);
         tmem_ld_wait_on(rb);
         tc_fence_before();
         mbar_arrive(bar_free + 8 * t);                       // the tile's TMEM region may take the next S
+        trace(tr, warp, it, 5);
         if (lane == 0) bulk_wait_read0();                    // previous TMA store has finished reading the staging tile
         __syncwarp();
         const float inv = 1.0f / sum;
@@ -284,6 +278,7 @@ attn_sp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           bulk_commit();
         }
         if (lse != nullptr && qi < seq) lse[static_cast<long long>(pair) * seq + qi] = mx * scale + __logf(sum);
+        trace(tr, warp, it, 6);
       }
       if (lane == 0) bulk_wait0();
     }
@@ -296,6 +291,18 @@ attn_sp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }  // namespace
 
 int make_tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t cols, uint64_t seq, uint64_t n_seq, uint32_t box_rows);
+
+// PVRL_SP_TRACE=1: device buffer the kernels' trace() calls write into (nullptr otherwise)
+long long* sp_trace_buffer() {
+  static long long* buf = [] {
+    const char* e = getenv("PVRL_SP_TRACE");
+    long long* p = nullptr;
+    if (e != nullptr && atoi(e) != 0 && cudaMalloc(&p, sizeof(long long) * TR_WARPS * TR_ITERS * TR_SLOTS) == cudaSuccess)
+      cudaMemset(p, 0, sizeof(long long) * TR_WARPS * TR_ITERS * TR_SLOTS);
+    return p;
+  }();
+  return buf;
+}
 
 int attn_sp_fwd_launch(const void* qkv, void* out, float* lse, int n_seq, int seq, int H, float scale, cudaStream_t stream) {
   const int npad = ((seq + 15) / 16) * 16;
@@ -313,8 +320,19 @@ int attn_sp_fwd_launch(const void* qkv, void* out, float* lse, int n_seq, int se
   const int total = n_seq * H;
   const int grid = total < num_sms() ? total : num_sms();
   PVRL_CUDA(launch_pdl(attn_sp_fwd_kernel, dim3(grid), dim3(SP_THREADS), smem, stream, tq, tkv, to, lse, seq, H, scale,
-                       npad, total));
+                       npad, total, sp_trace_buffer()));
   return launched("attn_sp_fwd_kernel");
 }
 
 }  // namespace pvrl
+
+// Development aid: copies the PVRL_SP_TRACE buffer ([12 warps][16 problems][8 slots] clock64 stamps of CTA 0) to `host_out`
+// and clears it; returns the number of int64 values written, 0 when tracing is off.
+extern "C" int pvrl_debug_sp_trace(long long* host_out) {
+  long long* buf = pvrl::sp_trace_buffer();
+  if (buf == nullptr || host_out == nullptr) return 0;
+  const size_t n = pvrl::TR_WARPS * pvrl::TR_ITERS * pvrl::TR_SLOTS;
+  if (cudaMemcpy(host_out, buf, n * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  cudaMemset(buf, 0, n * sizeof(long long));
+  return static_cast<int>(n);
+}

@@ -60,8 +60,11 @@ class EncoderEngine:
 
     # ------------------------------------------------------------------------------------------ parameters
     def _grad_names(self):
-        n = [self.pre + k for k in ("cls_token", "pos_embed", "time_embed", "patch_embed.proj.weight",
-                                    "patch_embed.proj.bias")]
+        # space_only models have no time_embed parameter (vit.py:213-215)
+        emb = ("cls_token", "pos_embed", "patch_embed.proj.weight", "patch_embed.proj.bias") \
+            if self.attention_type == "space_only" else \
+            ("cls_token", "pos_embed", "time_embed", "patch_embed.proj.weight", "patch_embed.proj.bias")
+        n = [self.pre + k for k in emb]
         for i in range(self.depth):
             b = f"{self.pre}blocks.{i}."
             for ln in (("norm1", "temporal_norm1", "norm2") if self.divided else ("norm1", "norm2")):
@@ -182,8 +185,11 @@ class EncoderEngine:
     def _pos_time(self, HW, T):
         """pos_embed / time_embed rows for this input size; nearest-neighbour resize as vit.py:375-386,398-402."""
         pos = self.p[self.pre + "pos_embed"].detach()[0]
-        te = self.p[self.pre + "time_embed"].detach()[0]
         pos_idx = te_idx = None
+        if self.attention_type == "space_only":               # no time embedding (vit.py:393); the caller passes zeros
+            te = None
+        else:
+            te = self.p[self.pre + "time_embed"].detach()[0]
         if pos.shape[0] != HW + 1:
             P0 = int(round(math.sqrt(pos.shape[0] - 1)))
             P1 = int(round(math.sqrt(HW)))
@@ -191,7 +197,7 @@ class EncoderEngine:
             pos_idx = torch.cat((torch.zeros(1, dtype=torch.long, device=pos.device),
                                  1 + (src.view(-1, 1) * P0 + src.view(1, -1)).reshape(-1)))
             pos = pos.index_select(0, pos_idx).contiguous()
-        if te.shape[0] != T:
+        if te is not None and te.shape[0] != T:
             te_idx = (torch.arange(T, device=te.device).float() * (te.shape[0] / T)).floor().long()
             te = te.index_select(0, te_idx).contiguous()
         return pos, te, pos_idx, te_idx
@@ -570,7 +576,8 @@ def _backward_plain(self, st, dfeat):
     dYp = self._act(Mp, D, dev)
     ops.gather_cast(dx, dYp, Mp, D, ops.MAP_PATCH, colsum=G[self.pre + "patch_embed.proj.bias"], **g)
     self.linear_dw(dYp, st["A"], G[self.pre + "patch_embed.proj.weight"].view(D, KP), None, Mp, D, KP)
-    gpos, gte = G[self.pre + "pos_embed"][0], G[self.pre + "time_embed"][0]
+    gpos = G[self.pre + "pos_embed"][0]
+    gte = None if so else G[self.pre + "time_embed"][0]
     dpos = gpos if st["pos_idx"] is None else torch.zeros(HW + 1, D, device=dev)
     dte = None if so else (gte if st["te_idx"] is None else torch.zeros(T, D, device=dev))
     ops.embed_bwd(dx, G[self.pre + "cls_token"].view(D), dpos, dte, Bx, D, Tx, HW)

@@ -3,8 +3,10 @@
 `MODEL_REGISTRY.get(cfg.MODEL.MODEL_NAME)(cfg)` builds the module, `build_model` moves it to the current CUDA
 device and, for NUM_GPUS > 1, wraps it in DistributedDataParallel: one process per GPU, a single bucketed NCCL
 gradient all-reduce over NVLink/NVSwitch overlapped with backward -- the only collective on
-the path.  Unlike the reference (`find_unused_parameters=True`, build.py:49-53) no per-step graph walk is
-needed: the encoder is one autograd node that always produces every parameter gradient."""
+the path.  `find_unused_parameters=True` as in the reference (build.py:49-53): its fine-tuning flows depend on it --
+`construct_optimizer` freezes the encoder for TRAIN.LINEAR only AFTER `build_model` has wrapped the module, and the
+NUM_SEG > 0 forecasting path never touches `order_tfm.pad_embedding` -- so parameters registered as trainable may see
+no gradient in a step."""
 import torch
 
 
@@ -52,5 +54,5 @@ def wrap_data_parallel(model, cfg, device=None):
     bucket_mb = cfg.B200.GRAD_BUCKET_MB if "B200" in cfg else 64
     ids = None if device is None else [device]
     return torch.nn.parallel.DistributedDataParallel(
-        module=model, device_ids=ids, output_device=device, find_unused_parameters=False,
+        module=model, device_ids=ids, output_device=device, find_unused_parameters=True,
         gradient_as_bucket_view=True, bucket_cap_mb=bucket_mb, broadcast_buffers=False)

@@ -321,19 +321,39 @@ class MViT(nn.Module):
 
 
 def load_pretrained(model, path):
-    """MViTv2 checkpoint -> `model.video_encoder` (reference helpers.py:100-130 for the mvit entry: keys of the released
-    MViTv2_S_in1k.pyth live under 'model_state'; its classification head is dropped, everything whose name and shape
-    match the encoder is loaded non-strictly)."""
+    """MViTv2 checkpoint -> `model.video_encoder` (reference helpers.py:100-145 for the mvit entry).  Keys of the released
+    image checkpoint MViTv2_S_in1k.pyth live under 'model_state' without the 'video_encoder.' prefix and are converted as
+    the reference does: `pool_*` and `patch_embed.proj.weight` (2-D convolutions) are repeated over the temporal kernel
+    extent (`unsqueeze(2).repeat`, helpers.py:131-133), `rel_pos_*` tables are linearly interpolated to the model's length
+    (helpers.py:134-138); an already converted checkpoint ('video_encoder.'-prefixed keys) loads as is.  Tensors whose
+    shape still does not match (the 1000-way ImageNet head) are reported, never dropped silently."""
     ck = torch.load(path, map_location="cpu")
     for key in ("model_state", "model", "state_dict"):
         if isinstance(ck, dict) and key in ck:
             ck = ck[key]
             break
     own = model.state_dict()
-    sd = {}
+    sd, skipped = {}, []
     for k, v in ck.items():
         k = k[6:] if k.startswith("model.") else k
-        for cand in (k, "video_encoder." + k):
-            if cand in own and own[cand].shape == v.shape:
-                sd[cand] = v
-    return model.load_state_dict(sd, strict=False)
+        cand = k if k in own else "video_encoder." + k
+        if cand not in own:
+            skipped.append((k, "no such parameter"))
+            continue
+        tgt = own[cand]
+        if tgt.shape != v.shape:
+            if ("pool_" in k or "patch_embed.proj.weight" in k) and v.dim() == 4 and tgt.dim() == 5 \
+                    and tgt.shape[:2] == v.shape[:2] and tgt.shape[3:] == v.shape[2:]:
+                v = v.unsqueeze(2).repeat(1, 1, tgt.shape[2], 1, 1)                        # helpers.py:131-133
+            elif "rel_pos_" in k and v.dim() == 2 and tgt.dim() == 2 and tgt.shape[1] == v.shape[1]:
+                v = torch.nn.functional.interpolate(v.t().unsqueeze(0).float(), size=tgt.shape[0], mode="linear")[0] \
+                    .t().contiguous().to(v.dtype)                                          # helpers.py:134-138
+            else:
+                skipped.append((k, f"shape {tuple(v.shape)} != {tuple(tgt.shape)}"))
+                continue
+        sd[cand] = v
+    if skipped:
+        print("load_pretrained: skipped " + ", ".join(f"{k} ({why})" for k, why in skipped), flush=True)
+    res = model.load_state_dict(sd, strict=False)
+    model.pretrained_skipped = skipped
+    return res

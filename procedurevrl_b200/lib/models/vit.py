@@ -116,8 +116,9 @@ class VisionTransformer(nn.Module):
         self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
         self.pos_embed = nn.Parameter(torch.zeros(1, num_patches + 1, embed_dim))
         self.pos_drop = nn.Dropout(p=drop_rate)
-        self.time_embed = nn.Parameter(torch.zeros(1, num_frames, embed_dim))
-        self.time_drop = nn.Dropout(p=drop_rate)
+        if attention_type != "space_only":                                             # vit.py:213-215
+            self.time_embed = nn.Parameter(torch.zeros(1, num_frames, embed_dim))
+            self.time_drop = nn.Dropout(p=drop_rate)
         self.dpr = [x.item() for x in torch.linspace(0, drop_path_rate, depth)]        # vit.py:220
         self.blocks = nn.ModuleList([Block(embed_dim, num_heads, mlp_ratio, qkv_bias, self.dpr[i], norm_layer,
                                            attention_type) for i in range(depth)])
@@ -375,9 +376,11 @@ class vit_base_patch16_224_develop(nn.Module):
 
 
 def load_pretrained(model, path, num_frames):
-    """Checkpoint -> TimeSformer initialisation with the key conventions of reference helpers.py:24-52,203-241:
-    accepts {'model_state': ...} / {'model': ...}, strips a leading 'model.', copies spatial attention / norm1
-    into the temporal branch when the checkpoint has none, resizes time_embed, loads non-strictly."""
+    """Checkpoint -> TimeSformer initialisation with the key conventions of reference helpers.py:24-52,196-243:
+    accepts {'model_state': ...} / {'model': ...}, strips a leading 'model.', nearest-resizes `pos_embed`
+    (helpers.py:199-211) and `time_embed` (:213-218) when their lengths differ, copies spatial attention / norm1 into
+    the temporal branch when the checkpoint has none (:220-237), drops a classifier of another width (:185-192) and
+    loads non-strictly.  Anything else whose shape does not match is reported, never dropped silently."""
     ck = torch.load(path, map_location="cpu")
     for key in ("model_state", "model", "state_dict"):
         if isinstance(ck, dict) and key in ck:
@@ -385,13 +388,23 @@ def load_pretrained(model, path, num_frames):
             break
     sd = {(k[6:] if k.startswith("model.") else k): v for k, v in ck.items()}
     own = model.state_dict()
+    interp = torch.nn.functional.interpolate
+    if "pos_embed" in sd and "pos_embed" in own and sd["pos_embed"].shape[1] != own["pos_embed"].shape[1]:
+        pe = sd["pos_embed"]
+        grid = interp(pe[:, 1:].transpose(1, 2), size=own["pos_embed"].shape[1] - 1, mode="nearest").transpose(1, 2)
+        sd["pos_embed"] = torch.cat((pe[:, :1], grid), 1)
     if "time_embed" in sd and sd["time_embed"].shape[1] != num_frames:
-        te = sd["time_embed"].transpose(1, 2)
-        sd["time_embed"] = torch.nn.functional.interpolate(te, size=(num_frames), mode="nearest").transpose(1, 2)
-    for k in list(sd):
-        if "blocks" in k and ".attn." in k and k.replace(".attn.", ".temporal_attn.") not in sd:
-            sd[k.replace(".attn.", ".temporal_attn.")] = sd[k]
-        if "blocks" in k and ".norm1." in k and k.replace(".norm1.", ".temporal_norm1.") not in sd:
-            sd[k.replace(".norm1.", ".temporal_norm1.")] = sd[k]
+        sd["time_embed"] = interp(sd["time_embed"].transpose(1, 2), size=num_frames, mode="nearest").transpose(1, 2)
+    if getattr(model, "attention_type", "divided_space_time") == "divided_space_time":
+        for k in list(sd):
+            if "blocks" in k and ".attn." in k and k.replace(".attn.", ".temporal_attn.") not in sd:
+                sd[k.replace(".attn.", ".temporal_attn.")] = sd[k]
+            if "blocks" in k and ".norm1." in k and k.replace(".norm1.", ".temporal_norm1.") not in sd:
+                sd[k.replace(".norm1.", ".temporal_norm1.")] = sd[k]
+    skipped = [(k, f"shape {tuple(v.shape)} != {tuple(own[k].shape)}") for k, v in sd.items()
+               if k in own and own[k].shape != v.shape]
+    if skipped:
+        print("load_pretrained: skipped " + ", ".join(f"{k} ({why})" for k, why in skipped), flush=True)
     sd = {k: v for k, v in sd.items() if k in own and own[k].shape == v.shape}
+    model.pretrained_skipped = skipped
     return model.load_state_dict(sd, strict=False)

@@ -71,6 +71,7 @@ _SIGS = {
     "pvrl_attn_tc_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_void_p],
     "pvrl_attn_tc_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float,
                          _c_void_p],
+    "pvrl_debug_sp_trace": [_c_void_p],
     "pvrl_linear_small_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
     "pvrl_linear_small_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int,
                               _c_void_p],
@@ -316,6 +317,15 @@ def attn_tc_bwd(qkv, out, dout, lse, dqkv, n_seq, seq, H, scale):
     _check(lib().pvrl_attn_tc_bwd(_p(qkv), _p(out), _p(dout), _p(lse), _p(dqkv), n_seq, seq, H, scale, _stream()),
            "pvrl_attn_tc_bwd")
     return dqkv
+
+
+def debug_sp_trace():
+    """PVRL_SP_TRACE=1: clock64 stamps of CTA 0 of the last persistent spatial-attention launch, [12, 16, 8] int64."""
+    import numpy as np
+    buf = np.zeros((12, 16, 8), dtype=np.int64)
+    torch.cuda.synchronize()
+    n = lib().pvrl_debug_sp_trace(buf.ctypes.data)
+    return buf if n else None
 
 
 # ---------------------------------------------------------------------------------------------- head / loss
