@@ -82,10 +82,23 @@ def block_taps(m):
     return taps, hooks
 
 
+def grad_windows(g, n_win=4, width=64):
+    """`n_win` windows of `width` consecutive elements at evenly spaced offsets past the head (the last one ends at the
+    tensor's end), so that an error anywhere in a large dW -- a permuted tile, a dropped split-K slice -- is seen."""
+    f = g.flatten()
+    n = f.numel()
+    if n <= width:
+        return torch.zeros(0, width), []
+    offs = sorted({min(n - width, (i + 1) * (n - width) // n_win) for i in range(n_win)})
+    return torch.stack([f[o:o + width] for o in offs]).clone(), offs
+
+
 def grad_summary(named_grads):
     out = {}
     for k, g in named_grads.items():
-        out[k] = {"norm": g.norm().item(), "head": g.flatten()[:64].clone(), "sum": g.double().sum().item()}
+        win, offs = grad_windows(g)
+        out[k] = {"norm": g.norm().item(), "head": g.flatten()[:64].clone(), "sum": g.double().sum().item(),
+                  "abs_sum": g.double().abs().sum().item(), "win": win, "win_offsets": offs}
     return out
 
 
@@ -155,16 +168,17 @@ def gold_droppath(name):
     print(name, "n_rand", len(rands), [tuple(r.shape) for r in rands])
 
 
-def gold_pretrain(depth, Bv, name):
-    """HowTo100M stage-2 pretrain step (procedurevrl_adamw.yaml) with the COIN step bank as LABEL_EMB
-    (small fixture) and the CLIP text tower replaced by pre-extracted text embeddings."""
+def gold_pretrain(depth, Bv, name, bank="./data/clip_step_emb_coin.pth", n_classes=778):
+    """HowTo100M stage-2 pretrain step (procedurevrl_adamw.yaml) with the COIN step bank (small fixture) or the shipped
+    HowTo100M verb-phrase bank (K = 9871, the one the YAML names) as LABEL_EMB, and the CLIP text tower replaced by
+    pre-extracted text embeddings."""
     T, max_len = 8, 9
     st = O.seeded_state(depth=depth, frames=T, seed=900 + depth, with_order=True)
     g = torch.Generator().manual_seed(77)
     text_emb = 0.4 * torch.randn(Bv * max_len, 512, generator=g)
     vis_emb = 0.4 * torch.randn(Bv * max_len, 512, generator=g)
-    ov = ["MODEL.DROP_PATH", 0.0, "TIMESFORMER.DEPTH", depth, "TRAIN.LABEL_EMB", "./data/clip_step_emb_coin.pth",
-          "MODEL.NUM_CLASSES", 778, "TRAIN.TEXT", "preextracted"]
+    ov = ["MODEL.DROP_PATH", 0.0, "TIMESFORMER.DEPTH", depth, "TRAIN.LABEL_EMB", bank,
+          "MODEL.NUM_CLASSES", n_classes, "TRAIN.TEXT", "preextracted"]
     m, cfg = build_ref("configs/HowTo100M/procedurevrl_adamw.yaml", ov, st)
     # pre-extracted text embeddings stand in for the frozen tower's output (north star)
     m.model.text_model.encode_text = lambda ids: text_emb
@@ -200,7 +214,8 @@ def gold_pretrain(depth, Bv, name):
     for i in sorted({0, depth - 1}):
         keys += [f"model.blocks.{i}.{s}" for s in BLOCK_GRAD]
     keys += [k for k in grads if k.startswith("model.order_tfm.")]
-    torch.save({"cfg": {"depth": depth, "Bv": Bv, "T": T, "state_seed": 900 + depth, "clip_seed": 9, "emb_seed": 77},
+    torch.save({"cfg": {"depth": depth, "Bv": Bv, "T": T, "state_seed": 900 + depth, "clip_seed": 9, "emb_seed": 77,
+                        "bank": os.path.basename(bank), "n_classes": n_classes},
                 "draws": {"mask_inds": mask_inds, "pad_start": pad_start, "noise": noise, "rand_inds": rand_inds},
                 "pred": pred.detach().clone(), "teacher": teacher.detach().clone(),
                 "mse0": mse[0].detach().clone(), "mse1": mse[1].detach().clone(),
@@ -228,21 +243,87 @@ def gold_forecast(name):
     print(name, tuple(probs.shape), probs.max().item())
 
 
+def gold_finetune_heads(name, dataset):
+    """SURVEY 8a row A14, vit.py:308-322: the fine-tuning path WITHOUT DEV.MATCH_LANG_EMB -- frozen `head` (768 -> 512),
+    L2 normalisation, then `head_cls` (512 -> NUM_CLASSES) / temp, or for TRAIN.DATASET Epickitchens the tuple
+    (`head_v` 512 -> 97, `head_n` 512 -> 300).  This is what every shipped COIN / EK fine-tuning YAML runs."""
+    depth, B, T = 2, 2, 8
+    ek = dataset == "Epickitchens"
+    yaml_rel = "configs/EK/egocentric_action_classification.yaml" if ek else "configs/COIN/step_classification.yaml"
+    ov = ["MODEL.DROP_PATH", 0.0, "TIMESFORMER.DEPTH", depth, "DATA.NUM_FRAMES", T, "DEV.MATCH_LANG_EMB", False]
+    vit, build, _ = ref_shims.load_reference()
+    cwd = os.getcwd()
+    os.chdir(ref_shims.REFERENCE_ROOT)
+    try:
+        cfg = ref_shims.reference_cfg(yaml_rel, ov)
+        m = build.build_model(cfg)
+    finally:
+        os.chdir(cwd)
+    st = O.seeded_state(depth=depth, frames=T, seed=640 + int(ek))
+    g = torch.Generator().manual_seed(641 + int(ek))
+    own = m.state_dict()
+    for k in own:                                        # the fine-tune heads are not part of seeded_state
+        if k not in st:
+            st[k] = 0.05 * torch.randn(own[k].shape, generator=g)
+    st = {k: v for k, v in st.items() if k in own}
+    m.load_state_dict(st, strict=True)
+    frozen = sorted(k for k, p_ in m.named_parameters() if not p_.requires_grad)
+    x = O.synthetic_clips(B, 3, T, 224, 224, seed=12)
+    m.train()
+    out = m(x)
+    outs = list(out) if isinstance(out, tuple) else [out]
+    labels = [torch.arange(B) * 29 % o.shape[1] for o in outs]
+    loss = sum(F.cross_entropy(o, l) for o, l in zip(outs, labels))
+    loss.backward()
+    grads = {k: p_.grad for k, p_ in m.named_parameters() if p_.grad is not None}
+    keys = [k for k in grads if "head" in k] + [k for k in GRAD_KEYS if k in grads]
+    keys += [f"model.blocks.{i}.{s_}" for i in (0, depth - 1) for s_ in BLOCK_GRAD if f"model.blocks.{i}.{s_}" in grads]
+    m.eval()
+    with torch.no_grad():
+        ev = m(x)
+    evs = list(ev) if isinstance(ev, tuple) else [ev]
+    torch.save({"cfg": {"depth": depth, "B": B, "T": T, "dataset": dataset, "state_seed": 640 + int(ek),
+                        "head_seed": 641 + int(ek), "clip_seed": 12, "n_classes": cfg.MODEL.NUM_CLASSES},
+                "extra_state": {k: v for k, v in st.items() if "head_" in k},
+                "frozen": frozen, "is_tuple": isinstance(out, tuple),
+                "outputs": [o.detach().clone() for o in outs], "eval_outputs": [o.clone() for o in evs],
+                "labels": labels, "loss": loss.item(), "grads": grad_summary({k: grads[k] for k in keys}),
+                "n_with_grad": len(grads)}, os.path.join(GOLD, name))
+    print(name, [tuple(o.shape) for o in outs], "loss", loss.item(), "frozen", frozen, "n_with_grad", len(grads))
+
+
+HT100M_EMB = os.path.join(GOLD, "clip_step_emb_ht100m_vbphrase.pt")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
+    only = set(sys.argv[1:])                 # optional: names of the fixtures to (re)generate
+
+    def want(name):
+        return not only or name in only
     if not os.path.exists(COIN_EMB):
         e = torch.load(os.path.join(ref_shims.REFERENCE_ROOT, "data", "clip_step_emb_coin.pth"))
         torch.save(e.clone(), COIN_EMB)     # shipped fixture (SURVEY.md §2 row 5): fp32 [778,512], un-normalised
-    gold_coin_matchlang(2, 2, 8, "coin_d2_b2.pt")
-    gold_coin_matchlang(12, 4, 8, "coin_d12_b4.pt")
-    gold_coin_matchlang(2, 1, 4, "coin_d2_t4.pt")
-    gold_coin_matchlang(2, 2, 8, "coin_d2_joint.pt", attention_type="joint_space_time", with_grads=False)
-    gold_coin_matchlang(2, 2, 8, "coin_d2_spaceonly.pt", attention_type="space_only", with_grads=False)
-    gold_droppath("droppath_d2.pt")
-    gold_pretrain(2, 2, "pretrain_d2_v2.pt")
-    gold_pretrain(12, 1, "pretrain_d12_v1.pt")
-    gold_forecast("forecast_d2.pt")
+    if not os.path.exists(HT100M_EMB):
+        e = torch.load(os.path.join(ref_shims.REFERENCE_ROOT, "data", "clip_step_emb_ht100m_vbphrase.pth"))
+        torch.save(e.clone(), HT100M_EMB)   # shipped fixture: fp32 [9871,512], the bank procedurevrl_adamw.yaml trains on
+    jobs = [("coin_d2_b2.pt", lambda n: gold_coin_matchlang(2, 2, 8, n)),
+            ("coin_d12_b4.pt", lambda n: gold_coin_matchlang(12, 4, 8, n)),
+            ("coin_d2_t4.pt", lambda n: gold_coin_matchlang(2, 1, 4, n)),
+            ("coin_d2_joint.pt", lambda n: gold_coin_matchlang(2, 2, 8, n, attention_type="joint_space_time", with_grads=False)),
+            ("coin_d2_spaceonly.pt", lambda n: gold_coin_matchlang(2, 2, 8, n, attention_type="space_only", with_grads=False)),
+            ("droppath_d2.pt", gold_droppath),
+            ("pretrain_d2_v2.pt", lambda n: gold_pretrain(2, 2, n)),
+            ("pretrain_d12_v1.pt", lambda n: gold_pretrain(12, 1, n)),
+            ("pretrain_d12_ht100m.pt", lambda n: gold_pretrain(12, 1, n, "./data/clip_step_emb_ht100m_vbphrase.pth", 9871)),
+            ("forecast_d2.pt", gold_forecast),
+            ("finetune_headcls_d2.pt", lambda n: gold_finetune_heads(n, "howto100m_develop")),
+            ("finetune_ek_d2.pt", lambda n: gold_finetune_heads(n, "Epickitchens"))]
+    for name, fn in jobs:
+        if want(name):
+            fn(name)
+    return
 
 
 if __name__ == "__main__":
