@@ -177,7 +177,7 @@ int pvrl_attn_tc_bwd(const void* qkv, const void* out, const void* dout, const f
                      int32_t n_seq, int32_t seq, int32_t H, float scale, void* stream);
 
 /* Development aid.  With PVRL_SP_TRACE=1 in the environment the persistent spatial-attention kernels record clock64()
- * stamps of CTA 0 at their phase boundaries ([12 warps][16 problems][8 slots] int64); this copies them to host_out and
+ * stamps of CTA 0 at their phase boundaries ([20 warps][16 problems][8 slots] int64); this copies them to host_out and
  * clears the buffer.  Returns the number of values written, 0 when tracing is off. */
 int pvrl_debug_sp_trace(long long* host_out);
 

@@ -220,12 +220,13 @@ def finetune_cls_forward(p: P, x, depth=12, temp=0.02, training=True, drop_scale
 
 def finetune_ek_forward(p: P, x, depth=12, temp=0.02, training=True, drop_scales=None):
     """VisionTransformer.forward, EPIC-Kitchens fine-tune branch (TRAIN.DATASET Epickitchens): vit.py:308-314 -- frozen
-    `head`, L2 normalisation, then the verb (97) and noun (300) heads, each / temp; returned as the tuple (v, n)."""
+    `head`, L2 normalisation, then the verb (97) and noun (300) heads, each / temp; returned as the tuple (v, n) --
+    in eval mode too: the early `return (v, n)` at vit.py:314 bypasses the test-time softmax of vit.py:355-356."""
     feat = forward_features(p, x, depth, drop_scales=drop_scales)
     e = l2_normalize(linear(feat, p["model.head.weight"], p["model.head.bias"]))
     v = linear(e, p["model.head_v.weight"], p["model.head_v.bias"]) / temp
     n = linear(e, p["model.head_n.weight"], p["model.head_n.bias"]) / temp
-    return (v, n) if training else (v.softmax(dim=1), n.softmax(dim=1))
+    return (v, n)
 
 
 # ----------------------------------------------------------------------------------------------

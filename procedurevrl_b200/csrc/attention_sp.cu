@@ -21,7 +21,7 @@
 #include "pvrl_ptx.cuh"
 
 namespace pvrl {
-constexpr int TR_WARPS = 12, TR_ITERS = 16, TR_SLOTS = 8;
+constexpr int TR_WARPS = 20, TR_ITERS = 16, TR_SLOTS = 8;
 namespace {
 
 constexpr int SP_TILE_BYTES = 128 * 128;   // [128 rows][64 bf16], SWIZZLE_128B
@@ -356,7 +356,7 @@ int attn_sp_fwd_launch(const void* qkv, void* out, float* lse, int n_seq, int se
 
 }  // namespace pvrl
 
-// Development aid: copies the PVRL_SP_TRACE buffer ([12 warps][16 problems][8 slots] clock64 stamps of CTA 0) to `host_out`
+// Development aid: copies the PVRL_SP_TRACE buffer ([20 warps][16 problems][8 slots] clock64 stamps of CTA 0) to `host_out`
 // and clears it; returns the number of int64 values written, 0 when tracing is off.
 extern "C" int pvrl_debug_sp_trace(long long* host_out) {
   long long* buf = pvrl::sp_trace_buffer();

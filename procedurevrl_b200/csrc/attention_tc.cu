@@ -268,6 +268,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DK = 256, COL_DV = 320, COL_DQ = 384;
 
   if (warp == 8) {
+    // The whole warp runs the issue loop converged and one elected lane issues (umma_bf16_e): a single-lane branch costs
+    // ~120 cycles of register shuffling per tcgen05.mma (scripts/micro/mma_shapes.cu), and this loop issues 32 of them per
+    // tile pair, most of them N = 64 instructions that execute in 32 cycles.
+    if (tmem != 0) __trap();          // a 512-column allocation is all of TMEM: base column 0, lane 0
     if (lane == 0) {
       // tile 0 of every operand first (all the first iteration needs), tile 1 behind it
       // O rides along into the P region, which is idle until the first P tile is written: delta = dO . O is then
@@ -286,51 +290,53 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         tma_load_3d(sV + TILE_BYTES, &tmQKV, bar_load1, 2 * C + h * 64, 128, s_idx);
         tma_load_3d(sdO + TILE_BYTES, &tmDO, bar_load1, h * 64, 128, s_idx);
       }
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);
-      constexpr uint32_t idesc_dkv = make_idesc_bf16(128, 64, 1, 1);
-      auto issue_sdp = [&](int kt, int mt) {
-        const uint32_t q_t = sQ + mt * TILE_BYTES, do_t = sdO + mt * TILE_BYTES;
-        const uint32_t k_t = sK + kt * TILE_BYTES, v_t = sV + kt * TILE_BYTES;
+    }
+    __syncwarp();
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);
+    constexpr uint32_t idesc_dkv = make_idesc_bf16(128, 64, 1, 1);
+    auto issue_sdp = [&](int kt, int mt) {
+      const uint32_t q_t = sQ + mt * TILE_BYTES, do_t = sdO + mt * TILE_BYTES;
+      const uint32_t k_t = sK + kt * TILE_BYTES, v_t = sV + kt * TILE_BYTES;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem + COL_S, make_smem_desc(q_t + k * 32, 16, 1024), make_smem_desc(k_t + k * 32, 16, 1024),
-                    idesc_s, k > 0);
+      for (int k = 0; k < 4; ++k)
+        umma_bf16_e(COL_S, make_smem_desc(q_t + k * 32, 16, 1024), make_smem_desc(k_t + k * 32, 16, 1024), idesc_s, k > 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem + COL_DP, make_smem_desc(do_t + k * 32, 16, 1024), make_smem_desc(v_t + k * 32, 16, 1024),
-                    idesc_s, k > 0);
-        umma_commit(bar_sdp);
-      };
-      mbar_wait(bar_load0, 0);
+      for (int k = 0; k < 4; ++k)
+        umma_bf16_e(COL_DP, make_smem_desc(do_t + k * 32, 16, 1024), make_smem_desc(v_t + k * 32, 16, 1024), idesc_s, k > 0);
+      umma_commit_e(bar_sdp);
+    };
+    mbar_wait(bar_load0, 0);
+    __syncwarp();
+    tc_fence_after();
+    issue_sdp(0, 0);
+    for (int it = 0; it < n_iter; ++it) {
+      const int kt = it / n_tiles, mt = it % n_tiles;
+      const uint32_t q_t = sQ + mt * TILE_BYTES, do_t = sdO + mt * TILE_BYTES, k_t = sK + kt * TILE_BYTES;
+      mbar_wait(bar_pds, it & 1);      // P / dS of this iteration are in smem, S / dP columns are free again
+      __syncwarp();
       tc_fence_after();
-      issue_sdp(0, 0);
-      for (int it = 0; it < n_iter; ++it) {
-        const int kt = it / n_tiles, mt = it % n_tiles;
-        const uint32_t q_t = sQ + mt * TILE_BYTES, do_t = sdO + mt * TILE_BYTES, k_t = sK + kt * TILE_BYTES;
-        mbar_wait(bar_pds, it & 1);      // P / dS of this iteration are in smem, S / dP columns are free again
-        tc_fence_after();
-        if (it + 1 < n_iter) {
-          if (it == 0) {                 // first touch of the second tiles
-            mbar_wait(bar_load1, 0);
-            tc_fence_after();
-          }
-          issue_sdp((it + 1) / n_tiles, (it + 1) % n_tiles);
+      if (it + 1 < n_iter) {
+        if (it == 0) {                 // first touch of the second tiles
+          mbar_wait(bar_load1, 0);
+          __syncwarp();
+          tc_fence_after();
         }
+        issue_sdp((it + 1) / n_tiles, (it + 1) % n_tiles);
+      }
 #pragma unroll
-        for (int k = 0; k < 8; ++k)   // dQ_mt += dS[q, keys] K[keys, d]
-          umma_bf16(tmem + COL_DQ + mt * 64, make_smem_desc(sdS + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024),
+      for (int k = 0; k < 8; ++k)   // dQ_mt += dS[q, keys] K[keys, d]
+        umma_bf16_e(COL_DQ + mt * 64, make_smem_desc(sdS + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024),
                     make_smem_desc(k_t + k * 2048, TILE_BYTES, 1024), idesc_dq, (kt > 0 || k > 0));
 #pragma unroll
-        for (int k = 0; k < 8; ++k)   // dV_kt += P^T[keys, q] dO[q, d]
-          umma_bf16(tmem + COL_DV, make_smem_desc(sP + k * 2048, TILE_BYTES, 1024),
+      for (int k = 0; k < 8; ++k)   // dV_kt += P^T[keys, q] dO[q, d]
+        umma_bf16_e(COL_DV, make_smem_desc(sP + k * 2048, TILE_BYTES, 1024),
                     make_smem_desc(do_t + k * 2048, TILE_BYTES, 1024), idesc_dkv, (mt > 0 || k > 0));
 #pragma unroll
-        for (int k = 0; k < 8; ++k)   // dK_kt += dS^T[keys, q] Q[q, d]
-          umma_bf16(tmem + COL_DK, make_smem_desc(sdS + k * 2048, TILE_BYTES, 1024),
+      for (int k = 0; k < 8; ++k)   // dK_kt += dS^T[keys, q] Q[q, d]
+        umma_bf16_e(COL_DK, make_smem_desc(sdS + k * 2048, TILE_BYTES, 1024),
                     make_smem_desc(q_t + k * 2048, TILE_BYTES, 1024), idesc_dkv, (mt > 0 || k > 0));
-        umma_commit(bar_mma2);
-      }
+      umma_commit_e(bar_mma2);
     }
   } else {
     const int quarter = warp & 3, half = warp >> 2;
@@ -434,23 +440,29 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 
 }  // namespace
 
-// 3-D bf16 tensor map over a row-major [n_seq, seq, cols] view, box [1, box_rows, 64], 128B swizzle, zero OOB fill.
-int make_tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t cols, uint64_t seq, uint64_t n_seq, uint32_t box_rows) {
+// 3-D bf16 tensor map over a row-major [n_seq, seq, cols] view, box [1, box_rows, box_cols], zero OOB fill.
+int make_tmap_3d_bf16_box(CUtensorMap* out, const void* ptr, uint64_t cols, uint64_t seq, uint64_t n_seq, uint32_t box_cols,
+                          uint32_t box_rows) {
   EncodeTiledFn enc = get_encode_fn();
   if (enc == nullptr) return fail(-2, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || (cols * 2) % 16 != 0)
     return fail(-1, "attention operand must be 16-byte aligned with a row pitch multiple of 8 elements");
+  if (box_cols != 64 && box_cols != 32) return fail(-1, "attention tensor map: box of 32 or 64 columns expected");
   cuuint64_t dims[3] = {cols, seq, n_seq};
   cuuint64_t strides[2] = {cols * 2, seq * cols * 2};
-  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(-3, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", static_cast<int>(r));
   return 0;
 }
 
+// 3-D bf16 tensor map over a row-major [n_seq, seq, cols] view, box [1, box_rows, 64], 128B swizzle, zero OOB fill.
+int make_tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t cols, uint64_t seq, uint64_t n_seq, uint32_t box_rows) {
+  return make_tmap_3d_bf16_box(out, ptr, cols, seq, n_seq, 64, box_rows);
+}
 
 int attn_sp_fwd_launch(const void* qkv, void* out, float* lse, int n_seq, int seq, int H, float scale, cudaStream_t stream);
 
@@ -475,6 +487,7 @@ extern "C" int pvrl_attn_tc_fwd(const void* qkv, void* out, float* lse, int32_t 
                                 float scale, void* stream) {
   PVRL_CHECK_ARG(qkv && out && n_seq > 0 && H > 0, "pvrl_attn_tc_fwd: bad arguments");
   PVRL_CHECK_ARG(seq > 0 && seq <= 256, "pvrl_attn_tc_fwd: seq=%d must be in [1, 256]", seq);
+
   if (use_sp()) return attn_sp_fwd_launch(qkv, out, lse, n_seq, seq, H, scale, static_cast<cudaStream_t>(stream));
   const int npad = ((seq + 31) / 32) * 32;
   CUtensorMap tq, tkv;

@@ -122,7 +122,7 @@ def lib():
     """The loaded C-ABI library.  Fails loudly when it has not been built (python -m procedurevrl_b200.build)."""
     global _lib
     if _lib is None:
-        path = _build.LIB_PATH
+        path = os.environ.get("PVRL_LIB") or _build.LIB_PATH        # PVRL_LIB: A/B runs of an alternative build of the same ABI
         if not os.path.exists(path):
             raise RuntimeError(f"{path} is missing: run `python -m procedurevrl_b200.build` (there is no fallback path)")
         L = ctypes.CDLL(path)
@@ -320,9 +320,9 @@ def attn_tc_bwd(qkv, out, dout, lse, dqkv, n_seq, seq, H, scale):
 
 
 def debug_sp_trace():
-    """PVRL_SP_TRACE=1: clock64 stamps of CTA 0 of the last persistent spatial-attention launch, [12, 16, 8] int64."""
+    """PVRL_SP_TRACE=1: clock64 stamps of CTA 0 of the last persistent spatial-attention launch, [20, 16, 8] int64."""
     import numpy as np
-    buf = np.zeros((12, 16, 8), dtype=np.int64)
+    buf = np.zeros((20, 16, 8), dtype=np.int64)
     torch.cuda.synchronize()
     n = lib().pvrl_debug_sp_trace(buf.ctypes.data)
     return buf if n else None

@@ -30,7 +30,7 @@ else:
 tr = ops.debug_sp_trace()
 t0 = tr[tr > 0].min()
 print("rows: warp; per problem the stamps relative to the CTA's first stamp (cycles)")
-for w in range(12):
+for w in range(20):
     if not (tr[w] > 0).any():
         continue
     print(f"warp {w}")

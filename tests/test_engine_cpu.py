@@ -43,13 +43,22 @@ def pretrain_cfg(gold_dir, depth, precision):
 
 
 def check_grads(named, gold, rtol):
-    assert gold
-    for k, g in gold.items():
-        mine = named[k]
-        assert mine is not None, k
-        assert abs(mine.norm().item() - g["norm"]) <= rtol * g["norm"] + 1e-7, (k, mine.norm().item(), g["norm"])
-        torch.testing.assert_close(mine.flatten()[:64].cpu(), g["head"], rtol=rtol,
-                                   atol=rtol * g["norm"] / mine.numel() ** 0.5 + 1e-7, msg=k)
+    from golden_checks import check_grads as _cg
+    _cg(named, gold, rtol)
+
+
+def finetune_cfg(gold_dir, c, precision):
+    """configs/COIN/step_classification.yaml / configs/EK/egocentric_action_classification.yaml without MATCH_LANG_EMB."""
+    cfg = coin_cfg(gold_dir, c["depth"], c["T"], precision)
+    cfg.merge_from_list(["DEV.MATCH_LANG_EMB", False, "TRAIN.DATASET", c["dataset"], "MODEL.NUM_CLASSES", c["n_classes"]])
+    return cfg
+
+
+def finetune_state(g):
+    c = g["cfg"]
+    st = O.seeded_state(depth=c["depth"], frames=c["T"], seed=c["state_seed"])
+    st.update(g["extra_state"])
+    return st
 
 
 def test_state_dict_schema(gold_dir):
@@ -114,11 +123,16 @@ def test_droppath(shadow, gold_dir):
     assert set((ds[1]["temporal"] * keep).round().tolist()) <= {0.0, 1.0}
 
 
-def test_pretrain_step(shadow, gold_dir):
-    g = torch.load(os.path.join(gold_dir, "pretrain_d2_v2.pt"))
+@pytest.mark.parametrize("name", ["pretrain_d2_v2.pt", "pretrain_d12_ht100m.pt"])
+def test_pretrain_step(shadow, gold_dir, name):
+    """pretrain_d12_ht100m.pt: depth 12 on the shipped HowTo100M bank (TRAIN.LABEL_EMB of procedurevrl_adamw.yaml, K = 9871)."""
+    g = torch.load(os.path.join(gold_dir, name))
     c = g["cfg"]
     Bv = c["Bv"]
-    m = MODEL_REGISTRY.get("vit_base_patch16_224_develop")(pretrain_cfg(gold_dir, c["depth"], "bf16x3"))
+    cfg = pretrain_cfg(gold_dir, c["depth"], "bf16x3")
+    cfg.merge_from_list(["TRAIN.LABEL_EMB", os.path.join(gold_dir, c.get("bank", "clip_step_emb_coin.pth").replace(".pth", ".pt")),
+                         "MODEL.NUM_CLASSES", c.get("n_classes", 778)])
+    m = MODEL_REGISTRY.get("vit_base_patch16_224_develop")(cfg)
     m.load_state_dict(O.seeded_state(depth=c["depth"], frames=c["T"], seed=c["state_seed"], with_order=True), strict=True)
     gen = torch.Generator().manual_seed(c["emb_seed"])
     text_emb = 0.4 * torch.randn(Bv * 9, 512, generator=gen)
@@ -144,6 +158,36 @@ def test_pretrain_step(shadow, gold_dir):
     with torch.no_grad():
         den, mask_inds, pair, inter = m.model.order_tfm(torch.randn(Bv * 9, 512), is_pretrain=True)
     assert den.shape == (Bv, 512) and inter.shape == (4 * Bv, 512) and int(mask_inds.max()) < 9
+
+
+@pytest.mark.parametrize("name", ["finetune_headcls_d2.pt", "finetune_ek_d2.pt"])
+def test_finetune_heads(shadow, gold_dir, name):
+    """SURVEY 8a row A14 (vit.py:308-322): the path every shipped COIN / EK fine-tuning YAML takes -- frozen `head`, then
+    `head_cls`, or the EPIC-Kitchens (verb, noun) tuple, which also skips the eval-mode softmax."""
+    g = torch.load(os.path.join(gold_dir, name))
+    c = g["cfg"]
+    m = MODEL_REGISTRY.get("vit_base_patch16_224_develop")(finetune_cfg(gold_dir, c, "bf16x3"))
+    m.load_state_dict(finetune_state(g), strict=True)
+    assert sorted(k for k, p in m.named_parameters() if not p.requires_grad) == g["frozen"]
+    x = O.synthetic_clips(c["B"], 3, c["T"], 224, 224, seed=c["clip_seed"])
+    m.train()
+    out = m(x)
+    assert isinstance(out, tuple) == g["is_tuple"]
+    outs = list(out) if g["is_tuple"] else [out]
+    for o, ref in zip(outs, g["outputs"]):
+        torch.testing.assert_close(o, ref, rtol=1e-3, atol=2e-3)
+        assert torch.equal(o.argmax(1), ref.argmax(1))
+    loss = sum(torch.nn.functional.cross_entropy(o, l) for o, l in zip(outs, g["labels"]))
+    assert abs(loss.item() - g["loss"]) < 2e-3
+    loss.backward()
+    grads = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+    assert len(grads) == g["n_with_grad"]
+    check_grads(grads, g["grads"], rtol=5e-3)
+    m.eval()
+    with torch.no_grad():
+        ev = m(x)
+    for o, ref in zip(list(ev) if g["is_tuple"] else [ev], g["eval_outputs"]):
+        torch.testing.assert_close(o, ref, rtol=5e-3, atol=1e-6 if not g["is_tuple"] else 2e-3)
 
 
 def test_forecast(shadow, gold_dir):
