@@ -211,38 +211,48 @@ __device__ __forceinline__ void store_tile_coalesced(uint8_t* stage, const float
   asm volatile("bar.sync 1, 256;" ::: "memory");   // staging tile reusable
 }
 
+// development trace (see attention_sp.cu): the LAST CTA (the first problem) stamps clock64() into tr[(warp * 16 + it) * 8 + slot]
+__device__ __forceinline__ void btrace(long long* tr, int warp, int it, int slot) {
+  if (tr != nullptr && blockIdx.x == gridDim.x - 1 && (threadIdx.x & 31) == 0) tr[(warp * 16 + it) * 8 + slot] = clock64();
+}
+
 // =====================================================================================================
-// backward: one CTA per (sequence, head); Q, K, V, dO resident (two 128-row tiles each), loop over 128-key tiles
-// kt and 128-query tiles mt:   S = Q K^T, dP = dO V^T  ->  P = exp(S*scale - lse), dS = P*(dP - delta)*scale  ->
-// dQ_mt += dS K,  dV_kt += P^T dO,  dK_kt += dS^T Q.   TMEM: S 0..127 | dP 128..255 | dK 256..319 |
-// dV 320..383 | dQ_0 384..447 | dQ_1 448..511.
+// backward: ONE persistent CTA per SM streams (sequence, head) problems; Q, K, V, dO, O resident (two 128-row tiles each),
+// loop over 128-key tiles kt and 128-query tiles mt:   S = Q K^T, dP = dO V^T  ->  P = exp(S*scale - lse),
+// dS = P*(dP - delta)*scale  ->  dQ_mt += dS K,  dV_kt += P^T dO,  dK_kt += dS^T Q.
+// TMEM: S 0..127 | dP 128..255 | dK 256..319 | dV 320..383 | dQ_0 384..447 | dQ_1 448..511.
 // 288 threads: warps 0-7 = softmax-gradient threads (TMEM quarter = warp % 4, column half = warp / 4),
-// warp 8 = TMA + MMA issuer.  The S/dP MMAs of iteration it+1 are issued before the dQ/dV/dK MMAs of iteration
-// it, so the threads' TMEM loads and exp/FMA work overlap the tensor-core work of the previous tile pair.
+// warp 8 = TMA + MMA issuer (the whole warp runs the issue loop converged, one elected lane issues).  The S/dP MMAs of
+// iteration it+1 are issued before the dQ/dV/dK MMAs of iteration it, so the threads' TMEM loads and exp/FMA work overlap
+// the tensor-core work of the previous tile pair.  As soon as the last MMAs of a problem have completed, the issuer
+// refills the operand buffers with the NEXT problem (O has its own buffer; P / dS double as the output staging tiles), so
+// the ~7500 cycles of TMA latency + delta prologue that a one-problem CTA exposed (measured with PVRL_SP_TRACE) run under
+// the dK / dV / dQ stores of the previous problem.
 // =====================================================================================================
 constexpr int BWD_THREADS = 288;
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                    const __grid_constant__ CUtensorMap tmO, const float* __restrict__ lse,
-                   __nv_bfloat16* __restrict__ dqkv, int seq, int H, float scale) {
+                   __nv_bfloat16* __restrict__ dqkv, int seq, int H, float scale, int total, long long* __restrict__ tr) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw_addr);
   const uint32_t sQ = base, sK = base + 2 * TILE_BYTES, sV = base + 4 * TILE_BYTES, sdO = base + 6 * TILE_BYTES;
-  const uint32_t sP = base + 8 * TILE_BYTES, sdS = base + 10 * TILE_BYTES;
+  const uint32_t sP = base + 8 * TILE_BYTES, sdS = base + 10 * TILE_BYTES, sO = base + 12 * TILE_BYTES;
   uint8_t* pP = smem + 8 * TILE_BYTES;
   uint8_t* pdS = smem + 10 * TILE_BYTES;
-  const uint32_t bars = base + 12 * TILE_BYTES;
+  const uint8_t* pO = smem + 12 * TILE_BYTES;
+  const uint32_t bars = base + 14 * TILE_BYTES;
   const uint32_t bar_load0 = bars, bar_load1 = bars + 8, bar_sdp = bars + 16, bar_pds = bars + 24, bar_mma2 = bars + 32;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 12 * TILE_BYTES + 48);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 14 * TILE_BYTES + 48);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pair = gridDim.x - 1 - blockIdx.x;   // last sequences first (dO was just written by the proj dX GEMM)
-  const int s_idx = pair / H, h = pair % H;
   const int C = H * 64;
   const int n_tiles = (seq + 127) / 128;   // 1 or 2 (seq <= 256)
   const int n_iter = n_tiles * n_tiles;
+  const int G = gridDim.x;
+  const int n_my = (total - static_cast<int>(blockIdx.x) + G - 1) / G;
 
   if (warp == 8) {
     if (lane == 0) {
@@ -268,30 +278,29 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DK = 256, COL_DV = 320, COL_DQ = 384;
 
   if (warp == 8) {
-    // The whole warp runs the issue loop converged and one elected lane issues (umma_bf16_e): a single-lane branch costs
-    // ~120 cycles of register shuffling per tcgen05.mma (scripts/micro/mma_shapes.cu), and this loop issues 32 of them per
-    // tile pair, most of them N = 64 instructions that execute in 32 cycles.
     if (tmem != 0) __trap();          // a 512-column allocation is all of TMEM: base column 0, lane 0
-    if (lane == 0) {
-      // tile 0 of every operand first (all the first iteration needs), tile 1 behind it
-      // O rides along into the P region, which is idle until the first P tile is written: delta = dO . O is then
-      // read from shared memory instead of 32 uncoalesced 16-byte global loads per thread
-      mbar_expect_tx(bar_load0, 5 * TILE_BYTES);
-      tma_load_3d(sP, &tmO, bar_load0, h * 64, 0, s_idx);
-      tma_load_3d(sQ, &tmQKV, bar_load0, h * 64, 0, s_idx);
-      tma_load_3d(sK, &tmQKV, bar_load0, C + h * 64, 0, s_idx);
-      tma_load_3d(sV, &tmQKV, bar_load0, 2 * C + h * 64, 0, s_idx);
-      tma_load_3d(sdO, &tmDO, bar_load0, h * 64, 0, s_idx);
-      if (n_tiles > 1) {
-        mbar_expect_tx(bar_load1, 5 * TILE_BYTES);
-        tma_load_3d(sP + TILE_BYTES, &tmO, bar_load1, h * 64, 128, s_idx);
-        tma_load_3d(sQ + TILE_BYTES, &tmQKV, bar_load1, h * 64, 128, s_idx);
-        tma_load_3d(sK + TILE_BYTES, &tmQKV, bar_load1, C + h * 64, 128, s_idx);
-        tma_load_3d(sV + TILE_BYTES, &tmQKV, bar_load1, 2 * C + h * 64, 128, s_idx);
-        tma_load_3d(sdO + TILE_BYTES, &tmDO, bar_load1, h * 64, 128, s_idx);
+    // tile 0 of every operand first (all the first iteration needs), tile 1 behind it
+    auto load_problem = [&](int j) {
+      if (lane == 0) {
+        const int pair = total - 1 - (static_cast<int>(blockIdx.x) + j * G);   // last sequences first (dO was just written)
+        const int s_idx = pair / H, h = pair - s_idx * H;
+        mbar_expect_tx(bar_load0, 5 * TILE_BYTES);
+        tma_load_3d(sO, &tmO, bar_load0, h * 64, 0, s_idx);
+        tma_load_3d(sdO, &tmDO, bar_load0, h * 64, 0, s_idx);
+        tma_load_3d(sQ, &tmQKV, bar_load0, h * 64, 0, s_idx);
+        tma_load_3d(sK, &tmQKV, bar_load0, C + h * 64, 0, s_idx);
+        tma_load_3d(sV, &tmQKV, bar_load0, 2 * C + h * 64, 0, s_idx);
+        if (n_tiles > 1) {
+          mbar_expect_tx(bar_load1, 5 * TILE_BYTES);
+          tma_load_3d(sO + TILE_BYTES, &tmO, bar_load1, h * 64, 128, s_idx);
+          tma_load_3d(sdO + TILE_BYTES, &tmDO, bar_load1, h * 64, 128, s_idx);
+          tma_load_3d(sQ + TILE_BYTES, &tmQKV, bar_load1, h * 64, 128, s_idx);
+          tma_load_3d(sK + TILE_BYTES, &tmQKV, bar_load1, C + h * 64, 128, s_idx);
+          tma_load_3d(sV + TILE_BYTES, &tmQKV, bar_load1, 2 * C + h * 64, 128, s_idx);
+        }
       }
-    }
-    __syncwarp();
+      __syncwarp();
+    };
     constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
     constexpr uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);
     constexpr uint32_t idesc_dkv = make_idesc_bf16(128, 64, 1, 1);
@@ -306,131 +315,157 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         umma_bf16_e(COL_DP, make_smem_desc(do_t + k * 32, 16, 1024), make_smem_desc(v_t + k * 32, 16, 1024), idesc_s, k > 0);
       umma_commit_e(bar_sdp);
     };
-    mbar_wait(bar_load0, 0);
-    __syncwarp();
-    tc_fence_after();
-    issue_sdp(0, 0);
-    for (int it = 0; it < n_iter; ++it) {
-      const int kt = it / n_tiles, mt = it % n_tiles;
-      const uint32_t q_t = sQ + mt * TILE_BYTES, do_t = sdO + mt * TILE_BYTES, k_t = sK + kt * TILE_BYTES;
-      mbar_wait(bar_pds, it & 1);      // P / dS of this iteration are in smem, S / dP columns are free again
+    load_problem(0);
+    for (int j = 0; j < n_my; ++j) {
+      const int g0 = j * n_iter;       // running tile-pair count: phase parities of bar_sdp / bar_pds / bar_mma2
+      mbar_wait(bar_load0, j & 1);
       __syncwarp();
       tc_fence_after();
-      if (it + 1 < n_iter) {
-        if (it == 0) {                 // first touch of the second tiles
-          mbar_wait(bar_load1, 0);
-          __syncwarp();
-          tc_fence_after();
+      btrace(tr, 8, 15, 1);
+      issue_sdp(0, 0);
+      for (int it = 0; it < n_iter; ++it) {
+        const int kt = it / n_tiles, mt = it % n_tiles;
+        const uint32_t q_t = sQ + mt * TILE_BYTES, do_t = sdO + mt * TILE_BYTES, k_t = sK + kt * TILE_BYTES;
+        mbar_wait(bar_pds, (g0 + it) & 1);   // P / dS of this iteration are in smem, S / dP columns are free again
+        __syncwarp();
+        tc_fence_after();
+        btrace(tr, 8, it, 0);
+        if (it + 1 < n_iter) {
+          if (it == 0) {                 // first touch of the second tiles
+            mbar_wait(bar_load1, j & 1);
+            __syncwarp();
+            tc_fence_after();
+          }
+          issue_sdp((it + 1) / n_tiles, (it + 1) % n_tiles);
         }
-        issue_sdp((it + 1) / n_tiles, (it + 1) % n_tiles);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dQ_mt += dS[q, keys] K[keys, d]
+          umma_bf16_e(COL_DQ + mt * 64, make_smem_desc(sdS + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024),
+                      make_smem_desc(k_t + k * 2048, TILE_BYTES, 1024), idesc_dq, (kt > 0 || k > 0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dV_kt += P^T[keys, q] dO[q, d]
+          umma_bf16_e(COL_DV, make_smem_desc(sP + k * 2048, TILE_BYTES, 1024),
+                      make_smem_desc(do_t + k * 2048, TILE_BYTES, 1024), idesc_dkv, (mt > 0 || k > 0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dK_kt += dS^T[keys, q] Q[q, d]
+          umma_bf16_e(COL_DK, make_smem_desc(sdS + k * 2048, TILE_BYTES, 1024),
+                      make_smem_desc(q_t + k * 2048, TILE_BYTES, 1024), idesc_dkv, (mt > 0 || k > 0));
+        umma_commit_e(bar_mma2);
+        btrace(tr, 8, it, 1);
       }
-#pragma unroll
-      for (int k = 0; k < 8; ++k)   // dQ_mt += dS[q, keys] K[keys, d]
-        umma_bf16_e(COL_DQ + mt * 64, make_smem_desc(sdS + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024),
-                    make_smem_desc(k_t + k * 2048, TILE_BYTES, 1024), idesc_dq, (kt > 0 || k > 0));
-#pragma unroll
-      for (int k = 0; k < 8; ++k)   // dV_kt += P^T[keys, q] dO[q, d]
-        umma_bf16_e(COL_DV, make_smem_desc(sP + k * 2048, TILE_BYTES, 1024),
-                    make_smem_desc(do_t + k * 2048, TILE_BYTES, 1024), idesc_dkv, (mt > 0 || k > 0));
-#pragma unroll
-      for (int k = 0; k < 8; ++k)   // dK_kt += dS^T[keys, q] Q[q, d]
-        umma_bf16_e(COL_DK, make_smem_desc(sdS + k * 2048, TILE_BYTES, 1024),
-                    make_smem_desc(q_t + k * 2048, TILE_BYTES, 1024), idesc_dkv, (mt > 0 || k > 0));
-      umma_commit_e(bar_mma2);
+      if (j + 1 < n_my) {
+        // every MMA of this problem has read its operands: refill the buffers while the threads store dK / dV / dQ
+        mbar_wait(bar_mma2, (g0 + n_iter - 1) & 1);
+        __syncwarp();
+        load_problem(j + 1);
+      }
     }
   } else {
     const int quarter = warp & 3, half = warp >> 2;
     const int r = quarter * 32 + lane;
     const uint32_t trow = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
     const long long pitch = 3LL * C;
-    // per-row constants for both query tiles: lse and delta = dO . O (both operands from shared memory)
-    float lse_l2[2], delta[2];
     const uint8_t* pdO = smem + 6 * TILE_BYTES;
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-      const int qi = mt * 128 + r;
-      lse_l2[mt] = 0.f, delta[mt] = 0.f;
-      if (mt < n_tiles) {
-        mbar_wait(mt == 0 ? bar_load0 : bar_load1, 0);
-        float acc = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint4 a = *reinterpret_cast<const uint4*>(pP + mt * TILE_BYTES + swz(r, i));
-          const uint4 b = *reinterpret_cast<const uint4*>(pdO + mt * TILE_BYTES + swz(r, i));
-          const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
-          const float2 b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y), b2 = unpack_bf16x2(b.z), b3 = unpack_bf16x2(b.w);
-          acc += a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y + a3.x * b3.x +
-                 a3.y * b3.y;
-        }
-        delta[mt] = acc;                       // rows past seq are zero-filled -> delta = 0
-        if (qi < seq) lse_l2[mt] = lse[(long long)pair * seq + qi] * LOG2E;
-      }
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");   // every O row has been read before any P tile overwrites it
     const float sl2 = scale * LOG2E;
-    for (int it = 0; it < n_iter; ++it) {
-      const int kt = it / n_tiles, mt = it % n_tiles;
-      mbar_wait(bar_sdp, it & 1);
-      tc_fence_after();
-      // No per-element masks: padded query rows have Q = dO = 0 (TMA zero fill) and lse = delta = 0, so P = 1 but
-      // dS = 0 and P^T dO = 0; padded key columns have K = V = 0, so their dS meets K = 0 in dQ and their dK / dV rows
-      // are never stored.
-      const float l2 = lse_l2[mt], dls = delta[mt] * scale;
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c0 = half * 64 + cc * 32;
-        uint32_t rs[32], rp[32];
-        tmem_ld32(trow + COL_S + c0, rs);
-        tmem_ld32(trow + COL_DP + c0, rp);
-        tmem_ld_wait_on(rs);
-        tmem_ld_wait_on(rp);
-        float p[32], ds[32];
+    for (int j = 0; j < n_my; ++j) {
+      const int pair = total - 1 - (static_cast<int>(blockIdx.x) + j * G);
+      const int s_idx = pair / H, h = pair - s_idx * H;
+      const int g0 = j * n_iter;
+      // per-row constants for both query tiles: lse and delta = dO . O (both operands from shared memory)
+      float lse_l2[2], delta[2];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          p[j] = ex2_approx(fmaf(__uint_as_float(rs[j]), sl2, -l2));
-          ds[j] = p[j] * fmaf(__uint_as_float(rp[j]), scale, -dls);
-        }
-        if (cc == 0 && it > 0) mbar_wait(bar_mma2, (it - 1) & 1);   // previous P / dS tiles consumed by the MMAs
-        const int tile = c0 >> 6, piece0 = (c0 & 63) >> 3;
+      for (int mt = 0; mt < 2; ++mt) {
+        const int qi = mt * 128 + r;
+        lse_l2[mt] = 0.f, delta[mt] = 0.f;
+        if (mt < n_tiles) {
+          mbar_wait(mt == 0 ? bar_load0 : bar_load1, j & 1);
+          float acc = 0.f;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          st_piece(pP + tile * TILE_BYTES, r, piece0 + q, p + 8 * q);
-          st_piece(pdS + tile * TILE_BYTES, r, piece0 + q, ds + 8 * q);
+          for (int i = 0; i < 8; ++i) {
+            const uint4 a = *reinterpret_cast<const uint4*>(pO + mt * TILE_BYTES + swz(r, i));
+            const uint4 b = *reinterpret_cast<const uint4*>(pdO + mt * TILE_BYTES + swz(r, i));
+            const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+            const float2 b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y), b2 = unpack_bf16x2(b.z), b3 = unpack_bf16x2(b.w);
+            acc += a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y + a3.x * b3.x +
+                   a3.y * b3.y;
+          }
+          delta[mt] = acc;                       // rows past seq are zero-filled -> delta = 0
+          if (qi < seq) lse_l2[mt] = lse[(long long)pair * seq + qi] * LOG2E;
         }
       }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(bar_pds);
-      if (mt == n_tiles - 1) {   // key tile finished: dK_kt / dV_kt, this thread = key kt*128 + r, 32 of the 64 dims
-        mbar_wait(bar_mma2, it & 1);   // all MMAs of this iteration are done: the P / dS tiles are free as staging
+      btrace(tr, warp, 15, 1);
+      for (int it = 0; it < n_iter; ++it) {
+        const int kt = it / n_tiles, mt = it % n_tiles;
+        btrace(tr, warp, it, 0);
+        mbar_wait(bar_sdp, (g0 + it) & 1);
         tc_fence_after();
-        const int rows_valid = min(128, seq - kt * 128);
-        __nv_bfloat16* gk = dqkv + ((long long)s_idx * seq + kt * 128) * pitch + C + h * 64;
+        btrace(tr, warp, it, 1);
+        // No per-element masks: padded query rows have Q = dO = 0 (TMA zero fill) and lse = delta = 0, so P = 1 but
+        // dS = 0 and P^T dO = 0; padded key columns have K = V = 0, so their dS meets K = 0 in dQ and their dK / dV rows
+        // are never stored.
+        const float l2 = lse_l2[mt], dls = delta[mt] * scale;
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c0 = half * 64 + cc * 32;
+          uint32_t rs[32], rp[32];
+          tmem_ld32(trow + COL_S + c0, rs);
+          tmem_ld32(trow + COL_DP + c0, rp);
+          tmem_ld_wait_on(rs);
+          tmem_ld_wait_on(rp);
+          float p[32], ds[32];
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            p[jj] = ex2_approx(fmaf(__uint_as_float(rs[jj]), sl2, -l2));
+            ds[jj] = p[jj] * fmaf(__uint_as_float(rp[jj]), scale, -dls);
+          }
+          // previous P / dS tiles consumed by the MMAs (the first tile pair of the kernel has no predecessor; the first
+          // pair of a later problem waits for the last pair of the previous problem, whose stores used P as staging)
+          if (cc == 0 && g0 + it > 0) mbar_wait(bar_mma2, (g0 + it - 1) & 1);
+          const int tile = c0 >> 6, piece0 = (c0 & 63) >> 3;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            st_piece(pP + tile * TILE_BYTES, r, piece0 + q, p + 8 * q);
+            st_piece(pdS + tile * TILE_BYTES, r, piece0 + q, ds + 8 * q);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(bar_pds);
+        btrace(tr, warp, it, 2);
+        if (mt == n_tiles - 1) {   // key tile finished: dK_kt / dV_kt, this thread = key kt*128 + r, 32 of the 64 dims
+          mbar_wait(bar_mma2, (g0 + it) & 1);   // all MMAs of this iteration are done: the P / dS tiles are free as staging
+          tc_fence_after();
+          const int rows_valid = min(128, seq - kt * 128);
+          __nv_bfloat16* gk = dqkv + ((long long)s_idx * seq + kt * 128) * pitch + C + h * 64;
+          uint32_t raw[32];
+          float v[32];
+          tmem_ld32(trow + COL_DK + half * 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) v[jj] = __uint_as_float(raw[jj]);
+          store_tile_coalesced(pP, v, r, half, warp, lane, gk, pitch, rows_valid);
+          tmem_ld32(trow + COL_DV + half * 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) v[jj] = __uint_as_float(raw[jj]);
+          store_tile_coalesced(pP, v, r, half, warp, lane, gk + C, pitch, rows_valid);
+          tc_fence_before();
+          btrace(tr, warp, it, 3);
+        }
+      }
+      // dQ tiles (the last bar_mma2 wait above covers every MMA)
+      for (int mt = 0; mt < n_tiles; ++mt) {
         uint32_t raw[32];
         float v[32];
-        tmem_ld32(trow + COL_DK + half * 32, raw);
+        tmem_ld32(trow + COL_DQ + mt * 64 + half * 32, raw);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        store_tile_coalesced(pP, v, r, half, warp, lane, gk, pitch, rows_valid);
-        tmem_ld32(trow + COL_DV + half * 32, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        store_tile_coalesced(pP, v, r, half, warp, lane, gk + C, pitch, rows_valid);
-        tc_fence_before();
+        for (int jj = 0; jj < 32; ++jj) v[jj] = __uint_as_float(raw[jj]);
+        store_tile_coalesced(pP, v, r, half, warp, lane, dqkv + ((long long)s_idx * seq + mt * 128) * pitch + h * 64,
+                             pitch, min(128, seq - mt * 128));
       }
-    }
-    // dQ tiles (the last bar_mma2 wait above covers every MMA)
-    for (int mt = 0; mt < n_tiles; ++mt) {
-      uint32_t raw[32];
-      float v[32];
-      tmem_ld32(trow + COL_DQ + mt * 64 + half * 32, raw);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-      store_tile_coalesced(pP, v, r, half, warp, lane, dqkv + ((long long)s_idx * seq + mt * 128) * pitch + h * 64,
-                           pitch, min(128, seq - mt * 128));
+      tc_fence_before();     // the next problem's first MMAs overwrite the accumulators these loads just read
+      btrace(tr, warp, 15, 2);
     }
   }
   tc_fence_before();
@@ -464,6 +499,7 @@ int make_tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t cols, uint64_t
   return make_tmap_3d_bf16_box(out, ptr, cols, seq, n_seq, 64, box_rows);
 }
 
+long long* sp_trace_buffer();
 int attn_sp_fwd_launch(const void* qkv, void* out, float* lse, int n_seq, int seq, int H, float scale, cudaStream_t stream);
 
 namespace {
@@ -515,13 +551,15 @@ extern "C" int pvrl_attn_tc_bwd(const void* qkv, const void* out, const void* do
   if ((rc = make_tmap_3d(&tqkv, qkv, 3ull * H * 64, seq, n_seq, 128))) return rc;
   if ((rc = make_tmap_3d(&tdo, dout, 1ull * H * 64, seq, n_seq, 128))) return rc;
   if ((rc = make_tmap_3d(&to, out, 1ull * H * 64, seq, n_seq, 128))) return rc;
-  const size_t smem = 12 * TILE_BYTES + 64 + 1024;
+  const size_t smem = 14 * TILE_BYTES + 64 + 1024;
   static bool configured = false;
   if (!configured) {
     PVRL_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  PVRL_CUDA(launch_pdl(attn_tc_bwd_kernel, dim3(n_seq * H), dim3(BWD_THREADS), smem, static_cast<cudaStream_t>(stream), tqkv,
-                       tdo, to, lse, static_cast<__nv_bfloat16*>(dqkv), seq, H, scale));
+  const int total = n_seq * H;
+  const int grid = total < num_sms() ? total : num_sms();
+  PVRL_CUDA(launch_pdl(attn_tc_bwd_kernel, dim3(grid), dim3(BWD_THREADS), smem, static_cast<cudaStream_t>(stream), tqkv,
+                       tdo, to, lse, static_cast<__nv_bfloat16*>(dqkv), seq, H, scale, total, sp_trace_buffer()));
   return launched("attn_tc_bwd_kernel");
 }
