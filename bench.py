@@ -2,16 +2,24 @@
 """Headline benchmark: clips/sec of one TimeSformer-B 8x224 HowTo100M stage-2 pretrain step (forward + KL/MSE
 loss + backward + gradient all-reduce + AdamW) on N B200s, synthetic clips (BASELINE.json configs[1]/[2]).
 
-    python bench.py --gpus 1 --steps 10 --warmup 3
+    python bench.py --gpus 1 --steps 20 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference ...      # the reference algorithm (oracle port) on the host CPU cores
 
-Prints ONE JSON line on rank 0 (contract in the task statement): value = whole-job clips/s with inputs resident
-in HBM, e2e = same metric with the H2D copy of the frames and the D2H read of the loss inside the timed region,
-roofline = achieved TFLOP/s of the tcgen05 GEMM kernel family (CUDA events around every launch in the timed
-region) against the measured sustained bf16 peak, cpu_baseline = the oracle on the host cores."""
+Prints ONE JSON line on rank 0 (contract in the task statement):
+  value            whole-job clips/s with inputs resident in HBM (CUDA-graph replays of the whole step);
+  e2e              same metric with the H2D copy of the frames and the D2H read of the loss inside the timed region;
+  roofline         achieved TFLOP/s of the tcgen05 GEMM kernel family (CUDA events around every GEMM launch of one
+                   eager step) against the measured sustained bf16 peak;
+  parity           the BENCHED model (same weights, same precision) against the CPU oracle at depth 12 on the shipped
+                   HowTo100M step bank: max / mean |logit error|, top-1 agreement (north star: rtol 1e-3, exact top-1);
+  value_parity_mode  clips/s of the same step in the tolerance-meeting precision (bf16x3), with its own parity numbers;
+  extra            BASELINE configs 4 / 5 (32x224 and MViTv2-S 16x224 steps) and the reference algorithm run eagerly on
+                   the SAME GPU in fp32 / TF32 / bf16 autocast (the "kernel to beat", SURVEY 8d / BASELINE.md 4 B2);
+  cpu_baseline     the oracle on the host cores (N = 1 only)."""
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -28,6 +36,8 @@ import torch  # noqa: E402
 METRIC = "clips/sec TimeSformer-B 8x224 pretrain step"
 UNIT = "clips/s"
 N_STEP_PHRASES, EMB = 9871, 512           # data/clip_step_emb_ht100m_vbphrase.pth is fp32 [9871, 512]
+HT100M_BANK = os.path.join(ROOT, "tests", "golden", "clip_step_emb_ht100m_vbphrase.pt")   # the shipped bank (copy)
+MVIT_TRAIN_FLOPS_PER_CLIP = 3 * 128.45e9  # MViTv2-S 16x224 forward = 128.45 GFLOP
 
 
 def fwd_flops_per_clip(T, depth=12, D=768, N=196, h=12, d=64):
@@ -88,26 +98,18 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def pretrain_cfg(T, depth, label_path, precision):
+def pretrain_cfg(T, depth, label_path, precision, model_name="vit_base_patch16_224_develop"):
     from procedurevrl_b200.lib.config import get_cfg
     c = get_cfg()
     # configs/HowTo100M/procedurevrl_adamw.yaml, model-relevant keys
     c.merge_from_list(["DEV.ENABLE", True, "DEV.MATCH_LANG_EMB", True, "DEV.ORDER_PRETRAIN_ENABLED", True,
                        "DEV.ORDER_TFM_LAYERS", 4, "TRAIN.DATASET", "howto100m_develop", "TRAIN.BATCH_SIZE", 16,
                        "TRAIN.LABEL_EMB", label_path, "TRAIN.TOPK", 5, "DATA.NUM_FRAMES", T, "DATA.TRAIN_CROP_SIZE", 224,
-                       "DATA.TEST_CROP_SIZE", 224, "MODEL.MODEL_NAME", "vit_base_patch16_224_develop",
+                       "DATA.TEST_CROP_SIZE", 224, "MODEL.MODEL_NAME", model_name,
                        "MODEL.NUM_CLASSES", N_STEP_PHRASES, "MODEL.ARCH", "vit", "MODEL.LOSS_FUNC", "kldiv",
                        "MODEL.TEXT_MODEL", "clip_vit_b_16", "MODEL.PRETRAINED", False, "MODEL.DROP_PATH", 0.1,
                        "TIMESFORMER.DEPTH", depth, "B200.PRECISION", precision])
     return c
-
-
-def synthetic_label_bank(path):
-    """Synthetic stand-in for the shipped CLIP step-phrase bank (same shape / scale: std 0.40)."""
-    if not os.path.exists(path):
-        g = torch.Generator().manual_seed(1234)
-        torch.save(0.4 * torch.randn(N_STEP_PHRASES, EMB, generator=g), path)
-    return path
 
 
 def synthetic_batch(Bv, T, seed, as_u8=False):
@@ -120,66 +122,136 @@ def synthetic_batch(Bv, T, seed, as_u8=False):
     return frames, meta
 
 
+def release():
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
 # ------------------------------------------------------------------------------------------------ B200 arm
-def run_b200(args):
-    import torch.distributed as dist
-    from procedurevrl_b200 import functional as PF
-    from procedurevrl_b200 import ops
+class Dist:
+    def __init__(self, args):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        assert self.world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={self.world} (launch with torch.distributed.run)"
+        self.group = dist.group.WORLD if self.world > 1 else None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        if self.world == 1:
+            return list(vals)
+        t = torch.tensor(list(vals), device=self.dev, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
+
+def build_step(D, T, depth, precision, Bv, use_graph=True, input_u8=False, model_name="vit_base_patch16_224_develop",
+               mvit=False):
+    """Model + flat-gradient trainer (+ captured CUDA graph) for one workload.  Returns a dict of handles."""
     from procedurevrl_b200.lib.models import build_model
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
-
-    T, Bv = args.frames, args.videos_per_gpu
-    import tempfile
-    bank = synthetic_label_bank(os.path.join(tempfile.gettempdir(), f"pvrl_synthetic_step_bank_{os.getpid()}.pt"))
+    from procedurevrl_b200.trainer import AutogradPretrainStep, PretrainStep
     torch.manual_seed(0)
-    cfg = pretrain_cfg(T, args.depth, bank, args.precision)
-    cfg.NUM_GPUS = world if args.ddp else 1        # the flat-gradient trainer does its own all-reduce (no DDP wrapper)
+    cfg = pretrain_cfg(T, depth, HT100M_BANK, precision, model_name)
+    if mvit:
+        with open(os.path.join(ROOT, "tests", "golden", "mvit_full_geometry.json")) as f:
+            for k, v in json.load(f)["mvit"].items():
+                cfg.MVIT[k] = v
+        cfg.merge_from_list(["DATA.INPUT_CHANNEL_NUM", [3]])
+    cfg.NUM_GPUS = 1                       # the flat-gradient trainer does its own all-reduce (no DDP wrapper)
     model = build_model(cfg)
-    inner = (model.module if hasattr(model, "module") else model).model
-    with torch.no_grad():                       # a fresh reference init has all-zero temporal_fc / time_embed
-        for blk in inner.blocks:
-            torch.nn.init.trunc_normal_(blk.temporal_fc.weight, std=0.02)
-        torch.nn.init.trunc_normal_(inner.time_embed, std=0.02)
+    inner = model.model
+    if not mvit:
+        with torch.no_grad():               # a fresh reference init has all-zero temporal_fc / time_embed (SURVEY 3.3)
+            for blk in inner.blocks:
+                torch.nn.init.trunc_normal_(blk.temporal_fc.weight, std=0.02)
+            torch.nn.init.trunc_normal_(inner.time_embed, std=0.02)
     model.train()
-
-    frames_h, meta_h = synthetic_batch(Bv, T, seed=cfg.RNG_SEED + rank, as_u8=args.input_u8)
+    frames_h, meta_h = synthetic_batch(Bv, T, seed=cfg.RNG_SEED + D.rank, as_u8=input_u8)
     frames_pin = frames_h.pin_memory()
-    frames = frames_h.to(dev)
-    meta = {k: v.to(dev) for k, v in meta_h.items()}
-    clips_per_step = Bv * 9 * world
+    frames = frames_h.to(D.dev)
+    meta = {k: v.to(D.dev) for k, v in meta_h.items()}
+    Step = AutogradPretrainStep if mvit else PretrainStep
+    trainer = Step(model, cfg, lr=5e-5, weight_decay=1e-4, process_group=D.group, use_graph=use_graph)
+    if use_graph:
+        trainer.capture(frames, meta, warmup=2)
+    return dict(cfg=cfg, model=model, inner=inner, trainer=trainer, frames=frames, meta=meta, frames_pin=frames_pin,
+                mode="graph" if trainer.graph is not None else "eager")
 
-    if args.ddp:        # reference-style driver loop: DistributedDataParallel wrapper + per-op dispatch (train_net.py:146-191)
-        params = [p for p in model.parameters() if p.requires_grad]
-        opt = torch.optim.AdamW(params, lr=5e-5, weight_decay=1e-4, fused=True)     # procedurevrl_adamw.yaml SOLVER
 
-        def step(fr):
-            pred, teacher, mse = model([fr, meta])
-            loss, _, _ = PF.pretrain_loss(pred, teacher, mse, topk=cfg.TRAIN.TOPK)
-            opt.zero_grad(set_to_none=True)
-            loss.backward()
-            opt.step()
-            return loss
-        mode = "ddp-eager"
-    else:               # flat-gradient step, single NCCL all-reduce, optionally replayed from a CUDA graph
-        from procedurevrl_b200.trainer import PretrainStep
-        trainer = PretrainStep(model, cfg, lr=5e-5, weight_decay=1e-4,
-                               process_group=dist.group.WORLD if world > 1 else None, use_graph=not args.no_graph)
-        if not args.no_graph and not args.profile:
-            trainer.capture(frames, meta, warmup=2)
+def time_steps(D, step, steps):
+    """EXACTLY `steps` calls bracketed by barrier + synchronize on both sides, CUDA events, max over ranks (ms)."""
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    D.barrier()
+    t0.record()
+    for _ in range(steps):
+        out = step()
+    t1.record()
+    D.barrier()
+    return D.max_over_ranks(t0.elapsed_time(t1))[0], out
 
-        def step(fr):
-            return trainer(fr, meta)
-        mode = "graph" if trainer.graph is not None else "eager"
 
-    # CUDA events around every GEMM launch (the dominant kernel family) for the roofline
+def settle(step, seconds):
+    """Untimed steps until the chip has been under this load for `seconds` (power-capped parts settle ~100-200 MHz lower
+    than where a cold start begins: without this the first timed steps run at clocks the steady state never sees)."""
+    n, t = 0, time.perf_counter()
+    while time.perf_counter() - t < seconds:
+        step()
+        n += 1
+        if n % 8 == 0:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    return n
+
+
+def parity_check(D, handles, depth, T, n_clips=4):
+    """The benched model (same weights, same precision, DropPath off = eval) against the CPU oracle on `n_clips` synthetic
+    clips and the shipped HowTo100M bank: vit.py:299-307 logits [n, 9871]."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import timesformer_oracle as O
+    from procedurevrl_b200 import functional as PF
+    inner = handles["inner"]
+    x = O.synthetic_clips(n_clips, 3, T, 224, 224, seed=4242)
+    was_training = inner.training
+    inner.eval()
+    with torch.no_grad():
+        feat = inner.forward_features(x.to(D.dev))
+        bank = inner.check_device_norm(inner.label_emb, feat.device, norm=True)
+        inner.label_emb = bank
+        emb = PF.l2_normalize(PF.linear_small(feat, inner.head.weight, inner.head.bias))
+        logits = PF.similarity_logits(emb, bank, inner.temp).float().cpu()
+    inner.train(was_training)
+    state = {"model." + k: v.detach().float().cpu() for k, v in inner.state_dict().items()
+             if not k.startswith("text_model.")}
+    torch.set_num_threads(os.cpu_count() or 1)
+    e = torch.load(HT100M_BANK)
+    with torch.no_grad():
+        ref = O.match_lang_forward(state, x, e / e.norm(dim=1, keepdim=True), depth=depth)
+    err = (logits - ref).abs()
+    tol = 5e-3 + 1e-3 * ref.abs()                       # north star: rtol 1e-3 (atol 5e-3 as tests/test_model_gpu.py)
+    top_ref = ref.topk(2, dim=1).values
+    return {"max_abs_logit_err": round(err.max().item(), 6), "mean_abs_logit_err": round(err.mean().item(), 6),
+            "argmax_agree": int((logits.argmax(1) == ref.argmax(1)).sum().item()), "n": n_clips,
+            "frac_within_rtol1e-3_atol5e-3": round((err <= tol).float().mean().item(), 6),
+            "min_ref_top1_margin": round((top_ref[:, 0] - top_ref[:, 1]).min().item(), 4),
+            "logit_abs_max": round(ref.abs().max().item(), 3), "bank": "clip_step_emb_ht100m_vbphrase (shipped, K=9871)",
+            "oracle": "oracle/timesformer_oracle.py fp32 on the host cores, same weights / inputs"}
+
+
+def gemm_roofline(handles, ms_step, D):
+    """CUDA events around every GEMM launch of ONE eager step (events cannot time nodes inside a graph).  The eager step
+    is host-bound, so the GPU is first parked on a spin kernel long enough for the host to enqueue the whole step: events
+    and kernels are then consumed back to back and an event pair brackets the kernel's execution only."""
+    from procedurevrl_b200 import ops
     gemm_events, real_gemm = [], ops.gemm
 
     def timed_gemm(A, B, out, **kw):
@@ -189,65 +261,31 @@ def run_b200(args):
         e1.record()
         gemm_events.append((e0, e1, 2.0 * kw["M"] * kw["N"] * kw["K"]))
         return r
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step(frames)
-    barrier()
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    graphed = mode == "graph"
-    if not graphed:
-        ops.gemm = timed_gemm
+    ops.gemm = timed_gemm
     launches0 = ops.launch_count()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t0.record()
-    for _ in range(args.steps):
-        loss = step(frames)
-    t1.record()
-    barrier()
-    launches = ops.launch_count() - launches0
-    ms = t0.elapsed_time(t1)
-    clocks = sampler.stop() if rank == 0 else None
-    if graphed:
-        # graph replays launch the recorded kernels without going through the C ABI: count them from one eager step,
-        # which also carries the CUDA events around every GEMM launch (events cannot time nodes inside a graph)
-        ops.gemm = timed_gemm
-        launches0 = ops.launch_count()
-        te0, te1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        # The eager step is host-bound (one Python / ctypes call per launch): on an idle GPU the event recorded BEFORE a
-        # launch is stamped ~10 us before the kernel starts, and that host gap would be billed to the kernel.  Park the
-        # GPU on a spin kernel first, long enough for the host to enqueue the whole step, so that events and kernels are
-        # consumed back to back and an event pair brackets the kernel's execution only.
+    try:
         torch.cuda._sleep(int(0.12 * 1.9e9))
-        te0.record()
-        trainer._eager(frames, meta)
-        te1.record()
-        barrier()
-        launches = (ops.launch_count() - launches0) * args.steps
-        eager_ms = te0.elapsed_time(te1)
-    ops.gemm = real_gemm
+        handles["trainer"]._eager(handles["frames"], handles["meta"])
+        D.barrier()
+    finally:
+        ops.gemm = real_gemm
+    launches = ops.launch_count() - launches0
     gemm_ms = sum(a.elapsed_time(b) for a, b, _ in gemm_events)
     gemm_flops = sum(f for _, _, f in gemm_events)
-    n_gemm = len(gemm_events)
+    return gemm_flops, gemm_ms, len(gemm_events), launches
 
-    # end to end: pinned host frames -> device every step, loss read back (a host sync) every step.  As in the reference's
-    # loop (non_blocking .cuda() copies of a pinned DataLoader batch, train_net.py:103-107) the H2D copy of step i+1 is
-    # issued on a copy stream while step i computes; each step's input still crosses PCIe inside the timed region
-    # (exactly `steps` copies), and the step consumes it through a device-to-device copy into the graph's static input.
-    barrier()
-    n_e2e = 0 if args.profile else args.steps
+
+def e2e_loop(D, handles, step, steps):
+    """Pinned host frames -> device every step, loss read back (a host sync) every step.  As in the reference's loop
+    (non_blocking .cuda() copies of a pinned DataLoader batch, train_net.py:103-107) the H2D copy of step i+1 is issued
+    on a copy stream while step i computes; each step's input still crosses PCIe inside the timed region (exactly
+    `steps` copies) and reaches the graph's static input through a device-to-device copy."""
+    frames, frames_pin = handles["frames"], handles["frames_pin"]
     copy_stream = torch.cuda.Stream()
     stage = torch.empty_like(frames)
     staged, consumed = torch.cuda.Event(), torch.cuda.Event()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    D.barrier()
     e0.record()
 
     def issue_h2d():
@@ -257,29 +295,148 @@ def run_b200(args):
             staged.record(copy_stream)
 
     consumed.record()
-    if n_e2e:
-        issue_h2d()
-    for i in range(n_e2e):
+    issue_h2d()
+    last = float("nan")
+    for i in range(steps):
         torch.cuda.current_stream().wait_event(staged)
         frames.copy_(stage, non_blocking=True)
         consumed.record()
-        if i + 1 < n_e2e:
+        if i + 1 < steps:
             issue_h2d()
-        last = step(frames).item()
-    if args.profile:
-        last = loss.item()
+        last = step().item()
     e1.record()
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
+    D.barrier()
+    return D.max_over_ranks(e0.elapsed_time(e1))[0], last
 
-    if world > 1:
-        t = torch.tensor([ms, e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = t.tolist()
+
+def short_leg(D, T, depth, precision, Bv, steps, warmup, mvit=False, model_name="vit_base_patch16_224_develop"):
+    """A few timed steps of another workload / precision with the same trainer (extras; never the headline)."""
+    h = build_step(D, T, depth, precision, Bv, use_graph=not mvit, model_name=model_name, mvit=mvit)
+    tr, fr, meta = h["trainer"], h["frames"], h["meta"]
+
+    def step():
+        return tr(fr, meta)
+    for _ in range(warmup):
+        step()
+    ms, loss = time_steps(D, step, steps)
+    out = {"clips_per_s": round(Bv * 9 * D.world / (ms / steps / 1e3), 2), "ms_per_step": round(ms / steps, 3),
+           "steps": steps, "warmup": warmup, "clips_per_gpu": Bv * 9, "n_gpus": D.world, "dtype": precision,
+           "dispatch": h["mode"], "loss": round(float(loss), 4)}
+    return out, h
+
+
+def gpu_eager_leg(D, T, depth, Bv):
+    """BASELINE.md 4 B2 / SURVEY 8d: the reference ALGORITHM run eagerly by PyTorch on this same GPU -- the oracle's
+    functional restatement with the reference's own module kernels (F.linear / F.layer_norm / F.gelu, i.e. what nn.Linear /
+    nn.LayerNorm / nn.GELU launch) -- forward + loss + backward + fused AdamW on the same 18-clip pretrain step, in fp32,
+    with TF32 matmuls, and under bf16 autocast (with F.scaled_dot_product_attention).  `kind: port`: the reference package
+    itself cannot be imported on the GPU box."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import timesformer_oracle as O
+    F = torch.nn.functional
+    dev = D.dev
+    saved = (O.layer_norm, O.gelu_erf, O.linear, O.attention)
+    O.layer_norm = lambda x, w, b, eps=1e-6: F.layer_norm(x, (x.shape[-1],), w, b, eps)
+    O.gelu_erf = F.gelu
+    O.linear = lambda x, w, b=None: F.linear(x, w, b)
+    eager_attention = O.attention
+
+    def sdpa_attention(p, pre, x, num_heads=12):
+        B, N, C = x.shape
+        qkv = F.linear(x, p[pre + "qkv.weight"], p.get(pre + "qkv.bias")).reshape(B, N, 3, num_heads, C // num_heads)
+        q, k, v = qkv.permute(2, 0, 3, 1, 4)
+        out = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, C)
+        return F.linear(out, p[pre + "proj.weight"], p[pre + "proj.bias"])
+    res = {}
+    try:
+        p = {k: v.to(dev).requires_grad_(True) for k, v in O.seeded_state(depth=depth, frames=T, seed=0, with_order=True).items()}
+        opt = torch.optim.AdamW(list(p.values()), lr=5e-5, weight_decay=1e-4, fused=True)
+        e = torch.load(HT100M_BANK).to(dev)
+        label = e / e.norm(dim=1, keepdim=True)
+        frames_h, meta_h = synthetic_batch(Bv, T, seed=7)
+        frames = frames_h.to(dev)
+        text, vis = meta_h["clip_text_emb"].to(dev), meta_h["clip_vis_feat"].to(dev)
+        d0 = O.synthetic_draws(Bv)
+        draws = O.OrderDraws(d0.mask_inds.to(dev), d0.pad_start.to(dev), d0.noise.to(dev), d0.rand_inds.to(dev))
+
+        def run(name, tf32, autocast, steps=3):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            O.attention = sdpa_attention if autocast else eager_attention
+
+            def step():
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                    pred, teach, mse = O.pretrain_forward(p, frames, text, vis, label, draws, depth=depth)
+                loss, _, _ = O.pretrain_loss(pred.float(), teach.float(), [m.float() for m in mse])
+                opt.zero_grad(set_to_none=True)
+                loss.backward()
+                opt.step()
+                return loss
+            step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                loss = step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            res[name] = {"clips_per_s": round(Bv * 9 / (ms / 1e3), 2), "ms_per_step": round(ms, 2), "steps": steps,
+                         "loss": round(loss.item(), 4)}
+        run("fp32", False, False)
+        run("tf32", True, False)
+        run("bf16_autocast_sdpa", True, True)
+        res["what"] = ("oracle restatement of the reference, eager PyTorch on this GPU (F.linear / F.layer_norm / F.gelu; SDPA "
+                       f"in the autocast leg), {Bv * 9} clips per step, fwd + loss + bwd + fused AdamW, 1 GPU, kind: port")
+    finally:
+        O.layer_norm, O.gelu_erf, O.linear, O.attention = saved
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+    return res
+
+
+def run_b200(args):
+    from procedurevrl_b200 import ops
+    D = Dist(args)
+    T, Bv = args.frames, args.videos_per_gpu
+    world, rank = D.world, D.rank
+    clips_per_step = Bv * 9 * world
+
+    H = build_step(D, T, args.depth, args.precision, Bv, use_graph=not args.no_graph and not args.profile,
+                   input_u8=args.input_u8)
+    trainer, frames, meta = H["trainer"], H["frames"], H["meta"]
+    mode = H["mode"]
+
+    def step():
+        return trainer(frames, meta)
+
+    for _ in range(args.warmup):
+        step()
+    settle_steps = 0 if args.profile else settle(step, args.settle_s)
+    D.barrier()
+
+    sampler = ClockSampler(D.local)
+    if rank == 0:
+        sampler.start()
+    graphed = mode == "graph"
+    launches0 = ops.launch_count()
+    ms, loss = time_steps(D, step, args.steps)
+    launches_timed = ops.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    gemm_flops, gemm_ms, n_gemm, launches_eager = gemm_roofline(H, ms / args.steps, D)
+    # graph replays launch the recorded kernels without going through the C ABI: count them from the eager step
+    launches = launches_eager * args.steps if graphed else launches_timed
+
+    if args.profile:
+        e2e_ms, last = 0.0, float(loss)
+    else:
+        e2e_ms, last = e2e_loop(D, H, step, args.steps)
     ms_step = ms / args.steps
     value = clips_per_step / (ms_step / 1e3)
-    e2e = clips_per_step / (e2e_ms / args.steps / 1e3) if not args.profile else 0.0
+    e2e = clips_per_step / (e2e_ms / args.steps / 1e3) if e2e_ms > 0 else 0.0
 
+    out = None
     if rank == 0:
         peak, _, peak_src = measured_peaks()
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
@@ -296,9 +453,12 @@ def run_b200(args):
             "config": {"workload": f"TimeSformer-B {T}x224 HowTo100M stage-2 pretrain step (fwd+KL/MSE loss+bwd+"
                                    f"allreduce+AdamW), {Bv} videos x 9 clips per GPU, DROP_PATH 0.1",
                        "depth": args.depth, "clips_per_gpu": Bv * 9, "parallelism": f"dp{world}", "dispatch": mode,
+                       "label_bank": "data/clip_step_emb_ht100m_vbphrase.pth (shipped; copy under tests/golden/)",
                        "l2": "per-step working set ~14 GB >> 126 MB L2 (no flush needed)",
+                       "settle": f"{settle_steps} untimed steps ({args.settle_s} s under load) after the {args.warmup} "
+                                 "warm-up steps, before the timed region",
                        "loss": round(float(last), 4)},
-            "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": frames_pin.numel() * frames_pin.element_size(),
+            "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": H["frames_pin"].numel() * H["frames_pin"].element_size(),
                     "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -309,22 +469,97 @@ def run_b200(args):
                          "launches": n_gemm, "gemm_share_of_step": round(gemm_ms / ms_step, 4),
                          "timed_in": ("CUDA events around every GEMM launch of one eager step (GPU parked on a spin kernel while the "
                                       "host enqueues it, so no host gap is billed to a kernel) run after the graph-replayed timed "
-                                      "region (events cannot time nodes inside a graph); share = that GEMM time / ms_per_step")
-                         if graphed else "timed region",
+                                      "region (events cannot time nodes inside a graph); share = that GEMM time / ms_per_step"),
                          "step_mfu": round(step_flops / (ms_step / 1e3) / 1e12 / peak, 4)},
         }
+    if args.profile or args.no_extras:
+        if rank == 0:
+            print(json.dumps(out), flush=True)
+        del trainer, step
+        H.clear()
+        return finish(D)
+
+    # ---- parity of the benched model vs the oracle (rank 0 computes; every rank keeps its model alive meanwhile)
+    if rank == 0:
+        out["parity"] = parity_check(D, H, args.depth, T)
+    D.barrier()
+    del trainer, step
+    H.clear()
+    release()
+
+    # ---- the same step in the tolerance-meeting precision (bf16x3: every GEMM on [hi|hi|lo] x [hi|lo|hi] operands)
+    other = "bf16x3" if args.precision == "bf16" else "bf16"
+    leg, h2 = short_leg(D, T, args.depth, other, Bv, steps=max(3, min(10, args.steps)), warmup=3)
+    if rank == 0:
+        leg["parity"] = parity_check(D, h2, args.depth, T)
+        out["value_parity_mode" if other == "bf16x3" else "value_throughput_mode"] = leg
+    D.barrier()
+    h2.clear()
+    del h2
+    release()
+
+    extra = {}
+    # ---- BASELINE config 4: TimeSformer-B 32x224 (same step, T = 32)
+    if T != 32:
+        leg, h3 = short_leg(D, 32, args.depth, "bf16", Bv, steps=5, warmup=3)
+        leg["workload"] = "TimeSformer-B 32x224 pretrain step (BASELINE configs[3])"
+        leg["step_mfu"] = round(3 * fwd_flops_per_clip(32, args.depth) * Bv * 9 / (leg["ms_per_step"] / 1e3) / 1e12
+                                / measured_peaks()[0], 4)
+        extra["t32"] = leg
+        h3.clear()
+        del h3
+        release()
+    # ---- BASELINE config 5: MViTv2-S 16x224 (TRAIN.BATCH_SIZE 8 / 8 GPUs = 1 video = 9 clips per GPU)
+    try:
+        leg, h4 = short_leg(D, 16, args.depth, "bf16", 1, steps=5, warmup=3, mvit=True, model_name="MViT")
+        leg["workload"] = "MViTv2-S 16x224 pretrain step (BASELINE configs[4]): fwd + KL/MSE loss + bwd + allreduce + flat AdamW"
+        leg["achieved_tflops_per_gpu"] = round(leg["clips_per_s"] / D.world * MVIT_TRAIN_FLOPS_PER_CLIP / 1e12, 1)
+        extra["mvit"] = leg
+        h4.clear()
+        del h4
+    except Exception as e:                                    # an extra must never take the headline line down
+        extra["mvit"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    release()
+    # ---- the reference algorithm, eager PyTorch, same GPU (rank 0, N = 1 only: it is a single-GPU comparator)
+    if world == 1:
+        try:
+            extra["gpu_eager"] = gpu_eager_leg(D, T, args.depth, Bv)
+            be = extra["gpu_eager"].get("bf16_autocast_sdpa", {}).get("clips_per_s")
+            if be:
+                extra["gpu_eager"]["this_repo_bf16_over_eager_bf16_autocast"] = round(value / be, 2)
+        except Exception as e:
+            extra["gpu_eager"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        release()
+    if rank == 0:
+        out["extra"] = extra
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(T, args.depth, budget_s=25.0)
         print(json.dumps(out), flush=True)
-    if world > 1:
-        # Leave without tearing NCCL down: the step's CUDA graph holds the communicator's all-reduce, and
-        # ncclCommDestroy behind destroy_process_group() hung the 2-GPU run after the result line was printed.
+    finish(D)
+
+
+def finish(D):
+    """Orderly shutdown: the captured graphs that hold the communicator's all-reduce are destroyed first (the callers
+    have dropped their trainers; release() collects them), then the process group.  Round 1 left through os._exit(0)
+    because ncclCommDestroy hung behind a still-alive graph; a watchdog keeps that exit only as a last resort, after the
+    result line is out, should the teardown ever stall again."""
+    release()
+    if D.world > 1:
         torch.cuda.synchronize()
-        dist.barrier()
+        D.dist.barrier()
         torch.cuda.synchronize()
         sys.stdout.flush()
         sys.stderr.flush()
-        os._exit(0)
+        done = threading.Event()
+
+        def watchdog():
+            if not done.wait(30.0):
+                sys.stderr.write("bench.py: destroy_process_group() did not return within 30 s; leaving\n")
+                sys.stderr.flush()
+                os._exit(0)
+        threading.Thread(target=watchdog, daemon=True).start()
+        D.dist.destroy_process_group()
+        done.set()
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle)
@@ -337,7 +572,8 @@ def _oracle_step_fn(T, depth, n_clips, full_pretrain):
         v.requires_grad_(True)
     opt = torch.optim.AdamW(list(p.values()), lr=5e-5, weight_decay=1e-4)
     g = torch.Generator().manual_seed(0)
-    label = torch.nn.functional.normalize(0.4 * torch.randn(N_STEP_PHRASES, EMB, generator=g), dim=1)
+    e = torch.load(HT100M_BANK)
+    label = e / e.norm(dim=1, keepdim=True)
     if full_pretrain:
         Bv = n_clips // 9
         frames = O.synthetic_clips(Bv, 9, 3, T, 224, 224, seed=1)
@@ -381,33 +617,34 @@ def cpu_baseline(T, depth, budget_s):
 
 
 def run_reference(args):
+    """The reference algorithm (oracle port) on the host cores, ALWAYS the same workload: one video = 9 clips of the
+    configured step, the full pretrain_forward (encoder + head + order transformer + teacher) + KL/MSE loss + backward +
+    AdamW, so the line is comparable across runs and across N.  A 9-clip step takes tens of seconds on a 16-core host:
+    1 untimed warm-up step, then as many of the requested --steps as fit a ~200 s budget (at least 1; stated in the line)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     T, depth = args.frames, args.depth
-    cal = _oracle_step_fn(T, depth, 1, False)
+    step = _oracle_step_fn(T, depth, 9, True)
     t = time.perf_counter()
-    cal()
-    t1 = time.perf_counter() - t
-    total = args.steps + args.warmup
-    full = 9 * t1 * total <= 240.0
-    n = 9 if full else int(max(1, min(9, 240.0 / total / max(t1, 1e-3))))
-    step = _oracle_step_fn(T, depth, n, full)
-    for _ in range(args.warmup):
-        step()
+    step()                                   # warm-up (untimed)
+    t_warm = time.perf_counter() - t
+    n_steps = int(max(1, min(args.steps, (200.0 - t_warm) // max(t_warm, 1e-3))))
     t = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(n_steps):
         step()
     dt = time.perf_counter() - t
-    value = n * args.steps / dt
-    sample = (f"1 video x 9 clips full pretrain step (oracle.pretrain_forward + loss + backward + AdamW)" if full else
-              f"{n} clip(s): encoder + head + KL top-k loss + backward + AdamW (order transformer omitted to bound time)")
+    value = 9 * n_steps / dt
+    sample = (f"1 video x 9 clips, full pretrain step (oracle.pretrain_forward incl. order transformer + KL/MSE loss + backward "
+              f"+ AdamW) on the shipped HT100M bank; 1 untimed warm-up step, {n_steps} timed step(s) of the {args.steps} requested "
+              f"(bounded to ~200 s of host time); the GPU arm's step is 2 such videos per GPU")
     out = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 1),
+           "steps": args.steps, "steps_timed": n_steps, "warmup": args.warmup, "ms_per_step": round(dt / n_steps * 1e3, 1),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"TimeSformer-B {T}x224 HowTo100M stage-2 pretrain step on the host CPU", "depth": depth},
+           "config": {"workload": f"TimeSformer-B {T}x224 HowTo100M stage-2 pretrain step on the host CPU, 1 video x 9 clips",
+                      "depth": depth, "clips_per_step": 9, "same_workload_every_run": True},
            "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
@@ -416,18 +653,19 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=8)
     ap.add_argument("--depth", type=int, default=12)
     ap.add_argument("--videos-per-gpu", type=int, default=2)        # TRAIN.BATCH_SIZE 16 / NUM_GPUS 8
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
+    ap.add_argument("--settle-s", type=float, default=1.5, help="seconds of untimed steps after the warm-up (clock settle)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline measurement only (no parity / bf16x3 / t32 / mvit / eager legs)")
     ap.add_argument("--no-graph", action="store_true", help="dispatch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--input-u8", action="store_true",
                     help="feed uint8 frames (normalisation fused into the patch im2col kernel): 4x less H2D traffic in e2e")
-    ap.add_argument("--ddp", action="store_true", help="reference-style DistributedDataParallel wrapper (eager)")
     ap.add_argument("--profile", action="store_true",
                     help="short run for ncu: 1 warm-up + --steps timed steps, no e2e / cpu legs (never a bench value)")
     args = ap.parse_args()

@@ -57,9 +57,15 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   uint32_t it = 0;
+#ifdef PVRL_MBAR_NO_HINT
+  while (!mbar_try_wait(bar, parity)) {
+    if (++it > 400000000u) __trap();
+  }
+#else
   while (!mbar_try_wait_hint(bar, parity, 20000u)) {
     if (++it > 100000u) __trap();
   }
+#endif
 }
 
 // programmatic dependent launch (see launch_pdl in pvrl_host.h); both are no-ops for a kernel launched without the attribute

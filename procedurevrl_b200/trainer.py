@@ -154,3 +154,38 @@ class PretrainStep:
         self.opt.sync_hyper()                       # learning-rate changes reach the graph through a device scalar
         self.graph.replay()
         return self.static_loss
+
+
+class AutogradPretrainStep:
+    """The same pre-training step for a model whose encoder is scheduled through autograd (the MViTv2 mirror, BASELINE
+    config 5): forward + KL/MSE loss + `loss.backward()` into the flat gradient buffer of a `FlatOptimizer`, ONE NCCL
+    all-reduce of that buffer, one `pvrl_adam_flat` pass that also clears the gradients.  Eager dispatch (no CUDA graph):
+    the MViT schedule still contains torch glue between the C-ABI ops."""
+
+    def __init__(self, model, cfg, lr=5e-5, weight_decay=1e-4, process_group=None, use_graph=False, optimizer=None):
+        self.model, self.cfg, self.topk = model, cfg, cfg.TRAIN.TOPK
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        params = [p for p in model.parameters() if p.requires_grad]
+        self.opt = optimizer if optimizer is not None else \
+            FlatOptimizer([{"params": params, "lr_mult": 1.0}], "adamw", lr=lr, weight_decay=weight_decay)
+        self.flat_grad = self.opt.flat_grad
+        self.graph = None
+
+    def capture(self, frames, meta, warmup=2):
+        for _ in range(warmup):
+            self(frames, meta)
+        return self
+
+    def _eager(self, frames, meta, update=True):
+        pred, teacher, mse = self.model([frames, meta])
+        loss, _, _ = PF.pretrain_loss(pred, teacher, mse, topk=self.topk)
+        loss.backward()
+        if update:
+            if self.world > 1:
+                torch.distributed.all_reduce(self.flat_grad, op=torch.distributed.ReduceOp.AVG, group=self.pg)
+            self.opt.step(zero_grad=True)
+        return loss.detach()
+
+    def __call__(self, frames=None, meta=None):
+        return self._eager(frames, meta)
