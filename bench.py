@@ -223,6 +223,7 @@ def parity_check(D, handles, depth, T, n_clips=4):
     x = O.synthetic_clips(n_clips, 3, T, 224, 224, seed=4242)
     was_training = inner.training
     inner.eval()
+    inner.engine().invalidate_weights()          # operand copies re-cast from the current masters
     with torch.no_grad():
         feat = inner.forward_features(x.to(D.dev))
         bank = inner.check_device_norm(inner.label_emb, feat.device, norm=True)

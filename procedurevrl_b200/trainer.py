@@ -120,6 +120,9 @@ class PretrainStep:
         assert not (self.accum_steps > 1 and self._ar_ranges is not None), \
             "bucketed exchange during the backward and gradient accumulation are not combined"
         self.static = (frames, meta)
+        # The warm-up steps are real optimizer steps on the capture batch: snapshot parameters, optimizer state and step
+        # counter and put them back afterwards, so that capturing is invisible to the training trajectory.
+        snap = (self.opt.flat_param.clone(), [b.clone() for b in self.opt._state], self.opt._step_dev.clone())
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -127,6 +130,14 @@ class PretrainStep:
                 self._eager(frames, meta)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        with torch.no_grad():
+            self.opt.flat_param.copy_(snap[0])
+            for b, b0 in zip(self.opt._state, snap[1]):
+                b.copy_(b0)
+            self.opt._step_dev.copy_(snap[2])
+            self.flat_grad.zero_()
+        del snap
+        self.inner.engine().invalidate_weights()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.static_loss = self._eager(frames, meta)
@@ -153,6 +164,10 @@ class PretrainStep:
             return self.static_micro_loss
         self.opt.sync_hyper()                       # learning-rate changes reach the graph through a device scalar
         self.graph.replay()
+        # The replay cast the bf16 operand copies at its start and updated the fp32 masters at its end, through raw
+        # pointers: no `_version` changed.  Mark the copies stale so that an eager forward after training (evaluation,
+        # validation) re-casts them instead of running on weights one optimizer step old.
+        self.inner.engine().invalidate_weights()
         return self.static_loss
 
 

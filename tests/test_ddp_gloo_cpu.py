@@ -112,3 +112,58 @@ def test_allreduce_bucket_ranges_tile_the_flat_buffer():
         assert cover[0][0] == 0 and cover[-1][1] == total
         assert all(cover[k][1] == cover[k + 1][0] for k in range(len(cover) - 1)), (bpb, cover)
         assert all(lo > 0 for lo in ranges)          # block 0's bucket always rides with the final exchange
+
+
+def _linear_worker(rank, world, port, bank, out_path):
+    """the reference's fine-tuning flow under DDP -- build_model wraps FIRST, construct_optimizer freezes the
+    encoder for TRAIN.LINEAR afterwards (optimizer.py:25-31), and with MODEL.NUM_SEG > 0 `order_tfm.pad_embedding` never
+    receives a gradient.  With find_unused_parameters=False the second iteration dies in 'Expected to have finished
+    reduction'; with the reference's True (build.py:49-53) it trains."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(2)
+    _setup()
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from procedurevrl_b200.lib.models import MODEL_REGISTRY
+    from procedurevrl_b200.lib.models.build import wrap_data_parallel
+    from procedurevrl_b200.lib.models.optimizer import parameter_groups
+    cfg = _small_cfg(bank)
+    cfg.merge_from_list(["DEV.MATCH_LANG_EMB", False, "MODEL.NUM_SEG", 2, "TRAIN.LINEAR", True, "MODEL.DROP_E", 0.0])
+    torch.manual_seed(3)
+    m = MODEL_REGISTRY.get("vit_base_patch16_224_develop")(cfg).train()
+    ddp = wrap_data_parallel(m, cfg)
+    groups = parameter_groups(ddp, cfg)                      # freezes the encoder AFTER the wrap, as train_net.py does
+    opt = torch.optim.SGD([{"params": [p for p in g["params"] if p.requires_grad], "lr": 0.1} for g in groups])
+    g = torch.Generator().manual_seed(5 + rank)
+    losses = []
+    for it in range(3):
+        x = torch.randn(2, 3, 2 * 2, 32, 32, generator=g)    # [B, 3, NUM_SEG * T, H, W]
+        y = torch.tensor([1 + it, 50 + rank])
+        loss = torch.nn.functional.cross_entropy(ddp(x), y)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    if rank == 0:
+        torch.save({"losses": losses, "pad_grad_none": m.model.order_tfm.pad_embedding.weight.grad is None,
+                    "enc_frozen": not m.model.blocks[0].attn.qkv.weight.requires_grad,
+                    "head_cls": m.model.head_cls.weight.detach().clone()}, out_path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_linear_finetune_with_forecast_under_ddp(gold_dir, tmp_path):
+    bank = os.path.join(gold_dir, "clip_step_emb_coin.pt")
+    out_path = str(tmp_path / "linear.pt")
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_linear_worker, args=(2, port, bank, out_path), nprocs=2, join=True)
+    r = torch.load(out_path)
+    assert len(r["losses"]) == 3 and all(l == l for l in r["losses"])
+    assert r["enc_frozen"]
+    try:
+        pass
+    finally:
+        import importlib
+        from procedurevrl_b200 import ops
+        from procedurevrl_b200.lib.models.vit import VisionTransformer
+        importlib.reload(ops)
+        VisionTransformer._require_cuda = True

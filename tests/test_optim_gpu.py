@@ -211,3 +211,51 @@ def test_flat_optimizer_foreign_and_missing_grads(ops):
     ws[0].data = ws[0].data.clone()
     with pytest.raises(RuntimeError, match="no longer lives in the flat buffer"):
         o.step()
+
+
+def test_flat_optimizer_loads_reference_grouping_with_frozen_parameters(ops):
+    """the reference's groups always contain frozen parameters (`head.*` in every fine-tuning config, the CLIP
+    tower in pre-training) and torch.optim keeps them in `param_groups` and in its integer numbering.  A state_dict saved by
+    torch.optim.AdamW on that grouping must load into FlatOptimizer (and back), and both must continue identically."""
+    from procedurevrl_b200.lib.models.optimizer import FlatOptimizer
+    torch.manual_seed(1)
+    shapes = [(6, 5), (5,), (4, 6), (4,), (7,)]                 # encoder w, b | frozen head w, b | head_cls b
+    frozen = {2, 3}
+
+    def make():
+        g = torch.Generator().manual_seed(2)
+        ps = [torch.nn.Parameter(torch.randn(*s, generator=g).cuda()) for s in shapes]
+        for i in frozen:
+            ps[i].requires_grad_(False)
+        return ps
+    tw, fw = make(), make()
+    groups = lambda ps: [{"params": ps[:2], "weight_decay": 0.0, "lr_mult": 0.1},     # noqa: E731
+                         {"params": ps[2:], "weight_decay": 0.05, "lr_mult": 1.0}]
+    t = torch.optim.AdamW(groups(tw), lr=1e-2)
+    gg = torch.Generator().manual_seed(3)
+    for _ in range(2):
+        for p in tw:
+            p.grad = torch.randn(p.shape, generator=gg).cuda() if p.requires_grad else None
+        t.step()
+    sd = t.state_dict()
+    assert [len(g["params"]) for g in sd["param_groups"]] == [2, 3] and sorted(sd["state"]) == [0, 1, 4]
+    with torch.no_grad():
+        for a, b in zip(fw, tw):
+            a.copy_(b)
+    o = FlatOptimizer(groups(fw), "adamw", lr=1e-2)
+    assert [len(g["params"]) for g in o.param_groups] == [2, 3] and o._ids == [0, 1, 4]
+    o.load_state_dict(sd)                                        # raised "parameter groups don't match" before
+    back = o.state_dict()
+    assert sorted(back["state"]) == [0, 1, 4] and [g["params"] for g in back["param_groups"]] == [[0, 1], [2, 3, 4]]
+    t2 = torch.optim.AdamW(groups(tw), lr=1e-2)
+    t2.load_state_dict(back)                                     # and a checkpoint saved here loads on the reference side
+    for _ in range(2):
+        gs = [torch.randn(p.shape, generator=gg).cuda() for p in tw]
+        for p, q, g in zip(tw, fw, gs):
+            if p.requires_grad:
+                p.grad = g.clone()
+                q.grad.copy_(g)
+        t.step()
+        o.step()
+    for p, q in zip(tw, fw):
+        torch.testing.assert_close(q.detach(), p.detach(), rtol=2e-6, atol=1e-7)
