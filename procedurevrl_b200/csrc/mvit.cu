@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(256) pool3d_bwd_w_kernel(const T* __restrict__
   for (int e = threadIdx.x; e < g.C * 27; e += blockDim.x) atomicAdd(dw + e, sacc[e]);
 }
 
-// Variant (opt-in, PVRL_POOL_DW = 2; not yet run on a GPU): the same sums with ONE channel per lane -- blockIdx.y picks the
+// Variant (default since its hardware run; PVRL_POOL_DW = 1 selects the kernel above): the same sums with ONE channel per lane -- blockIdx.y picks the
 // 32-channel group -- so a lane carries 27 accumulators instead of 108 (254 registers, one block per SM, 310 us per launch
 // in the first launch list): ~5x the resident warps for the same loads.
 template <typename T>
@@ -951,8 +951,10 @@ extern "C" int pvrl_pool3d_bwd(const void* dout, const void* in, const float* w,
   const long long orows = (long long)g.B * g.heads * g.OT * g.OH * g.OW;
   int gw = grid_for(orows, 8 * 16);
   if (gw > num_sms() * 2) gw = num_sms() * 2;
+  // one channel per lane (27 accumulators, 64 registers, 32 resident warps per SM): 1.49 ms vs 2.67 ms for both weight-
+  // gradient launches of block 0 (9 clips) on B200 -- the default; PVRL_POOL_DW=1 selects the 254-register kernel
   const char* variant = getenv("PVRL_POOL_DW");
-  if (variant != nullptr && atoi(variant) == 2) {
+  if (variant == nullptr || atoi(variant) == 2) {
     const dim3 grid2(grid_for(orows, 8 * 8), (g.C + 31) / 32);
     if (dtype == PVRL_F32)
       pool3d_bwd_w_cg_kernel<float><<<grid2, 256, 0, STREAM>>>((const float*)dout, (const float*)in, dw, g);
@@ -1058,11 +1060,12 @@ extern "C" int pvrl_pooled_attn_bwd(const void* q, const void* k, const void* v,
   int rc = check_attn(a, "pvrl_pooled_attn_bwd");
   if (rc) return rc;
   PVRL_CHECK_ARG(q && k && v && bq && dout && lse && dq && dk && dv && dbq && delta, "pvrl_pooled_attn_bwd: null buffer");
-  // PVRL_MVIT_ATTN_MMA_BWD = 1: the mma.sync dQ and dK/dV passes (mvit_attn_mma.cu) for bf16 problems.  Opt-in: their
-  // fragment algebra is checked by the CPU emulation (tests/test_mvit_mma_emulation.py), they have not run on a GPU yet.
+  // The mma.sync dQ and dK/dV passes (mvit_attn_mma.cu) for bf16 problems: default since their first hardware run was green
+  // (round-1 driver run, XPASS; tests/test_zz_mvit_mma_bwd_gpu.py now holds them strictly).  PVRL_MVIT_ATTN_MMA_BWD=0
+  // selects the CUDA-core passes.
   if (dtype == PVRL_BF16) {
     const char* e = getenv("PVRL_MVIT_ATTN_MMA_BWD");
-    if (e != nullptr && atoi(e) != 0)
+    if (e == nullptr || atoi(e) != 0)
       return pooled_attn_bwd_mma_launch(q, k, v, bq, dout, lse, dq, dk, dv, dbq, delta, a->B, a->heads, a->Nq, a->Nk, a->Kt,
                                         a->Kh, a->Kw, a->scale, a->residual_pooling, STREAM);
   }

@@ -92,7 +92,6 @@ print("RESULT_ATTN " + json.dumps(out), flush=True)
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="mma.sync backward kernels: CPU-emulated only, first hardware run")
 def test_mma_backward_first_hardware_run():
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
