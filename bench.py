@@ -407,6 +407,12 @@ def run_b200(args):
                    input_u8=args.input_u8)
     trainer, frames, meta = H["trainer"], H["frames"], H["meta"]
     mode = H["mode"]
+    exchange_desc = {"none": "single GPU: no exchange",
+                     "ce": f"flat fp32 gradient buffer in symmetric memory, buckets of {trainer.blocks_per_bucket} encoder blocks "
+                           "averaged over NVLink by the copy engines under the backward (grad_exchange.py)",
+                     "nccl": "NCCL all-reduce of the flat fp32 gradient buffer"
+                             + (f" in buckets of {trainer.blocks_per_bucket} blocks" if trainer.blocks_per_bucket else " after the backward")
+                     }[trainer.exchange_kind]
 
     def step():
         return trainer(frames, meta)
@@ -454,6 +460,7 @@ def run_b200(args):
             "config": {"workload": f"TimeSformer-B {T}x224 HowTo100M stage-2 pretrain step (fwd+KL/MSE loss+bwd+"
                                    f"allreduce+AdamW), {Bv} videos x 9 clips per GPU, DROP_PATH 0.1",
                        "depth": args.depth, "clips_per_gpu": Bv * 9, "parallelism": f"dp{world}", "dispatch": mode,
+                       "grad_exchange": exchange_desc,
                        "label_bank": "data/clip_step_emb_ht100m_vbphrase.pth (shipped; copy under tests/golden/)",
                        "l2": "per-step working set ~14 GB >> 126 MB L2 (no flush needed)",
                        "settle": f"{settle_steps} untimed steps ({args.settle_s} s under load) after the {args.warmup} "

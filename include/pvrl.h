@@ -261,6 +261,11 @@ int pvrl_optim_tick(float* step_dev, void* stream);
 int pvrl_adam_flat(float* p, float* g, float* m, float* v, int64_t n, const float* lr_dev, const float* step_dev,
                    float lr_mult, double beta1, double beta2, float eps, float weight_decay, int32_t decoupled,
                    float grad_scale, int32_t zero_grad, void* stream);
+/* dst[i] = (dst[i] + sum_{s < n_src} src[s * stride + i]) * scale, i < n (fp32; vectorised when dst, src are 16-byte aligned):
+ * the local reduction of the copy-engine gradient exchange -- the peers' copies of this rank's chunk of the flat
+ * gradient buffer (pulled over NVLink by the DMA engines, no SMs) are summed into it and averaged.  Replaces the
+ * reduction half of the NCCL all-reduce behind DistributedDataParallel, reference lib/models/build.py:49-53. */
+int pvrl_reduce_chunks(float* dst, const float* src, int32_t n_src, int64_t stride, int64_t n, float scale, void* stream);
 /* torch.optim.SGD semantics: g += wd*p; buf = g on step 1 else momentum*buf + (1-dampening)*g;
  * update = g + momentum*buf (nesterov) or buf; p -= lr*update.  momentum == 0 ignores buf's contents. */
 int pvrl_sgd_flat(float* p, float* g, float* buf, int64_t n, const float* lr_dev, const float* step_dev, float lr_mult,

@@ -186,6 +186,46 @@ extern "C" int pvrl_adam_flat(float* p, float* g, float* m, float* v, int64_t n,
   return launched("pvrl_adam_flat");
 }
 
+// dst[i] = (dst[i] + sum_s src[s * stride + i]) * scale: the local reduction of the copy-engine gradient exchange
+// (procedurevrl_b200/grad_exchange.py): `n_src` peers' copies of this rank's gradient chunk sit in a staging buffer.
+template <bool VEC>
+__global__ void __launch_bounds__(THREADS)
+reduce_chunks_kernel(float* __restrict__ dst, const float* __restrict__ src, int n_src, long long stride, long long n,
+                     float scale) {
+  const long long nvec = VEC ? n >> 2 : 0;
+  const long long step = static_cast<long long>(gridDim.x) * THREADS;
+  for (long long i = static_cast<long long>(blockIdx.x) * THREADS + threadIdx.x; i < nvec; i += step) {
+    float4 a = reinterpret_cast<const float4*>(dst)[i];
+    for (int s = 0; s < n_src; ++s) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(src + s * stride) + i);
+      a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+    }
+    a.x *= scale, a.y *= scale, a.z *= scale, a.w *= scale;
+    reinterpret_cast<float4*>(dst)[i] = a;
+  }
+  // tail of the vector path (block 0), or everything when the range does not start on a 16-byte boundary (grid-strided)
+  const long long i0 = VEC ? (nvec << 2) + threadIdx.x : static_cast<long long>(blockIdx.x) * THREADS + threadIdx.x;
+  if (VEC && blockIdx.x != 0) return;
+  for (long long i = i0; i < n; i += VEC ? THREADS : step) {
+    float a = dst[i];
+    for (int s = 0; s < n_src; ++s) a += src[s * stride + i];
+    dst[i] = a * scale;
+  }
+}
+
+extern "C" int pvrl_reduce_chunks(float* dst, const float* src, int32_t n_src, int64_t stride, int64_t n, float scale,
+                                  void* stream) {
+  PVRL_CHECK_ARG(dst && (src || n_src == 0) && n > 0 && n_src >= 0, "pvrl_reduce_chunks: bad arguments");
+  PVRL_CHECK_ARG((reinterpret_cast<uintptr_t>(dst) & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0,
+                 "pvrl_reduce_chunks: dst, src must be fp32-aligned");
+  const bool vec = (reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && stride % 4 == 0;
+  if (vec)
+    reduce_chunks_kernel<true><<<stream_grid(n), THREADS, 0, STREAM>>>(dst, src, n_src, stride, n, scale);
+  else   // a range that does not start on a 16-byte boundary (never the case for the model's parameter layout)
+    reduce_chunks_kernel<false><<<stream_grid(n), THREADS, 0, STREAM>>>(dst, src, n_src, stride, n, scale);
+  return launched("pvrl_reduce_chunks");
+}
+
 extern "C" int pvrl_sgd_flat(float* p, float* g, float* buf, int64_t n, const float* lr_dev, const float* step_dev,
                              float lr_mult, float momentum, float dampening, int32_t nesterov, float weight_decay,
                              float grad_scale, int32_t zero_grad, void* stream) {

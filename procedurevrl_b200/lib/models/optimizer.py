@@ -138,7 +138,10 @@ class FlatOptimizer:
     torch would skip it; setting `p.grad = None` before `step()` restores torch's behaviour for that step."""
 
     def __init__(self, groups, method="adamw", lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, momentum=0.0,
-                 dampening=0.0, nesterov=False):
+                 dampening=0.0, nesterov=False, grad_buffer=None):
+        """grad_buffer: optional pre-allocated fp32 CUDA tensor (at least as many elements as there are trainable
+        parameters) to use as the flat gradient buffer -- e.g. symmetric memory for the peer-to-peer gradient exchange
+        (procedurevrl_b200/grad_exchange.py)."""
         assert method in ("sgd", "adam", "adamw")
         if isinstance(groups, (list, tuple)) and groups and not isinstance(groups[0], dict):
             groups = [{"params": list(groups)}]
@@ -174,7 +177,12 @@ class FlatOptimizer:
         if total == 0:
             raise ValueError("optimizer got an empty parameter list")
         self.flat_param = torch.empty(total, device=dev, dtype=torch.float32)
-        self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        if grad_buffer is not None:
+            assert grad_buffer.is_cuda and grad_buffer.dtype == torch.float32 and grad_buffer.numel() >= total
+            self.flat_grad = grad_buffer[:total]
+            self.flat_grad.zero_()
+        else:
+            self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
         n_state = 1 if method == "sgd" else 2
         self._state = [torch.zeros(total, device=dev, dtype=torch.float32) for _ in range(n_state)]
         with torch.no_grad():

@@ -72,6 +72,7 @@ _SIGS = {
     "pvrl_attn_tc_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float,
                          _c_void_p],
     "pvrl_debug_sp_trace": [_c_void_p],
+    "pvrl_reduce_chunks": [_c_void_p, _c_void_p, _c_int, ctypes.c_int64, ctypes.c_int64, _c_float, _c_void_p],
     "pvrl_linear_small_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
     "pvrl_linear_small_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int,
                               _c_void_p],
@@ -317,6 +318,13 @@ def attn_tc_bwd(qkv, out, dout, lse, dqkv, n_seq, seq, H, scale):
     _check(lib().pvrl_attn_tc_bwd(_p(qkv), _p(out), _p(dout), _p(lse), _p(dqkv), n_seq, seq, H, scale, _stream()),
            "pvrl_attn_tc_bwd")
     return dqkv
+
+
+def reduce_chunks(dst, src, n_src, stride, n, scale):
+    """dst[:n] = (dst[:n] + sum_s src[s * stride : s * stride + n]) * scale (fp32): local half of the copy-engine gradient exchange."""
+    assert dst.dtype == torch.float32 and (n_src == 0 or src.dtype == torch.float32)
+    _check(lib().pvrl_reduce_chunks(_p(dst), _p(src) if n_src else None, n_src, stride, n, scale, _stream()), "pvrl_reduce_chunks")
+    return dst
 
 
 def debug_sp_trace():

@@ -48,11 +48,25 @@ class PretrainStep:
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         self.params = [p for p in model.parameters() if p.requires_grad]
+        # Data-parallel gradient exchange (the only collective).  Default ("ce"): the flat gradient buffer lives
+        # in symmetric memory and buckets of encoder blocks are averaged over NVLink by the copy engines while the backward
+        # continues (grad_exchange.PeerGradExchange: DMA pulls + one small reduction kernel + device barriers, no SMs taken
+        # from the persistent GEMMs).  PVRL_GRAD_EXCHANGE=nccl: NCCL all-reduce(s) of the same buffer.
+        self.exchange = None
+        self.exchange_kind = os.environ.get("PVRL_GRAD_EXCHANGE", "ce") if self.world > 1 else "none"
+        grad_buffer = None
+        if self.exchange_kind == "ce" and optimizer is None:
+            from .grad_exchange import PeerGradExchange
+            self.exchange = PeerGradExchange(sum(p.numel() for p in self.params), process_group)
+            grad_buffer = self.exchange.buffer
+        elif self.exchange_kind == "ce":
+            self.exchange_kind = "nccl"           # a caller-built optimizer owns its gradient buffer
         # Parameters, gradients and AdamW state in flat fp32 buffers (`p.data` / `p.grad` become views): the engine's
         # dW / db kernels accumulate straight into flat_grad, the update + the clearing of the gradients for the next
         # backward is one `pvrl_adam_flat` launch (procedurevrl_adamw.yaml SOLVER: one group, uniform decay).
         self.opt = optimizer if optimizer is not None else \
-            FlatOptimizer([{"params": self.params, "lr_mult": 1.0}], "adamw", lr=lr, weight_decay=weight_decay)
+            FlatOptimizer([{"params": self.params, "lr_mult": 1.0}], "adamw", lr=lr, weight_decay=weight_decay,
+                          grad_buffer=grad_buffer)
         self.flat_grad = self.opt.flat_grad
         # Gradient accumulation (train_net.py:99-100,182-192: GLOBAL_BATCH_SIZE // (NUM_SHARDS * TRAIN.BATCH_SIZE) micro-steps,
         # `p.grad /= num_iters`, then step + zero_grad): the dW kernels accumulate across micro-steps by construction,
@@ -68,12 +82,14 @@ class PretrainStep:
         assert all(g is not None for g in eng.grad_sink.values()), "every encoder parameter must be trainable here"
         if getattr(self.inner, "order_tfm", None) is not None:
             self.inner.order_tfm.grad_into_params = True      # same for the order transformer's 48 block parameters
-        # Data-parallel gradient exchange (the only collective).  Default: ONE NCCL all-reduce of the flat buffer
-        # after the backward (measured on 2 B200s: 34.4 ms/step).  PVRL_AR_BLOCKS_PER_BUCKET = n > 0 instead exchanges
-        # buckets of n encoder blocks on a side stream as soon as the backward has finished them (part of the captured
-        # CUDA graph); on 2 GPUs that measured 34.9 ms -- the NCCL kernels take SMs away from the persistent GEMMs for
-        # longer than the ~0.3 ms the exposed exchange costs -- so it stays opt-in until it is measured on 8 GPUs.
-        self.blocks_per_bucket = int(os.environ.get("PVRL_AR_BLOCKS_PER_BUCKET", "0"))
+        # Buckets: PVRL_AR_BLOCKS_PER_BUCKET = n exchanges n encoder blocks at a time as soon as the backward has finished
+        # them (part of the captured CUDA graph).  Copy-engine exchange: default n = 2 (the transfers cost the GEMMs nothing).
+        # NCCL: default 0 = ONE all-reduce after the backward -- overlapped NCCL buckets were measured on 2 and on 8 B200s
+        # (profiles/README.md): its kernels take SMs from the persistent GEMMs for as long as the exposed exchange costs.
+        default_bpb = "2" if self.exchange is not None else "0"
+        self.blocks_per_bucket = int(os.environ.get("PVRL_AR_BLOCKS_PER_BUCKET", default_bpb))
+        if self.accum_steps > 1:
+            self.blocks_per_bucket = 0            # under accumulation the replicas exchange once, before the update
         self._ar_stream = torch.cuda.Stream() if self.world > 1 else None
         self._ar_ranges = None
         if self.world > 1 and self.blocks_per_bucket > 0:
@@ -82,11 +98,27 @@ class PretrainStep:
             self._ar_ranges, self._ar_front_end, self._ar_tail_start = bucket_ranges(names, eng.depth,
                                                                                      self.blocks_per_bucket)
             eng.on_block_bwd_done = self._bucket_ready
+            if self.exchange is not None:
+                self.exchange.reserve(max([b - a for a, b in self._ar_ranges.values()] +
+                                          [self._ar_front_end, self.flat_grad.numel() - self._ar_tail_start]))
+        elif self.exchange is not None:
+            self.exchange.reserve(self.flat_grad.numel())
+        self._depth = eng.depth
         self.use_graph = use_graph
         self.graph = None
         self.static = None
 
     def _bucket_ready(self, i):
+        """Encoder block i's parameter gradients are complete (called by the engine's backward, top block first)."""
+        if self.exchange is not None:
+            # final norm / head / order transformer: complete once the encoder backward has begun (their kernels were
+            # enqueued before it) -- exchanged first, under the whole encoder backward
+            if i == self._depth - 1:
+                self.exchange.all_reduce_mean(self._ar_tail_start, self.flat_grad.numel())
+            rng = self._ar_ranges.get(i)
+            if rng is not None:
+                self.exchange.all_reduce_mean(rng[0], rng[1])
+            return
         rng = self._ar_ranges.get(i)
         if rng is None:
             return
@@ -103,7 +135,13 @@ class PretrainStep:
         loss.backward()
         if not update:
             return loss.detach()
-        if self.world > 1:
+        if self.exchange is not None:
+            if self._ar_ranges is None:
+                self.exchange.all_reduce_mean(0, self.flat_grad.numel())
+            else:      # embeddings + lowest blocks: the only exposed part of the exchange
+                self.exchange.all_reduce_mean(0, self._ar_front_end)
+            self.exchange.join()
+        elif self.world > 1:
             if self._ar_ranges is None:
                 torch.distributed.all_reduce(self.flat_grad, op=torch.distributed.ReduceOp.AVG, group=self.pg)
             else:      # what the block buckets did not cover: [embeddings | first blocks) and (norm | head | order transformer]

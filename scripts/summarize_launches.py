@@ -17,7 +17,7 @@ def kname(full):
     return base
 
 
-def main(path, skip=0):
+def main(path, skip=0, steps=1, exclude=None):
     with open(path) as f:
         lines = [l for l in f if not l.startswith("==")]
     agg = collections.defaultdict(lambda: [0, 0.0])
@@ -32,14 +32,19 @@ def main(path, skip=0):
         unit = row.get("Metric Unit", "us")
         v = v / 1e3 if unit == "ns" else v * 1e3 if unit == "ms" else v
         n = kname(row["Kernel Name"])
+        if exclude and re.search(exclude, n):
+            continue
         agg[n][0] += 1
         agg[n][1] += v
         total += v
-    print(f"# {path}: {sum(a[0] for a in agg.values())} launches, {total / 1e3:.2f} ms summed device time")
-    print(f"{'share':>7} {'ms':>9} {'n':>6} {'avg_us':>9}  kernel")
-    for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:40]:
-        print(f"{t / total * 100:6.2f}% {t / 1e3:9.3f} {n:6d} {t / n:9.1f}  {k}")
+    print(f"# {path}: {sum(a[0] for a in agg.values())} launches, {total / 1e3:.2f} ms summed device time"
+          + (f" over {steps} identical steps -> {total / 1e3 / steps:.2f} ms and {sum(a[0] for a in agg.values()) // steps} launches per step"
+             if steps > 1 else ""))
+    print(f"{'share':>7} {'ms/step':>9} {'n/step':>6} {'avg_us':>9}  kernel")
+    for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:45]:
+        print(f"{t / total * 100:6.2f}% {t / 1e3 / steps:9.3f} {n / steps:6.0f} {t / n:9.1f}  {k}")
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 0, int(sys.argv[3]) if len(sys.argv) > 3 else 1,
+         sys.argv[4] if len(sys.argv) > 4 else None)

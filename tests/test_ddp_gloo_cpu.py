@@ -167,3 +167,15 @@ def test_linear_finetune_with_forecast_under_ddp(gold_dir, tmp_path):
         from procedurevrl_b200.lib.models.vit import VisionTransformer
         importlib.reload(ops)
         VisionTransformer._require_cuda = True
+
+
+def test_peer_exchange_chunks_tile_every_range():
+    """Host logic of the copy-engine gradient exchange (grad_exchange.PeerGradExchange.chunk_bounds): the per-rank chunks of
+    any range are disjoint, ordered, 16-byte granular and cover it exactly, for every world size."""
+    from procedurevrl_b200.grad_exchange import PeerGradExchange
+    for world in (2, 3, 4, 8):
+        for a, b in ((0, 134_600_000), (12345, 13_000_001), (5, 8), (0, 1), (7, 7 + 4 * world), (100, 100)):
+            ch = PeerGradExchange.chunk_bounds(a, b, world)
+            assert len(ch) == world and ch[0][0] == a and ch[-1][1] == b
+            assert all(ch[i][1] == ch[i + 1][0] for i in range(world - 1))
+            assert all(0 <= e - s for s, e in ch) and all((s - a) % 4 == 0 for s, e in ch if e > s)
