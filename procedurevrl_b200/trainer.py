@@ -83,10 +83,10 @@ class PretrainStep:
         if getattr(self.inner, "order_tfm", None) is not None:
             self.inner.order_tfm.grad_into_params = True      # same for the order transformer's 48 block parameters
         # Buckets: PVRL_AR_BLOCKS_PER_BUCKET = n exchanges n encoder blocks at a time as soon as the backward has finished
-        # them (part of the captured CUDA graph).  Copy-engine exchange: default n = 2 (the transfers cost the GEMMs nothing).
+        # them (part of the captured CUDA graph).  Copy-engine exchange: default n = 1 (the transfers cost the GEMMs nothing; only block 0 + the embeddings stay exposed).
         # NCCL: default 0 = ONE all-reduce after the backward -- overlapped NCCL buckets were measured on 2 and on 8 B200s
         # (profiles/README.md): its kernels take SMs from the persistent GEMMs for as long as the exposed exchange costs.
-        default_bpb = "2" if self.exchange is not None else "0"
+        default_bpb = "1" if self.exchange is not None else "0"
         self.blocks_per_bucket = int(os.environ.get("PVRL_AR_BLOCKS_PER_BUCKET", default_bpb))
         if self.accum_steps > 1:
             self.blocks_per_bucket = 0            # under accumulation the replicas exchange once, before the update
