@@ -210,9 +210,15 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int m_blk, n_blk, ks;
       decode_tile<TN>(tile, m_tiles, n_tiles, p.k_splits, m_blk, n_blk, ks);
       const int m_base = m_blk * TILE2_M + static_cast<int>(rank) * 128 + quarter * 32;
+      int nm = -1, nn = 0;
+      if (EPI == PVRL_EPI_RESID && tile + n_clusters < total_tiles) {
+        int m2, n2, k2;
+        decode_tile<TN>(tile + n_clusters, m_tiles, n_tiles, p.k_splits, m2, n2, k2);
+        nm = m2 * TILE2_M + static_cast<int>(rank) * 128 + quarter * 32, nn = n2 * TILE2_N + half * HALF_COLS;
+      }
       epilogue_tile<EPI, OutT, HALF_COLS>(
           p, stg, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * TILE2_N + half * HALF_COLS, m_base,
-          n_blk * TILE2_N + half * HALF_COLS, tfull_bar(acc), acc_phase, lane);
+          n_blk * TILE2_N + half * HALF_COLS, tfull_bar(acc), acc_phase, lane, nm, nn);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {

@@ -29,6 +29,7 @@ struct GemmArgs {
   const float* add_pos;
   const float* add_time;
   float* colsum;
+  int prefetch_side;   // RESID: bulk-prefetch the next tile's residual rows into L2 while this tile's epilogue runs
   Geom g;
 };
 
@@ -138,6 +139,11 @@ inline GemmArgs make_gemm_args(const pvrl_gemm_t* d) {
   a.map = d->map, a.aux = d->aux, a.ld_aux = d->ld_aux, a.resid = d->resid;
   a.add_pos = d->add_pos, a.add_time = d->add_time;
   a.colsum = d->colsum;
+  static const int prefetch_side = [] {
+    const char* e = getenv("PVRL_GEMM_PREFETCH");   // 0: no L2 prefetch of the residual (A/B switch)
+    return e ? atoi(e) : 1;
+  }();
+  a.prefetch_side = prefetch_side;
   a.g = Geom(d->g.T > 0 ? d->g.T : 1, d->g.HW > 0 ? d->g.HW : 1);
   return a;
 }
@@ -165,9 +171,30 @@ __device__ __forceinline__ void decode_tile(int tile, int m_tiles, int n_tiles, 
 // The whole epilogue of one accumulator tile for one epilogue warp: rows [m_base, m_base + 32) (the warp's TMEM lane
 // quarter), columns [n_base, n_base + HALF_COLS) of the output (TMEM columns tmem_cols ...).  Waits for the
 // accumulator on `tfull` AFTER the first side-operand loads are in flight.
+// RESID: the fp32 residual is the one operand that comes from HBM with nothing to overlap it but a two-chunk register
+// pipeline (ncu: long-scoreboard bound, 39 % DRAM); [next_m_base, +32) x [next_n_base, +HALF_COLS) names this warp's share
+// of the CTA's NEXT tile (next_m_base < 0: none) and each lane asks the L2 for one row of it a whole tile ahead.
 template <int EPI, typename OutT, int HALF_COLS>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stg, uint32_t tmem_cols, int m_base, int n_base,
-                                              uint32_t tfull, uint32_t tfull_phase, int lane) {
+                                              uint32_t tfull, uint32_t tfull_phase, int lane, int next_m_base = -1,
+                                              int next_n_base = 0) {
+  if (EPI == PVRL_EPI_RESID && p.prefetch_side && p.resid != nullptr && next_m_base >= 0 && next_n_base < p.N) {
+    const int m = next_m_base + lane;
+    if (m < p.M) {
+      const long long orow = map_row(p.map, m, p.g);
+      if (orow >= 0) {
+        const float* src = p.resid + orow * p.ldo + next_n_base;
+        const int cols = min(HALF_COLS, p.N - next_n_base);
+        if (p.prefetch_side == 1) {
+          bulk_prefetch_l2(src, 4u * static_cast<uint32_t>(cols));
+        } else {
+#pragma unroll
+          for (int c = 0; c < HALF_COLS; c += 32)
+            if (c < cols) prefetch_l2_line(src + c);
+        }
+      }
+    }
+  }
   const int rsub = lane >> 3, piece = lane & 7;   // transposed ownership: row 4*i + rsub, columns [4*piece, +4)
   // per-row context, computed by the lane that owns the row in TMEM order ...
   RowCtx own;

@@ -161,9 +161,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int m_blk, n_blk, ks;
       decode_tile<TN>(tile, m_tiles, n_tiles, p.k_splits, m_blk, n_blk, ks);
       const int m_base = m_blk * BM + quarter * 32;
+      int nm = -1, nn = 0;
+      if (EPI == PVRL_EPI_RESID && tile + static_cast<int>(gridDim.x) < total_tiles) {
+        int m2, n2, k2;
+        decode_tile<TN>(tile + gridDim.x, m_tiles, n_tiles, p.k_splits, m2, n2, k2);
+        nm = m2 * BM + quarter * 32, nn = n2 * BN + half * HALF_COLS;
+      }
       epilogue_tile<EPI, OutT, HALF_COLS>(p, stg, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN +
                                                        half * HALF_COLS,
-                                          m_base, n_blk * BN + half * HALF_COLS, tfull_bar(acc), acc_phase, lane);
+                                          m_base, n_blk * BN + half * HALF_COLS, tfull_bar(acc), acc_phase, lane, nm, nn);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));

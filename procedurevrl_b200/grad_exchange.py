@@ -96,5 +96,12 @@ class PeerGradExchange:
                 self.comm.wait_stream(s)
             self.hdl.barrier(channel=2)                       # nobody still reads my chunk: it may be consumed / cleared
 
+    def mark(self):
+        """Event after everything enqueued on the exchange stream so far (capturable): lets the caller consume the ranges
+        already exchanged while a later `all_reduce_mean` is still running."""
+        ev = torch.cuda.Event()
+        ev.record(self.comm)
+        return ev
+
     def join(self, stream=None):
         (stream if stream is not None else torch.cuda.current_stream(self.device)).wait_stream(self.comm)

@@ -243,9 +243,12 @@ class FlatOptimizer:
                 self.flat_grad[a:b].view_as(p).copy_(p.grad)
         return missing
 
-    def step(self, closure=None, zero_grad=False):
+    def step(self, closure=None, zero_grad=False, split=None):
         """One update of every group.  `zero_grad=True` also clears the gradients in the same pass (the
-        optimizer.step(); optimizer.zero_grad() pair of train_net.py:191-192 as one read-modify-write)."""
+        optimizer.step(); optimizer.zero_grad() pair of train_net.py:191-192 as one read-modify-write).
+        `split=(offset, hook)`: update the elements at or above `offset` of the flat buffers first, call `hook()`, then
+        update the rest -- the caller's hook waits for a gradient exchange that still covers [0, offset), which thereby
+        runs under the bulk of the update (trainer.PretrainStep).  Same result as the unsplit call, element for element."""
         loss = closure() if closure is not None else None
         capturing = torch.cuda.is_current_stream_capturing()
         missing = []
@@ -254,9 +257,20 @@ class FlatOptimizer:
             missing = self._adopt_foreign_grads()
             torch.autograd.graph.increment_version(self._params)   # the kernels write through raw pointers
         ops.optim_tick(self._step_dev)
-        for gi, (g, (a, b)) in enumerate(zip(self.param_groups, self._ranges)):
-            for s, e in _runs(a, b, [self.offsets[i] for i in missing]):
+        runs = [(gi, g, s, e) for gi, (g, (a, b)) in enumerate(zip(self.param_groups, self._ranges))
+                for s, e in _runs(a, b, [self.offsets[i] for i in missing])]
+        if split is None:
+            for gi, g, s, e in runs:
                 self._launch(gi, g, s, e, zero_grad)
+            return loss
+        off, hook = split
+        for gi, g, s, e in runs:
+            if e > off:
+                self._launch(gi, g, max(s, off), e, zero_grad)
+        hook()
+        for gi, g, s, e in runs:
+            if s < off:
+                self._launch(gi, g, s, min(e, off), zero_grad)
         return loss
 
     def _launch(self, gi, g, s, e, zero_grad):

@@ -103,6 +103,7 @@ class PretrainStep:
                                           [self._ar_front_end, self.flat_grad.numel() - self._ar_tail_start]))
         elif self.exchange is not None:
             self.exchange.reserve(self.flat_grad.numel())
+        self._split_update = os.environ.get("PVRL_SPLIT_UPDATE", "1") != "0"
         self._depth = eng.depth
         self.use_graph = use_graph
         self.graph = None
@@ -138,9 +139,18 @@ class PretrainStep:
         if self.exchange is not None:
             if self._ar_ranges is None:
                 self.exchange.all_reduce_mean(0, self.flat_grad.numel())
-            else:      # embeddings + lowest blocks: the only exposed part of the exchange
+                self.exchange.join()
+            elif self._split_update:
+                # embeddings + lowest blocks are the only part of the exchange the backward cannot cover: it runs under
+                # the optimizer pass over everything above them, whose buckets are complete at `done`
+                done = self.exchange.mark()
                 self.exchange.all_reduce_mean(0, self._ar_front_end)
-            self.exchange.join()
+                torch.cuda.current_stream().wait_event(done)
+                self.opt.step(zero_grad=True, split=(self._ar_front_end, self.exchange.join))
+                return loss.detach()
+            else:
+                self.exchange.all_reduce_mean(0, self._ar_front_end)
+                self.exchange.join()
         elif self.world > 1:
             if self._ar_ranges is None:
                 torch.distributed.all_reduce(self.flat_grad, op=torch.distributed.ReduceOp.AVG, group=self.pg)

@@ -174,6 +174,32 @@ def test_flat_optimizer_in_cuda_graph(ops):
         torch.testing.assert_close(w.detach(), tw.detach(), rtol=2e-6, atol=1e-7)
 
 
+@pytest.mark.parametrize("off", [0, 12, 231, 236, 10 ** 6])
+def test_flat_optimizer_split_step_equals_unsplit(ops, off):
+    """step(split=(offset, hook)) -- the update above `offset` first, the hook (the trainer's wait for the last gradient
+    exchange), then the rest -- equals the plain step bit for bit, across group boundaries and unaligned offsets."""
+    from procedurevrl_b200.lib.models.optimizer import FlatOptimizer
+    torch.manual_seed(1)
+    shapes = [(33, 7), (5,), (4, 4, 4)]
+
+    def make():
+        torch.manual_seed(2)
+        ws = [torch.nn.Parameter(torch.randn(*sh, device="cuda")) for sh in shapes]
+        o = FlatOptimizer([{"params": ws[:2], "weight_decay": 0.1}, {"params": ws[2:], "weight_decay": 0.0}], "adamw", lr=1e-2)
+        return ws, o
+    (wa, oa), (wb, ob) = make(), make()
+    calls = []
+    for it in range(3):
+        for a, b in zip(wa, wb):
+            g = torch.randn_like(a)
+            a.grad.copy_(g), b.grad.copy_(g)
+        oa.step(zero_grad=True)
+        ob.step(zero_grad=True, split=(off, lambda: calls.append(it)))
+        assert torch.equal(oa.flat_param, ob.flat_param) and torch.equal(oa._state[0], ob._state[0])
+        assert torch.equal(oa._state[1], ob._state[1]) and (ob.flat_grad == 0).all()
+    assert calls == [0, 1, 2]
+
+
 def test_flat_optimizer_foreign_and_missing_grads(ops):
     """`.grad`s that a wrapper re-pointed (DistributedDataParallel's bucket views) are adopted by step() and cleared by
     zero_grad(); a `.grad` set to None skips that parameter for the step (torch semantics) and gets its view back; a
