@@ -210,15 +210,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int m_blk, n_blk, ks;
       decode_tile<TN>(tile, m_tiles, n_tiles, p.k_splits, m_blk, n_blk, ks);
       const int m_base = m_blk * TILE2_M + static_cast<int>(rank) * 128 + quarter * 32;
-      int nm = -1, nn = 0;
-      if (EPI == PVRL_EPI_RESID && tile + n_clusters < total_tiles) {
-        int m2, n2, k2;
-        decode_tile<TN>(tile + n_clusters, m_tiles, n_tiles, p.k_splits, m2, n2, k2);
-        nm = m2 * TILE2_M + static_cast<int>(rank) * 128 + quarter * 32, nn = n2 * TILE2_N + half * HALF_COLS;
-      }
       epilogue_tile<EPI, OutT, HALF_COLS>(
           p, stg, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * TILE2_N + half * HALF_COLS, m_base,
-          n_blk * TILE2_N + half * HALF_COLS, tfull_bar(acc), acc_phase, lane, nm, nn);
+          n_blk * TILE2_N + half * HALF_COLS, tfull_bar(acc), acc_phase, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -333,7 +327,8 @@ int gemm2_dispatch(const pvrl_gemm_t* d, cudaStream_t stream) {
       return f32 ? launch_gemm2<PVRL_EPI_DGELU, float, false>(ta, tb, a, stream)
                  : launch_gemm2<PVRL_EPI_DGELU, __nv_bfloat16, false>(ta, tb, a, stream);
     case PVRL_EPI_RESID:
-      return launch_gemm2<PVRL_EPI_RESID, float, false>(ta, tb, a, stream);
+      return d->add_pos != nullptr ? launch_gemm2<EPI_RESID_POS, float, false>(ta, tb, a, stream)
+                                   : launch_gemm2<PVRL_EPI_RESID, float, false>(ta, tb, a, stream);
     default:
       return d->trans ? launch_gemm2<PVRL_EPI_ATOMIC, float, true>(ta, tb, a, stream)
                       : launch_gemm2<PVRL_EPI_ATOMIC, float, false>(ta, tb, a, stream);

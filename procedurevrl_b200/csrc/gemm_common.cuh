@@ -13,6 +13,15 @@ constexpr int CHUNK_BYTES = 64 * BK * 2;      // one 64-wide MN chunk of a TN ti
 constexpr int NUM_THREADS = 384;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int EPI_STAGE_BYTES = 32 * 128;     // per epilogue warp: 32 rows x 32 fp32 columns, 16 B pieces xor-swizzled
+// Internal epilogue id (not part of the ABI): PVRL_EPI_RESID with the pos / time embedding adds of the patch-embedding
+// GEMM.  A separate instantiation keeps their index arithmetic (two integer divisions per row) out of the code of the 48
+// residual GEMMs per step that never take it: that epilogue is latency- and instruction-cache-bound, not a place for
+// dead branches (ncu: 4000 SASS instructions per tile and warp before the split, 11 % no-instruction stalls).
+constexpr int EPI_RESID_POS = 100;
+struct FalseT { static constexpr bool value = false; };
+struct TrueT { static constexpr bool value = true; };
+template <int EPI>
+__host__ __device__ constexpr bool is_resid() { return EPI == PVRL_EPI_RESID || EPI == EPI_RESID_POS; }
 struct GemmArgs {
   int M, N, K;
   int k_splits, kb_per_split;
@@ -29,7 +38,6 @@ struct GemmArgs {
   const float* add_pos;
   const float* add_time;
   float* colsum;
-  int prefetch_side;   // RESID: bulk-prefetch the next tile's residual rows into L2 while this tile's epilogue runs
   Geom g;
 };
 
@@ -83,8 +91,8 @@ struct RowCtx {
 // of these loads overlaps the MMAs / the previous chunk instead of sitting between the TMEM read and the store.
 template <int EPI, typename OutT>
 __device__ __forceinline__ float4 load_side(const GemmArgs& p, int m, const RowCtx& rc, int coff) {
-  if (EPI == PVRL_EPI_RESID) {
-    if (p.resid != nullptr && m < p.M && rc.orow >= 0) return ld_vec4<float>(reinterpret_cast<const float*>(rc.sd) + coff);
+  if (is_resid<EPI>()) {   // rc.sd == nullptr: no residual operand, or a cls row of a spatial sequence (parked, not added)
+    if (rc.sd != nullptr && m < p.M) return ld_vec4<float>(reinterpret_cast<const float*>(rc.sd) + coff);
   } else if (EPI == PVRL_EPI_DGELU) {
     if (m < p.M) return ld_vec4<OutT>(reinterpret_cast<const OutT*>(rc.sd) + coff);
   }
@@ -111,13 +119,11 @@ __device__ __forceinline__ void epilogue_vec4(const GemmArgs& p, int m, const Ro
   }
   if (EPI == PVRL_EPI_DGELU) v.x *= side.x, v.y *= side.y, v.z *= side.z, v.w *= side.w;
   mul4(v, rc.rs);
-  if (EPI == PVRL_EPI_RESID) {
-    if (rc.orow < 0) {  // cls row of a spatial sequence: park it for the mean over frames (vit.py:147-149); o1 -> out2
-      st_vec4<float>(reinterpret_cast<float*>(rc.o1) + coff, v);
-      return;
-    }
+  if (is_resid<EPI>()) {
+    // cls rows of a spatial sequence are parked in the side buffer for the mean over frames (vit.py:147-149): their o1
+    // points into out2 and their `side` is zero (load_side), so they take the same straight-line code as every other row
     add4(v, side);
-    if (p.add_pos != nullptr) {  // MAP_PATCH (patch embedding only): + pos_embed[1+n] + time_embed[t]  (vit.py:373-404)
+    if (EPI == EPI_RESID_POS) {  // MAP_PATCH (patch embedding only): + pos_embed[1+n] + time_embed[t]  (vit.py:373-404)
       const int bt = m / p.g.HW;
       add4(v, ld_vec4<float>(p.add_pos + (long long)(1 + m - bt * p.g.HW) * p.N + n));
       add4(v, ld_vec4<float>(p.add_time + (long long)(bt % p.g.T) * p.N + n));
@@ -139,11 +145,6 @@ inline GemmArgs make_gemm_args(const pvrl_gemm_t* d) {
   a.map = d->map, a.aux = d->aux, a.ld_aux = d->ld_aux, a.resid = d->resid;
   a.add_pos = d->add_pos, a.add_time = d->add_time;
   a.colsum = d->colsum;
-  static const int prefetch_side = [] {
-    const char* e = getenv("PVRL_GEMM_PREFETCH");   // 0: no L2 prefetch of the residual (A/B switch)
-    return e ? atoi(e) : 1;
-  }();
-  a.prefetch_side = prefetch_side;
   a.g = Geom(d->g.T > 0 ? d->g.T : 1, d->g.HW > 0 ? d->g.HW : 1);
   return a;
 }
@@ -171,30 +172,9 @@ __device__ __forceinline__ void decode_tile(int tile, int m_tiles, int n_tiles, 
 // The whole epilogue of one accumulator tile for one epilogue warp: rows [m_base, m_base + 32) (the warp's TMEM lane
 // quarter), columns [n_base, n_base + HALF_COLS) of the output (TMEM columns tmem_cols ...).  Waits for the
 // accumulator on `tfull` AFTER the first side-operand loads are in flight.
-// RESID: the fp32 residual is the one operand that comes from HBM with nothing to overlap it but a two-chunk register
-// pipeline (ncu: long-scoreboard bound, 39 % DRAM); [next_m_base, +32) x [next_n_base, +HALF_COLS) names this warp's share
-// of the CTA's NEXT tile (next_m_base < 0: none) and each lane asks the L2 for one row of it a whole tile ahead.
 template <int EPI, typename OutT, int HALF_COLS>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stg, uint32_t tmem_cols, int m_base, int n_base,
-                                              uint32_t tfull, uint32_t tfull_phase, int lane, int next_m_base = -1,
-                                              int next_n_base = 0) {
-  if (EPI == PVRL_EPI_RESID && p.prefetch_side && p.resid != nullptr && next_m_base >= 0 && next_n_base < p.N) {
-    const int m = next_m_base + lane;
-    if (m < p.M) {
-      const long long orow = map_row(p.map, m, p.g);
-      if (orow >= 0) {
-        const float* src = p.resid + orow * p.ldo + next_n_base;
-        const int cols = min(HALF_COLS, p.N - next_n_base);
-        if (p.prefetch_side == 1) {
-          bulk_prefetch_l2(src, 4u * static_cast<uint32_t>(cols));
-        } else {
-#pragma unroll
-          for (int c = 0; c < HALF_COLS; c += 32)
-            if (c < cols) prefetch_l2_line(src + c);
-        }
-      }
-    }
-  }
+                                              uint32_t tfull, uint32_t tfull_phase, int lane) {
   const int rsub = lane >> 3, piece = lane & 7;   // transposed ownership: row 4*i + rsub, columns [4*piece, +4)
   // per-row context, computed by the lane that owns the row in TMEM order ...
   RowCtx own;
@@ -211,18 +191,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stg, u
     const int src = 4 * i + rsub;
     rc[i].orow = __shfl_sync(0xffffffffu, own.orow, src);
     rc[i].rs = (EPI != PVRL_EPI_ATOMIC && EPI != PVRL_EPI_GELU) ? __shfl_sync(0xffffffffu, own.rs, src) : 1.0f;
-    constexpr int OSZ = (EPI == PVRL_EPI_RESID || EPI == PVRL_EPI_ATOMIC) ? 4 : static_cast<int>(sizeof(OutT));
+    constexpr int OSZ = (is_resid<EPI>() || EPI == PVRL_EPI_ATOMIC) ? 4 : static_cast<int>(sizeof(OutT));
     const long long oel = (long long)(rc[i].orow >= 0 ? rc[i].orow : -rc[i].orow - 1) * p.ldo + n_base + piece * 4;
-    rc[i].o1 = reinterpret_cast<uint8_t*>((EPI == PVRL_EPI_RESID && rc[i].orow < 0) ? p.out2 : p.out) + oel * OSZ;
+    rc[i].o1 = reinterpret_cast<uint8_t*>((is_resid<EPI>() && rc[i].orow < 0) ? p.out2 : p.out) + oel * OSZ;
     rc[i].o2 = EPI == PVRL_EPI_GELU ? reinterpret_cast<uint8_t*>(p.out2) + oel * OSZ : nullptr;
     rc[i].sd = nullptr;
-    if (EPI == PVRL_EPI_RESID) rc[i].sd = reinterpret_cast<const uint8_t*>(p.resid) + oel * 4;
+    if (is_resid<EPI>() && p.resid != nullptr && rc[i].orow >= 0)
+      rc[i].sd = reinterpret_cast<const uint8_t*>(p.resid) + oel * 4;
     if (EPI == PVRL_EPI_DGELU)
       rc[i].sd = reinterpret_cast<const uint8_t*>(p.aux) +
                  ((long long)(m_base + src) * p.ld_aux + n_base + piece * 4) * static_cast<int>(sizeof(OutT));
   }
   constexpr int NCH = HALF_COLS / 32;
-  constexpr bool HAS_SIDE = EPI == PVRL_EPI_RESID || EPI == PVRL_EPI_DGELU;
+  constexpr bool HAS_SIDE = is_resid<EPI>() || EPI == PVRL_EPI_DGELU;
   constexpr bool HAS_COLSUM = EPI == PVRL_EPI_STORE || EPI == PVRL_EPI_DGELU;
   // bf16 gelu' (DGELU): the side operand of the WHOLE tile is fetched packed (2 registers per piece) before the
   // accumulator is waited for -- one chunk of lookahead (~0.4 us of work) does not cover an HBM round trip.
@@ -270,23 +251,29 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stg, u
       float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (EPI != PVRL_EPI_ATOMIC && p.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
       float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+      // All but the last row block of the matrix are full: their eight rows run as straight-line code (no per-row
+      // bounds branch), so the shared-memory reads of all rows are in flight before the first row's arithmetic.
+      auto rows = [&](auto checked) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = 4 * i + rsub;
-        float4 v = *reinterpret_cast<const float4*>(stg + row * 128 + ((piece ^ (row & 7)) << 4));
-        const int m = m_base + row;
-        if (m < p.M) {
-          float4 sd = bias4;
-          if (SIDE_PACKED) {
-            const float2 lo = unpack_bf16x2(sidep[c][i].x), hi = unpack_bf16x2(sidep[c][i].y);
-            sd = make_float4(lo.x, lo.y, hi.x, hi.y);
-          } else if (HAS_SIDE) {
-            sd = side[c & 1][i];
+        for (int i = 0; i < 8; ++i) {
+          const int row = 4 * i + rsub;
+          float4 v = *reinterpret_cast<const float4*>(stg + row * 128 + ((piece ^ (row & 7)) << 4));
+          const int m = m_base + row;
+          if (!decltype(checked)::value || m < p.M) {
+            float4 sd = bias4;
+            if (SIDE_PACKED) {
+              const float2 lo = unpack_bf16x2(sidep[c][i].x), hi = unpack_bf16x2(sidep[c][i].y);
+              sd = make_float4(lo.x, lo.y, hi.x, hi.y);
+            } else if (HAS_SIDE) {
+              sd = side[c & 1][i];
+            }
+            epilogue_vec4<EPI, OutT>(p, m, rc[i], c * 32, n, v, bias4, sd);
+            if (HAS_COLSUM) add4(csum, v);
           }
-          epilogue_vec4<EPI, OutT>(p, m, rc[i], c * 32, n, v, bias4, sd);
-          if (HAS_COLSUM) add4(csum, v);
         }
-      }
+      };
+      if (m_base + 32 <= p.M) rows(FalseT{});
+      else rows(TrueT{});
       if (HAS_COLSUM && p.colsum != nullptr) {   // fused bias gradient: column sums of what was just stored
 #pragma unroll
         for (int o = 8; o <= 16; o <<= 1) {

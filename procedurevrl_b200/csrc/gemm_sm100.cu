@@ -161,15 +161,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int m_blk, n_blk, ks;
       decode_tile<TN>(tile, m_tiles, n_tiles, p.k_splits, m_blk, n_blk, ks);
       const int m_base = m_blk * BM + quarter * 32;
-      int nm = -1, nn = 0;
-      if (EPI == PVRL_EPI_RESID && tile + static_cast<int>(gridDim.x) < total_tiles) {
-        int m2, n2, k2;
-        decode_tile<TN>(tile + gridDim.x, m_tiles, n_tiles, p.k_splits, m2, n2, k2);
-        nm = m2 * BM + quarter * 32, nn = n2 * BN + half * HALF_COLS;
-      }
       epilogue_tile<EPI, OutT, HALF_COLS>(p, stg, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN +
                                                        half * HALF_COLS,
-                                          m_base, n_blk * BN + half * HALF_COLS, tfull_bar(acc), acc_phase, lane, nm, nn);
+                                          m_base, n_blk * BN + half * HALF_COLS, tfull_bar(acc), acc_phase, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -387,7 +381,8 @@ extern "C" int pvrl_gemm_bf16(const pvrl_gemm_t* d, void* stream_) {
       return f32 ? launch_gemm<PVRL_EPI_DGELU, float, false>(bn, ta, tb, a, stream)
                  : launch_gemm<PVRL_EPI_DGELU, __nv_bfloat16, false>(bn, ta, tb, a, stream);
     case PVRL_EPI_RESID:
-      return launch_gemm<PVRL_EPI_RESID, float, false>(bn, ta, tb, a, stream);
+      return d->add_pos != nullptr ? launch_gemm<EPI_RESID_POS, float, false>(bn, ta, tb, a, stream)
+                                   : launch_gemm<PVRL_EPI_RESID, float, false>(bn, ta, tb, a, stream);
     default:
       return d->trans ? launch_gemm<PVRL_EPI_ATOMIC, float, true>(bn, ta, tb, a, stream)
                       : launch_gemm<PVRL_EPI_ATOMIC, float, false>(bn, ta, tb, a, stream);

@@ -262,13 +262,6 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src,
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
-// hint: bring `bytes` (multiple of 16) starting at the 16-byte aligned global address into L2; no completion to wait for
-__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void prefetch_l2_line(const void* gptr) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(gptr) : "memory");
-}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
