@@ -26,11 +26,20 @@
 namespace pvrl {
 namespace {
 
-constexpr int TILE2_M = 256, TILE2_N = 256, STAGES2 = 6;
+constexpr int TILE2_M = 256, TILE2_N = 256;
 constexpr int B2_BYTES = (TILE2_N / 2) * BK * 2;             // this CTA's half of the B tile: 16 KB
 constexpr int STAGE2_BYTES = A_BYTES + B2_BYTES;             // 32 KB
-constexpr int PIPE2_BYTES = STAGES2 * STAGE2_BYTES;          // 192 KB
-constexpr int SMEM2_BYTES = PIPE2_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+// EW = epilogue warps per CTA: 8 (two 128-column groups per TMEM lane quarter, 6-stage ring; the default everywhere) or
+// 16 (four 64-column groups, 5-stage ring: an experiment for the bf16 GELU / gelu' epilogues, PVRL_GEMM2_EW=16, slower).
+template <int EW>
+struct Cfg2 {
+  static constexpr int STAGES = EW == 8 ? 6 : 5;
+  static constexpr int PIPE_BYTES = STAGES * STAGE2_BYTES;   // 192 / 160 KB
+  static constexpr int THREADS = 128 + 32 * EW;
+  static constexpr int GROUP_COLS = TILE2_N / (EW / 4);
+  static constexpr int SMEM_BYTES = PIPE_BYTES + EW * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(SMEM_BYTES <= 232448 && GROUP_COLS % 32 == 0, "tile configuration");
+};
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -81,9 +90,11 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
                : "memory");
 }
 
-template <int EPI, typename OutT, bool TN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+template <int EPI, typename OutT, bool TN, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
+  using C = Cfg2<EW>;
+  constexpr int STAGES2 = C::STAGES, PIPE2_BYTES = C::PIPE_BYTES, NUM_EPI_WARPS = EW;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
@@ -202,7 +213,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
     const int quarter = warp & 3;
     const int half = (warp - 4) >> 2;
-    constexpr int HALF_COLS = TILE2_N / 2;
+    constexpr int HALF_COLS = C::GROUP_COLS;
     uint8_t* stg = smem + PIPE2_BYTES + (warp - 4) * EPI_STAGE_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -230,11 +241,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // CTA pairs that can be co-resident (the persistent tile loop strides by the number of launched pairs, so launching
 // more pairs than fit at once would serialise them into waves).
 template <typename Kern>
-int max_active_pairs(Kern kern) {
+int max_active_pairs(Kern kern, int threads, int smem_bytes) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(num_sms(), 1, 1);
-  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = SMEM2_BYTES;
+  cfg.blockDim = dim3(threads, 1, 1);
+  cfg.dynamicSmemBytes = smem_bytes;
   cudaLaunchAttribute attr;
   attr.id = cudaLaunchAttributeClusterDimension;
   attr.val.clusterDim.x = 2, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
@@ -254,13 +265,14 @@ int g_pairs_override = [] {
 }();
 int g_last_max_pairs = 0;
 
-template <int EPI, typename OutT, bool TN>
-int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t stream) {
-  auto kern = gemm2_bf16_kernel<EPI, OutT, TN>;
+template <int EPI, typename OutT, bool TN, int EW>
+int launch_gemm2_ew(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t stream) {
+  auto kern = gemm2_bf16_kernel<EPI, OutT, TN, EW>;
+  constexpr int SMEM2_BYTES = Cfg2<EW>::SMEM_BYTES, NUM_THREADS = Cfg2<EW>::THREADS;
   static int pairs_max = 0;
   if (pairs_max == 0) {
     PVRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-    pairs_max = max_active_pairs(kern);
+    pairs_max = max_active_pairs(kern, NUM_THREADS, SMEM2_BYTES);
     g_last_max_pairs = pairs_max;
   }
   const int m_tiles = (a.M + TILE2_M - 1) / TILE2_M, n_tiles = (a.N + TILE2_N - 1) / TILE2_N;
@@ -269,6 +281,20 @@ int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a
   const int clusters = total < cap ? total : cap;
   PVRL_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(NUM_THREADS), SMEM2_BYTES, stream, ta, tb, a));
   return launched("gemm2_bf16_kernel");
+}
+
+template <int EPI, typename OutT, bool TN>
+int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t stream) {
+  constexpr bool HEAVY = (EPI == PVRL_EPI_GELU || EPI == PVRL_EPI_DGELU) && sizeof(OutT) == 2;
+  static const int heavy_ew = [] {
+    // development knob: 16 selects the four-group epilogue for the GELU GEMMs.  Measured (K = 768, N = 3072): 150 / 150 us
+    // against 141 / 130 us with two groups -- the epilogue is not what bounds these tiles on a CTA pair, and the fifth
+    // and sixth ring stages are worth more than the extra warps.
+    const char* e = getenv("PVRL_GEMM2_EW");
+    return e ? atoi(e) : 8;
+  }();
+  if (HEAVY && heavy_ew == 16) return launch_gemm2_ew<EPI, OutT, TN, HEAVY ? 16 : 8>(ta, tb, a, stream);
+  return launch_gemm2_ew<EPI, OutT, TN, 8>(ta, tb, a, stream);
 }
 
 }  // namespace

@@ -341,7 +341,15 @@ extern "C" int pvrl_gemm_bf16(const pvrl_gemm_t* d, void* stream_) {
     const char* e = getenv("PVRL_GEMM_2CTA");
     return e ? atoi(e) : 2;
   }();
-  if (mode_2cta == 1 || (mode_2cta == 2 && (d->trans == 1 || d->K >= 1536))) return gemm2_dispatch(d, stream);
+  // bf16 GELU / gelu' epilogues (fc1 forward, fc2 input gradient; K = 768, N = 3072): measured on the CTA-pair kernel
+  // 154 -> 141 us and 143 -> 131 us even with its two-group epilogue; PVRL_GEMM_HEAVY_2CTA=0 keeps them on 128 x 192 tiles.
+  static const bool heavy_2cta = [] {
+    const char* e = getenv("PVRL_GEMM_HEAVY_2CTA");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  const bool heavy = heavy_2cta && (d->epilogue == PVRL_EPI_GELU || d->epilogue == PVRL_EPI_DGELU) &&
+                     d->out_dtype == PVRL_BF16 && d->N % 256 == 0;
+  if (mode_2cta == 1 || (mode_2cta == 2 && (d->trans == 1 || d->K >= 1536 || heavy))) return gemm2_dispatch(d, stream);
   GemmArgs a = make_gemm_args(d);
 
   const int num_kb = (d->K + BK - 1) / BK;
