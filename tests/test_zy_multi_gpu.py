@@ -42,5 +42,7 @@ def test_exchange_variants_agree_and_exit_normally():
     # split-K fp32 atomics inside the dW GEMMs, i.e. the last bits of the gradients
     for other in (ce_unsplit, ce_one, nccl):
         assert other["losses"] == pytest.approx(ce["losses"], rel=2e-3), (ce, other)
-        for k in ("param_sum", "param_abs_sum", "param_sq_sum"):
-            assert other[k] == pytest.approx(ce[k], rel=1e-6), (k, ce, other)
+        # (AdamW's first steps move a parameter by ~lr * sign(g): a gradient whose last bits straddle zero flips 2 * lr)
+        for k in ("param_abs_sum", "param_sq_sum"):
+            assert other[k] == pytest.approx(ce[k], rel=1e-5), (k, ce, other)
+        assert other["param_sum"] == pytest.approx(ce["param_sum"], abs=1e-6 * ce["param_abs_sum"]), (ce, other)
