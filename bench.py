@@ -409,7 +409,9 @@ def run_b200(args):
     mode = H["mode"]
     exchange_desc = {"none": "single GPU: no exchange",
                      "ce": f"flat fp32 gradient buffer in symmetric memory, buckets of {trainer.blocks_per_bucket} encoder blocks "
-                           "averaged over NVLink by the copy engines under the backward (grad_exchange.py)",
+                           "averaged over NVLink by the copy engines under the backward (grad_exchange.py)"
+                           + ("; embeddings + block 0 exchanged under the optimizer pass over the rest"
+                              if getattr(trainer, "_split_update", False) and trainer.blocks_per_bucket else ""),
                      "nccl": "NCCL all-reduce of the flat fp32 gradient buffer"
                              + (f" in buckets of {trainer.blocks_per_bucket} blocks" if trainer.blocks_per_bucket else " after the backward")
                      }[trainer.exchange_kind]
