@@ -263,17 +263,24 @@ def gemm_roofline(handles, ms_step, D):
         gemm_events.append((e0, e1, 2.0 * kw["M"] * kw["N"] * kw["K"]))
         return r
     ops.gemm = timed_gemm
-    launches0 = ops.launch_count()
+    best = None
     try:
-        torch.cuda._sleep(int(0.12 * 1.9e9))
-        handles["trainer"]._eager(handles["frames"], handles["meta"])
-        D.barrier()
+        # two passes, the faster one counts: if the host falls behind the GPU anywhere in a pass (a slow first dispatch,
+        # a descheduled thread), the idle gap in front of a kernel lands inside its event pair and inflates the sum
+        for _ in range(2):
+            gemm_events.clear()
+            launches0 = ops.launch_count()
+            torch.cuda._sleep(int(0.25 * 1.9e9))
+            handles["trainer"]._eager(handles["frames"], handles["meta"])
+            D.barrier()
+            launches = ops.launch_count() - launches0
+            gemm_ms = sum(a.elapsed_time(b) for a, b, _ in gemm_events)
+            gemm_flops = sum(f for _, _, f in gemm_events)
+            if best is None or gemm_ms < best[1]:
+                best = (gemm_flops, gemm_ms, len(gemm_events), launches)
     finally:
         ops.gemm = real_gemm
-    launches = ops.launch_count() - launches0
-    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in gemm_events)
-    gemm_flops = sum(f for _, _, f in gemm_events)
-    return gemm_flops, gemm_ms, len(gemm_events), launches
+    return best
 
 
 def e2e_loop(D, handles, step, steps):
