@@ -486,7 +486,7 @@ def run_b200(args):
                          "launches": n_gemm, "gemm_share_of_step": round(gemm_ms / ms_step, 4),
                          "timed_in": ("CUDA events around every GEMM launch of one eager step (GPU parked on a spin kernel while the "
                                       "host enqueues it, so no host gap is billed to a kernel) run after the graph-replayed timed "
-                                      "region (events cannot time nodes inside a graph); share = that GEMM time / ms_per_step"),
+                                      "region (events cannot time nodes inside a graph), the faster of two such steps; share = that GEMM time / ms_per_step"),
                          "step_mfu": round(step_flops / (ms_step / 1e3) / 1e12 / peak, 4)},
         }
     if args.profile or args.no_extras:
