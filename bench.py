@@ -248,6 +248,29 @@ def parity_check(D, handles, depth, T, n_clips=4):
             "oracle": "oracle/timesformer_oracle.py fp32 on the host cores, same weights / inputs"}
 
 
+def parity_legs(D, handles, init_flat, depth, T):
+    """(parity at the seed-0 initial weights, parity at the weights the benchmark left behind).  The first is the reproducible
+    figure (same weights on every run, as tests/test_model_gpu.py::test_full_size_vs_oracle); the second says what a few
+    hundred optimizer steps on ONE synthetic batch do to it (the logits grow as the model memorises the batch)."""
+    opt = handles["trainer"].opt
+    flat = opt.flat_param
+    assert flat.numel() == init_flat.numel()
+    trained = flat.detach().clone()
+    with torch.no_grad():
+        flat.copy_(init_flat)
+    at_init = parity_check(D, handles, depth, T)
+    at_init["weights"] = "seed-0 initialisation of the benched model"
+    with torch.no_grad():
+        flat.copy_(trained)
+    after = parity_check(D, handles, depth, T)
+    keep = ("max_abs_logit_err", "mean_abs_logit_err", "argmax_agree", "n", "frac_within_rtol1e-3_atol5e-3", "logit_abs_max",
+            "min_ref_top1_margin")
+    after = {k: after[k] for k in keep}
+    after["weights"] = f"after the {int(opt._step_dev.item())} optimizer steps this run took on its one synthetic batch"
+    handles["inner"].engine().invalidate_weights()
+    return at_init, after
+
+
 def gemm_roofline(handles, ms_step, D):
     """CUDA events around every GEMM launch of ONE eager step (events cannot time nodes inside a graph).  The eager step
     is host-bound, so the GPU is first parked on a spin kernel long enough for the host to enqueue the whole step: events
@@ -414,6 +437,7 @@ def run_b200(args):
                    input_u8=args.input_u8)
     trainer, frames, meta = H["trainer"], H["frames"], H["meta"]
     mode = H["mode"]
+    init_flat = trainer.opt.flat_param.detach().clone()     # the seed-0 initialisation: where `parity` is evaluated
     exchange_desc = {"none": "single GPU: no exchange",
                      "ce": f"flat fp32 gradient buffer in symmetric memory, buckets of {trainer.blocks_per_bucket} encoder blocks "
                            "averaged over NVLink by the copy engines under the backward (grad_exchange.py)"
@@ -498,7 +522,7 @@ def run_b200(args):
 
     # ---- parity of the benched model vs the oracle (rank 0 computes; every rank keeps its model alive meanwhile)
     if rank == 0:
-        out["parity"] = parity_check(D, H, args.depth, T)
+        out["parity"], out["parity_after_training"] = parity_legs(D, H, init_flat, args.depth, T)
     D.barrier()
     del trainer, step
     H.clear()
@@ -508,7 +532,7 @@ def run_b200(args):
     other = "bf16x3" if args.precision == "bf16" else "bf16"
     leg, h2 = short_leg(D, T, args.depth, other, Bv, steps=max(3, min(10, args.steps)), warmup=3)
     if rank == 0:
-        leg["parity"] = parity_check(D, h2, args.depth, T)
+        leg["parity"], leg["parity_after_training"] = parity_legs(D, h2, init_flat, args.depth, T)
         out["value_parity_mode" if other == "bf16x3" else "value_throughput_mode"] = leg
     D.barrier()
     h2.clear()
