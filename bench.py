@@ -446,6 +446,8 @@ def run_b200(args):
                      "nccl": "NCCL all-reduce of the flat fp32 gradient buffer"
                              + (f" in buckets of {trainer.blocks_per_bucket} blocks" if trainer.blocks_per_bucket else " after the backward")
                      }[trainer.exchange_kind]
+    if getattr(trainer, "exchange_note", None):
+        exchange_desc += f" [{trainer.exchange_note}]"
 
     def step():
         return trainer(frames, meta)

@@ -55,10 +55,17 @@ class PretrainStep:
         self.exchange = None
         self.exchange_kind = os.environ.get("PVRL_GRAD_EXCHANGE", "ce") if self.world > 1 else "none"
         grad_buffer = None
+        self.exchange_note = None
         if self.exchange_kind == "ce" and optimizer is None:
             from .grad_exchange import PeerGradExchange
-            self.exchange = PeerGradExchange(sum(p.numel() for p in self.params), process_group)
-            grad_buffer = self.exchange.buffer
+            try:
+                self.exchange = PeerGradExchange(sum(p.numel() for p in self.params), process_group)
+                grad_buffer = self.exchange.buffer
+            except Exception as e:      # no peer access / no symmetric-memory support on this box: NCCL does the same mean
+                if os.environ.get("PVRL_GRAD_EXCHANGE") == "ce":
+                    raise               # asked for explicitly: fail loudly
+                self.exchange, self.exchange_kind = None, "nccl"
+                self.exchange_note = f"copy-engine exchange unavailable ({type(e).__name__}: {e}); NCCL all-reduce instead"[:300]
         elif self.exchange_kind == "ce":
             self.exchange_kind = "nccl"           # a caller-built optimizer owns its gradient buffer
         # Parameters, gradients and AdamW state in flat fp32 buffers (`p.data` / `p.grad` become views): the engine's
