@@ -124,6 +124,15 @@ def construct_optimizer(model, cfg):
 
 
 # ------------------------------------------------------------------------------------------------ flat optimizer
+def split_runs(runs, off):
+    """[(group, start, end)] element runs of the flat buffers -> (the parts at or above `off`, the parts below it): together
+    they cover every run exactly once (FlatOptimizer.step(split=...): the upper part is updated while the gradient exchange of
+    the lower part is still in flight)."""
+    above = [(g, max(s, off), e) for g, s, e in runs if e > off]
+    below = [(g, s, min(e, off)) for g, s, e in runs if s < off]
+    return above, below
+
+
 class FlatOptimizer:
     """torch.optim-shaped (param_groups / step / zero_grad / state_dict) optimizer over flat buffers.
 
@@ -264,13 +273,12 @@ class FlatOptimizer:
                 self._launch(gi, g, s, e, zero_grad)
             return loss
         off, hook = split
-        for gi, g, s, e in runs:
-            if e > off:
-                self._launch(gi, g, max(s, off), e, zero_grad)
+        above, below = split_runs([(gi, s, e) for gi, _, s, e in runs], off)
+        for gi, s, e in above:
+            self._launch(gi, self.param_groups[gi], s, e, zero_grad)
         hook()
-        for gi, g, s, e in runs:
-            if s < off:
-                self._launch(gi, g, s, min(e, off), zero_grad)
+        for gi, s, e in below:
+            self._launch(gi, self.param_groups[gi], s, e, zero_grad)
         return loss
 
     def _launch(self, gi, g, s, e, zero_grad):

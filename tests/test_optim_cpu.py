@@ -152,3 +152,32 @@ def test_mvit_load_pretrained_converts_image_checkpoint(tmp_path, gold_dir):
     for k, v in expect.items():
         torch.testing.assert_close(got[k], v, rtol=0, atol=1e-6, msg=k)
     assert [k for k, _ in m.model.pretrained_skipped] == ["head.projection.weight"]
+
+
+def test_split_runs_tile_the_flat_buffer():
+    """FlatOptimizer.step(split=(offset, hook)) updates [offset, end) before the hook and [0, offset) after it: the two launch
+    lists cover every element of every run exactly once, on the right side of the offset, group by group (the trainer hides
+    the last gradient exchange -- embeddings + block 0, the front of the buffer -- under the first list)."""
+    import random
+    from procedurevrl_b200.lib.models.optimizer import split_runs
+    rnd = random.Random(0)
+    for _ in range(200):
+        cuts = sorted(rnd.sample(range(1, 400), rnd.randint(1, 6)))
+        runs, start = [], 0
+        for gi, c in enumerate(cuts):                    # contiguous groups, some with a hole (a parameter without gradient)
+            if rnd.random() < 0.3 and c - start > 4:
+                hole = rnd.randint(start + 1, c - 2)
+                runs += [(gi, start, hole), (gi, hole + 1, c)]
+            else:
+                runs.append((gi, start, c))
+            start = c
+        off = rnd.choice([0, 1, cuts[0], cuts[-1], cuts[-1] + 5, rnd.randint(0, 400)])
+        above, below = split_runs(runs, off)
+        assert all(s >= off and e > s for _, s, e in above) and all(e <= off and e > s for _, s, e in below)
+        cover = {}
+        for g, s, e in above + below:
+            for i in range(s, e):
+                assert i not in cover
+                cover[i] = g
+        want = {i: g for g, s, e in runs for i in range(s, e)}
+        assert cover == want
