@@ -90,6 +90,26 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
                : "memory");
 }
 
+// warp-converged forms (the whole warp executes the call with warp-uniform operands, one elected lane issues)
+__device__ __forceinline__ void umma_bf16_2sm_e(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_e(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(bar), "h"(mask)
+      : "memory");
+}
+
 template <int EPI, typename OutT, bool TN, int EW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
@@ -174,8 +194,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread of the leader CTA)
-    if (lane == 0 && rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (warp 1 of the leader CTA, converged;
+    // one elected lane issues)
+    if (rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(TILE2_M, TILE2_N, TN ? 1 : 0, TN ? 1 : 0);
       constexpr uint32_t kstep = TN ? 16u * 128u : 32u;
       constexpr uint32_t lbo = TN ? CHUNK_BYTES : 16u;
@@ -200,12 +221,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t adesc = make_smem_desc(sA + k * kstep, lbo, 1024);
             const uint64_t bdesc = make_smem_desc(sB + k * kstep, lbo, 1024);
-            umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_bf16_2sm_e(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit_2sm(empty_bar(stage), 0b11);   // both CTAs' stage s is free once these MMAs have read it
+          umma_commit_2sm_e(empty_bar(stage), 0b11);   // both CTAs' stage s is free once these MMAs have read it
           if (++stage == STAGES2) stage = 0, phase ^= 1u;
         }
-        umma_commit_2sm(tfull_bar(acc), 0b11);       // accumulator complete -> both CTAs' epilogue warps
+        umma_commit_2sm_e(tfull_bar(acc), 0b11);       // accumulator complete -> both CTAs' epilogue warps
         if (++acc == 2) acc = 0, acc_phase ^= 1u;
       }
     }

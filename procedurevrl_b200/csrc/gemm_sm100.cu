@@ -113,8 +113,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer: the whole warp runs the loop
+    // converged and one elected lane issues (pvrl_ptx.cuh: a single-lane branch routes every descriptor through R2UR
+    // moves and an ELECT / BRA.U.ANY loop per instruction -- ~100 cycles per tcgen05.mma against the 96 / 128 it executes)
+    {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, TN ? 1 : 0, TN ? 1 : 0);
       // descriptor advance per UMMA_K = 16: K-major +32 B inside the swizzle atom, MN-major +16 k-rows
       constexpr uint32_t kstep = TN ? 16u * 128u : 32u;
@@ -140,12 +142,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t adesc = make_smem_desc(sA + k * kstep, lbo, 1024);
             const uint64_t bdesc = make_smem_desc(sB + k * kstep, lbo, 1024);
-            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_bf16_e(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
+          umma_commit_e(empty_bar(stage));  // smem slot reusable once these MMAs have read it
           if (++stage == STAGES) stage = 0, phase ^= 1u;
         }
-        umma_commit(tfull_bar(acc));      // accumulator complete -> epilogue
+        umma_commit_e(tfull_bar(acc));      // accumulator complete -> epilogue
         if (++acc == 2) acc = 0, acc_phase ^= 1u;
       }
     }
